@@ -1,0 +1,123 @@
+"""The backend entry points — mirror of raytracing_cpu::{render, render_single_pixel,
+CpuBackendSettings} (crates/raytracing-cpu/src/lib.rs:446-457, 645-858, 860-931) for `--backend cuda`.
+
+Every call goes through libraytracing_cuda.so (include/rtcuda.h). There is no CPU path here: when the
+library is missing `_ffi.load_library()` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional
+
+import numpy as np
+
+from . import _ffi
+from .renderer import AovFlags, RaytracerSettings, RenderOutput, SinglePixelOutput
+from .scene import Scene
+
+
+@dataclass
+class CudaBackendSettings:
+    """The analogue of CpuBackendSettings{num_threads} (lib.rs:446-457)."""
+    device_id: int = 0
+    max_paths_in_flight: int = 0       # 0 => backend default
+    tile_rank: int = 0                 # this context renders 64x64 tiles i with i % tile_world == tile_rank
+    tile_world: int = 1
+    collect_stats: bool = False
+
+    def to_c(self) -> _ffi.BackendSettings:
+        b = _ffi.BackendSettings()
+        b.device_id, b.max_paths_in_flight = self.device_id, self.max_paths_in_flight
+        b.tile_rank, b.tile_world, b.collect_stats = self.tile_rank, self.tile_world, int(self.collect_stats)
+        return b
+
+
+class CudaRenderer:
+    """A context + an uploaded scene (device BVH, textures). `render()` may be called repeatedly;
+    the one-shot `render()` function below is the reference-shaped call."""
+
+    def __init__(self, scene: Scene, backend_settings: Optional[CudaBackendSettings] = None):
+        self.lib = _ffi.load_library()
+        self.backend_settings = backend_settings or CudaBackendSettings()
+        self.scene = scene
+        self._ctx = C.c_void_p()
+        self._scene = C.c_void_p()
+        bs = self.backend_settings.to_c()
+        _ffi.check(self.lib, self.lib.rtcuda_init(C.byref(bs), C.byref(self._ctx)), "rtcuda_init")
+        holder = scene.to_desc()
+        try:
+            _ffi.check(self.lib, self.lib.rtcuda_scene_upload(self._ctx, C.byref(holder.desc), C.byref(self._scene)),
+                       "rtcuda_scene_upload")
+        except Exception:
+            self.close()
+            raise
+        self.width, self.height = scene.camera.raster_width, scene.camera.raster_height
+
+    def close(self) -> None:
+        if getattr(self, "_scene", None) is not None and self._scene:
+            self.lib.rtcuda_scene_release(self._scene)
+            self._scene = C.c_void_p()
+        if getattr(self, "_ctx", None) is not None and self._ctx:
+            self.lib.rtcuda_shutdown(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def render(self, settings: RaytracerSettings) -> RenderOutput:
+        """raytracing_cpu::render: host planes, row-major [H,W,C]."""
+        out = RenderOutput.allocate(self.width, self.height, AovFlags(settings.outputs))
+        s, o = settings.to_c(), out.to_c()
+        _ffi.check(self.lib, self.lib.rtcuda_render(self._scene, C.byref(s), C.byref(o)), "rtcuda_render")
+        return out
+
+    def render_into(self, settings: RaytracerSettings, out: RenderOutput) -> None:
+        s, o = settings.to_c(), out.to_c()
+        _ffi.check(self.lib, self.lib.rtcuda_render(self._scene, C.byref(s), C.byref(o)), "rtcuda_render")
+
+    def render_device(self, settings: RaytracerSettings, planes: dict) -> None:
+        """Same render with DEVICE plane pointers ({'beauty': ptr, ...}); nothing is copied to the host."""
+        o = _ffi.Outputs()
+        o.width, o.height = self.width, self.height
+        for k, v in planes.items():
+            setattr(o, k, v)
+        s = settings.to_c()
+        _ffi.check(self.lib, self.lib.rtcuda_render_device(self._scene, C.byref(s), C.byref(o)), "rtcuda_render_device")
+
+    def render_pixel(self, settings: RaytracerSettings, x: int, y: int, sample_lo: int, sample_hi: int) -> List[SinglePixelOutput]:
+        n = max(0, sample_hi - sample_lo)
+        buf = (_ffi.PixelOutput * max(1, n))()
+        s = settings.to_c()
+        _ffi.check(self.lib, self.lib.rtcuda_render_pixel(self._scene, C.byref(s), x, y, sample_lo, sample_hi, buf),
+                   "rtcuda_render_pixel")
+        return [SinglePixelOutput(b.sample_index, bool(b.hit), tuple(b.uv), tuple(b.normal), tuple(b.radiance)) for b in buf[:n]]
+
+    def stats(self) -> dict:
+        st = _ffi.Stats()
+        _ffi.check(self.lib, self.lib.rtcuda_get_stats(self._scene, C.byref(st)), "rtcuda_get_stats")
+        return {name: getattr(st, name) for name, _ in _ffi.Stats._fields_}
+
+
+def render(scene: Scene, raytracer_settings: RaytracerSettings,
+           backend_settings: Optional[CudaBackendSettings] = None) -> RenderOutput:
+    """pub fn render(&Scene, &RaytracerSettings, BackendSettings) -> RenderOutput (lib.rs:645-649)."""
+    with CudaRenderer(scene, backend_settings) as r:
+        return r.render(raytracer_settings)
+
+
+def render_single_pixel(scene: Scene, raytracer_settings: RaytracerSettings, x: int, y: int,
+                        sample_index: Optional[int] = None) -> SinglePixelOutput:
+    """pub fn render_single_pixel(.., x, y, sample_index: Option<u32>) (lib.rs:860-866)."""
+    i = 0 if sample_index is None else sample_index
+    with CudaRenderer(scene, backend_settings=None) as r:
+        return r.render_pixel(raytracer_settings, x, y, i, i + 1)[0]

@@ -1,0 +1,840 @@
+// api.cu — the C ABI of libraytracing_cuda.so (include/rtcuda.h): context, scene upload (device BVH +
+// mip pyramids), the wavefront render loop, single-pixel diagnostics, statistics.
+//
+// Replaces raytracing_cpu::render / render_single_pixel (crates/raytracing-cpu/src/lib.rs:645-931),
+// prepare_cpu_acceleration_structures (scene.rs:14-73) and CpuRaytracingContext::new (lib.rs:81-105).
+// Error handling: status codes + rtcuda_last_error() instead of the exit() of the OptiX precedent
+// (crates/raytracing-optix/csrc/host/util.hpp:7-27).
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/rtcuda.h"
+#include "kernels.cuh"
+
+using namespace rt;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+struct RtError {
+    rtcuda_status status;
+    std::string msg;
+};
+
+#define CK(call)                                                                                            \
+    do {                                                                                                    \
+        cudaError_t e_ = (call);                                                                            \
+        if (e_ != cudaSuccess) {                                                                            \
+            rtcuda_status st_ = e_ == cudaErrorMemoryAllocation ? RTCUDA_ERR_OUT_OF_MEMORY : RTCUDA_ERR_CUDA; \
+            throw RtError{st_, std::string(#call) + ": " + cudaGetErrorString(e_)};                           \
+        }                                                                                                   \
+    } while (0)
+
+#define REQUIRE(cond, msg)                                            \
+    do {                                                              \
+        if (!(cond)) throw RtError{RTCUDA_ERR_INVALID_ARGUMENT, msg}; \
+    } while (0)
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    void alloc(size_t count) {
+        release();
+        n = count;
+        CK(cudaMalloc((void**)&p, std::max<size_t>(count, 1) * sizeof(T)));
+    }
+    void ensure(size_t count) {
+        if (count > n || !p) alloc(count);
+    }
+    void upload(const T* src, size_t count, cudaStream_t st) {
+        alloc(count);
+        if (count) CK(cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, st));
+    }
+};
+
+M4 to_m4(const rtcuda_mat4& m) {
+    M4 r;
+    std::memcpy(r.m, m.m, sizeof r.m);
+    return r;
+}
+
+uint32_t next_pow2(uint32_t v) {
+    uint32_t p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+bool is_pow2(uint32_t v) { return v && !(v & (v - 1)); }
+uint32_t bytes_per_sample(uint32_t fmt) { return fmt == RTCUDA_IMAGE_U8 ? 1 : (fmt == RTCUDA_IMAGE_U16 ? 2 : 4); }
+
+}  // namespace
+
+struct rtcuda_ctx {
+    int device = 0;
+    rtcuda_backend_settings bs{};
+    cudaStream_t stream = nullptr;
+};
+
+struct rtcuda_scene {
+    rtcuda_ctx* ctx = nullptr;
+    SceneD sc{};
+    uint32_t width = 0, height = 0;
+    // scene data
+    DevBuf<float> vertices, normals, uvs;
+    DevBuf<uint32_t> tris;
+    DevBuf<uint8_t> image_bytes;
+    DevBuf<Instance> instances;
+    DevBuf<ShapeD> shapes;
+    DevBuf<LightD> lights;
+    DevBuf<MaterialD> materials;
+    DevBuf<TextureD> textures;
+    DevBuf<ImageD> images;
+    DevBuf<MipChain> mips;
+    DevBuf<Node8> nodes;
+    DevBuf<Prim> prims;
+    std::vector<rtcuda_light> host_lights;
+    // render state
+    DevBuf<uint32_t> pixel_list;
+    uint32_t n_my_pixels = 0;
+    DevBuf<float4> accum;
+    DevBuf<uint64_t> rng_state;
+    DevBuf<float4> weight, radiance, ray_o[2], ray_d[2], hits, shadow_point, shadow_origin, shadow_contrib;
+    DevBuf<uint32_t> shadow_queue, counters;
+    DevBuf<unsigned long long> stats_dev;
+    DevBuf<PixelOut> pixel_out;
+    // host-API staging planes
+    DevBuf<float> d_beauty, d_normals, d_albedo, d_uv, d_mip, d_depth;
+    DevBuf<uint32_t> d_ids;
+    rtcuda_stats stats{};
+    LaunchCounter lc;
+};
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------
+// scene upload
+// ---------------------------------------------------------------------------------------------------
+void validate_desc(const rtcuda_scene_desc* d) {
+    REQUIRE(d->abi_version == RTCUDA_ABI_VERSION, "scene_desc.abi_version mismatch");
+    REQUIRE(d->camera.raster_width > 0 && d->camera.raster_height > 0, "empty raster");
+    REQUIRE(d->camera.raster_width < 65536 && d->camera.raster_height < 65536, "raster larger than 65535");
+    REQUIRE(d->camera.kind <= RTCUDA_CAMERA_THIN_LENS, "unknown camera kind");
+    for (uint32_t i = 0; i < d->shape_count; i++) {
+        const rtcuda_shape& s = d->shapes[i];
+        REQUIRE(s.kind <= RTCUDA_SHAPE_SPHERE, "unknown shape kind");
+        REQUIRE(s.material < d->material_count, "shape.material out of range");
+        REQUIRE(s.area_light == RTCUDA_NONE || s.area_light < d->light_count, "shape.area_light out of range");
+        if (s.kind == RTCUDA_SHAPE_TRIANGLE_MESH) {
+            REQUIRE((uint64_t)s.vertex_offset + s.vertex_count <= d->vertex_count, "shape vertices out of range");
+            REQUIRE((uint64_t)s.tri_offset + s.tri_count <= d->tri_count, "shape tris out of range");
+            REQUIRE(s.normal_offset == RTCUDA_NONE || (uint64_t)s.normal_offset + s.vertex_count <= d->normal_count, "shape normals out of range");
+            REQUIRE(s.uv_offset == RTCUDA_NONE || (uint64_t)s.uv_offset + s.vertex_count <= d->uv_count, "shape uvs out of range");
+            for (uint64_t t = 0; t < (uint64_t)s.tri_count * 3; t++)
+                REQUIRE(d->tris[(uint64_t)s.tri_offset * 3 + t] < s.vertex_count, "triangle index out of range");
+        }
+    }
+    for (uint32_t i = 0; i < d->instance_count; i++) REQUIRE(d->instances[i].shape < d->shape_count, "instance.shape out of range");
+    for (uint32_t i = 0; i < d->light_count; i++) {
+        const rtcuda_light& l = d->lights[i];
+        REQUIRE(l.kind <= RTCUDA_LIGHT_DIFFUSE_AREA, "unknown light kind");
+        if (l.kind == RTCUDA_LIGHT_DIFFUSE_AREA) {
+            REQUIRE(l.shape < d->shape_count, "area light shape out of range");
+            // lights.rs:59: sampling a sphere emitter is todo!() in the reference
+            if (d->shapes[l.shape].kind != RTCUDA_SHAPE_TRIANGLE_MESH)
+                throw RtError{RTCUDA_ERR_UNSUPPORTED, "DiffuseAreaLight over a sphere is not supported (todo!() in the reference, lights.rs:59)"};
+            REQUIRE(d->shapes[l.shape].tri_count > 0, "area light mesh has no triangles");
+        }
+    }
+    auto tex_ok = [&](uint32_t t) { return t < d->texture_count; };
+    for (uint32_t i = 0; i < d->material_count; i++) {
+        const rtcuda_material& m = d->materials[i];
+        REQUIRE(m.kind <= RTCUDA_MATERIAL_COATED_DIFFUSE, "unknown material kind");
+        switch (m.kind) {
+            case RTCUDA_MATERIAL_DIFFUSE: REQUIRE(tex_ok(m.albedo), "material texture out of range"); break;
+            case RTCUDA_MATERIAL_SMOOTH_DIELECTRIC: REQUIRE(tex_ok(m.eta), "material texture out of range"); break;
+            case RTCUDA_MATERIAL_SMOOTH_CONDUCTOR: REQUIRE(tex_ok(m.eta) && tex_ok(m.kappa), "material texture out of range"); break;
+            case RTCUDA_MATERIAL_ROUGH_DIELECTRIC: REQUIRE(tex_ok(m.eta) && tex_ok(m.roughness), "material texture out of range"); break;
+            case RTCUDA_MATERIAL_ROUGH_CONDUCTOR: REQUIRE(tex_ok(m.eta) && tex_ok(m.kappa) && tex_ok(m.roughness), "material texture out of range"); break;
+            default:
+                REQUIRE(tex_ok(m.albedo) && tex_ok(m.eta) && tex_ok(m.thickness) && tex_ok(m.coat_albedo) &&
+                            (m.roughness == RTCUDA_NONE || tex_ok(m.roughness)), "material texture out of range");
+        }
+    }
+    for (uint32_t i = 0; i < d->texture_count; i++) {
+        const rtcuda_texture& t = d->textures[i];
+        REQUIRE(t.kind <= RTCUDA_TEXTURE_MIX, "unknown texture kind");
+        if (t.kind == RTCUDA_TEXTURE_IMAGE) REQUIRE(t.image < d->image_count && t.filter <= 2 && t.wrap <= 2, "image texture out of range");
+        // Scale / Mix may only refer to earlier textures: bounded nesting, no cycles
+        if (t.kind == RTCUDA_TEXTURE_SCALE) REQUIRE(tex_ok(t.a) && tex_ok(t.b), "scale texture operand out of range");
+        if (t.kind == RTCUDA_TEXTURE_MIX) REQUIRE(tex_ok(t.a) && tex_ok(t.b) && tex_ok(t.c), "mix texture operand out of range");
+    }
+    for (uint32_t i = 0; i < d->image_count; i++) {
+        const rtcuda_image& im = d->images[i];
+        REQUIRE(im.channels >= 1 && im.channels <= 4 && im.format <= RTCUDA_IMAGE_F32 && im.width && im.height, "bad image header");
+        REQUIRE(im.byte_offset + (uint64_t)im.width * im.height * im.channels * bytes_per_sample(im.format) <= d->image_byte_count, "image bytes out of range");
+    }
+    REQUIRE(d->environment_light_texture == RTCUDA_NONE || tex_ok(d->environment_light_texture), "environment texture out of range");
+}
+
+// texture nesting depth (Scale / Mix): the device evaluator is bounded at TEXTURE_NEST
+uint32_t texture_depth(const rtcuda_scene_desc* d, uint32_t t, uint32_t guard) {
+    if (guard > 16) throw RtError{RTCUDA_ERR_UNSUPPORTED, "texture graph too deep or cyclic"};
+    const rtcuda_texture& tx = d->textures[t];
+    if (tx.kind == RTCUDA_TEXTURE_SCALE) return 1 + std::max(texture_depth(d, tx.a, guard + 1), texture_depth(d, tx.b, guard + 1));
+    if (tx.kind == RTCUDA_TEXTURE_MIX)
+        return 1 + std::max({texture_depth(d, tx.a, guard + 1), texture_depth(d, tx.b, guard + 1), texture_depth(d, tx.c, guard + 1)});
+    return 0;
+}
+
+void build_mips(rtcuda_scene* s, const rtcuda_scene_desc* d, std::vector<ImageD>& images, std::vector<TextureD>& textures,
+                std::vector<MipChain>& chains) {
+    cudaStream_t st = s->ctx->stream;
+    // which images need a pyramid (CpuTextures::new, texture.rs:214-233)
+    std::vector<int> chain_of(d->image_count, -1);
+    uint64_t total_bytes = d->image_byte_count;
+    struct Plan { uint32_t image; uint32_t size; uint64_t offset; };
+    std::vector<Plan> plans;
+    for (uint32_t t = 0; t < d->texture_count; t++) {
+        const rtcuda_texture& tx = d->textures[t];
+        if (tx.kind != RTCUDA_TEXTURE_IMAGE || tx.filter != RTCUDA_FILTER_TRILINEAR) continue;
+        if (chain_of[tx.image] < 0) {
+            const rtcuda_image& im = d->images[tx.image];
+            uint32_t size = im.width;
+            if (!(is_pow2(im.width) && is_pow2(im.height)) || im.width != im.height) size = std::max(next_pow2(im.width), next_pow2(im.height));
+            total_bytes = (total_bytes + 15) & ~15ull;
+            chain_of[tx.image] = (int)plans.size();
+            plans.push_back({tx.image, size, total_bytes});
+            for (uint32_t lv = size; lv >= 1; lv /= 2) {
+                total_bytes += ((uint64_t)lv * lv * im.channels * bytes_per_sample(im.format) + 15) & ~15ull;
+                if (lv == 1) break;
+            }
+        }
+        textures[t].mip_base = (uint32_t)chain_of[tx.image];
+    }
+    s->image_bytes.alloc(total_bytes);
+    if (d->image_byte_count) CK(cudaMemcpyAsync(s->image_bytes.p, d->image_bytes, d->image_byte_count, cudaMemcpyHostToDevice, st));
+    for (const Plan& pl : plans) {
+        const rtcuda_image& im = d->images[pl.image];
+        const uint32_t ch = im.channels, fmt = im.format, bps = bytes_per_sample(fmt);
+        DevBuf<float> cur, tmp, nxt;
+        uint32_t w = im.width, h = im.height;
+        cur.alloc((size_t)w * h * ch);
+        launch_to_f32(st, s->image_bytes.p + im.byte_offset, fmt, cur.p, w * h * ch, s->lc);
+        if (w != pl.size || h != pl.size) {  // resize to the square power of two (vertical pass, then horizontal)
+            tmp.alloc((size_t)w * pl.size * ch);
+            nxt.alloc((size_t)pl.size * pl.size * ch);
+            launch_resize(st, cur.p, tmp.p, w, h, ch, pl.size, 0, s->lc);
+            launch_resize(st, tmp.p, nxt.p, w, pl.size, ch, pl.size, 1, s->lc);
+            CK(cudaStreamSynchronize(st));
+            std::swap(cur.p, nxt.p);
+            std::swap(cur.n, nxt.n);
+            w = h = pl.size;
+        }
+        MipChain mc;
+        mc.first_image = (uint32_t)images.size();
+        mc.level_count = 0;
+        uint64_t off = pl.offset;
+        for (;;) {
+            ImageD lv;
+            lv.width = w; lv.height = h; lv.channels = ch; lv.format = fmt; lv.byte_offset = off;
+            launch_cast(st, cur.p, fmt, s->image_bytes.p + off, w * h * ch, s->lc);
+            images.push_back(lv);
+            mc.level_count++;
+            off += ((uint64_t)w * h * ch * bps + 15) & ~15ull;
+            if (!(w > 1 && h > 1)) break;
+            const uint32_t nw = w / 2, nh = h / 2;
+            tmp.alloc((size_t)w * nh * ch);
+            nxt.alloc((size_t)nw * nh * ch);
+            launch_resize(st, cur.p, tmp.p, w, h, ch, nh, 0, s->lc);
+            launch_resize(st, tmp.p, nxt.p, w, nh, ch, nw, 1, s->lc);
+            CK(cudaStreamSynchronize(st));
+            std::swap(cur.p, nxt.p);
+            std::swap(cur.n, nxt.n);
+            w = nw;
+            h = nh;
+        }
+        chains.push_back(mc);
+    }
+    CK(cudaStreamSynchronize(st));
+}
+
+void build_bvh(rtcuda_scene* s, const std::vector<Instance>& instances, uint32_t n_prims) {
+    cudaStream_t st = s->ctx->stream;
+    s->sc.prim_count = n_prims;
+    s->sc.node_count = 0;
+    if (n_prims == 0) {
+        s->nodes.alloc(1);
+        s->prims.alloc(1);
+        s->sc.scene_center[0] = s->sc.scene_center[1] = s->sc.scene_center[2] = 0.0f;
+        s->sc.scene_radius = 0.0f;
+        return;
+    }
+    const uint32_t n = n_prims;
+    DevBuf<Prim> prims_unsorted;
+    DevBuf<float4> aabb_lo, aabb_hi, node_lo, node_hi;
+    DevBuf<uint32_t> bounds_keys, vals, vals_sorted, left, right, parent, range_lo, range_hi, visit, counters;
+    DevBuf<uint64_t> keys, keys_sorted;
+    DevBuf<WorkItem> queue_a, queue_b;
+    DevBuf<uint8_t> sort_temp;
+    prims_unsorted.alloc(n); aabb_lo.alloc(n); aabb_hi.alloc(n);
+    node_lo.alloc(2 * (size_t)n); node_hi.alloc(2 * (size_t)n);
+    bounds_keys.alloc(6); vals.alloc(n); vals_sorted.alloc(n); keys.alloc(n); keys_sorted.alloc(n);
+    left.alloc(n); right.alloc(n); parent.alloc(2 * (size_t)n); range_lo.alloc(n); range_hi.alloc(n); visit.alloc(n);
+    counters.alloc(4);
+    queue_a.alloc(n); queue_b.alloc(n);
+    s->nodes.alloc(n);   // every wide node consumes at least one binary internal node
+    s->prims.alloc(n);
+    const size_t temp_bytes = sort_temp_bytes(n);
+    sort_temp.alloc(temp_bytes);
+
+    const uint32_t init_keys[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
+    CK(cudaMemcpyAsync(bounds_keys.p, init_keys, sizeof init_keys, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(visit.p, 0, (size_t)n * 4, st));
+
+    BuildCtx b{};
+    b.instances = s->instances.p; b.instance_count = (uint32_t)instances.size();
+    b.vertices = s->vertices.p; b.tris = s->tris.p; b.n = n;
+    b.prims_unsorted = prims_unsorted.p; b.aabb_lo = aabb_lo.p; b.aabb_hi = aabb_hi.p; b.bounds_keys = bounds_keys.p;
+    b.keys = keys.p; b.vals = vals.p; b.keys_sorted = keys_sorted.p; b.vals_sorted = vals_sorted.p;
+    b.left = left.p; b.right = right.p; b.parent = parent.p; b.range_lo = range_lo.p; b.range_hi = range_hi.p;
+    b.node_lo = node_lo.p; b.node_hi = node_hi.p; b.visit = visit.p;
+    b.nodes = s->nodes.p; b.prims = s->prims.p; b.counters = counters.p;
+
+    launch_prim_setup(st, b, s->lc);
+    launch_morton(st, b, s->lc);
+    launch_sort(st, sort_temp.p, temp_bytes, keys.p, keys_sorted.p, vals.p, vals_sorted.p, n, s->lc);
+    launch_karras(st, b, s->lc);
+    launch_refit(st, b, s->lc);
+
+    // collapse, one launch per wide level
+    WorkItem root{0u, 0u};
+    CK(cudaMemcpyAsync(queue_a.p, &root, sizeof root, cudaMemcpyHostToDevice, st));
+    uint32_t h_counters[4] = {0u, 1u, 0u, 0u};  // next-level size, wide nodes (root allocated), packed prims
+    CK(cudaMemcpyAsync(counters.p, h_counters, sizeof h_counters, cudaMemcpyHostToDevice, st));
+    uint32_t n_items = 1;
+    WorkItem* qin = queue_a.p;
+    WorkItem* qout = queue_b.p;
+    while (n_items) {
+        b.queue_in = qin;
+        b.queue_out = qout;
+        launch_collapse(st, b, n_items, s->lc);
+        CK(cudaMemcpyAsync(h_counters, counters.p, sizeof h_counters, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        n_items = h_counters[0];
+        const uint32_t zero = 0;
+        CK(cudaMemcpyAsync(counters.p, &zero, 4, cudaMemcpyHostToDevice, st));
+        std::swap(qin, qout);
+    }
+    if (h_counters[2] != n) throw RtError{RTCUDA_ERR_CUDA, "BVH build lost primitives"};
+    s->sc.node_count = h_counters[1];
+    s->stats.bvh_node_count = h_counters[1];
+    s->stats.bvh_prim_count = n;
+
+    // CpuRaytracingContext::new (lib.rs:81-105): centre / radius of the root bounds (aabb.rs:27-33); a
+    // single-primitive scene has a leaf root with infinite bounds in the reference (bvh2.rs:448-452)
+    uint32_t hk[6];
+    CK(cudaMemcpyAsync(hk, bounds_keys.p, sizeof hk, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    V3 mn = mk3(key_float(hk[0]), key_float(hk[1]), key_float(hk[2])), mx = mk3(key_float(hk[3]), key_float(hk[4]), key_float(hk[5]));
+    V3 c = (mx + mn) / 2.0f;
+    s->sc.scene_center[0] = c.x; s->sc.scene_center[1] = c.y; s->sc.scene_center[2] = c.z;
+    s->sc.scene_radius = n == 1 ? INFINITY : length(mx - c);
+}
+
+void upload_scene(rtcuda_scene* s, const rtcuda_scene_desc* d) {
+    cudaStream_t st = s->ctx->stream;
+    validate_desc(d);
+    for (uint32_t m = 0; m < d->material_count; m++) {
+        const rtcuda_material& mm = d->materials[m];
+        const uint32_t ids[6] = {mm.albedo, mm.eta, mm.kappa, mm.roughness, mm.thickness, mm.coat_albedo};
+        for (uint32_t t : ids)
+            if (t != RTCUDA_NONE && t < d->texture_count && texture_depth(d, t, 0) > (uint32_t)TEXTURE_NEST)
+                throw RtError{RTCUDA_ERR_UNSUPPORTED, "texture nesting deeper than the device evaluator supports"};
+    }
+    cudaEvent_t e0, e1, e2;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&e2));
+    CK(cudaEventRecord(e0, st));
+
+    s->width = d->camera.raster_width;
+    s->height = d->camera.raster_height;
+    CameraD& cam = s->sc.camera;
+    cam.kind = d->camera.kind; cam.width = s->width; cam.height = s->height;
+    cam.near_clip = d->camera.near_clip; cam.far_clip = d->camera.far_clip;
+    cam.aperture_radius = d->camera.aperture_radius; cam.focal_distance = d->camera.focal_distance;
+    cam.raster_to_camera = to_m4(d->camera.raster_to_camera.forward);
+    cam.camera_to_world = to_m4(d->camera.camera_to_world.forward);
+
+    s->vertices.upload(d->vertices, d->vertex_count * 3, st);
+    s->tris.upload(d->tris, d->tri_count * 3, st);
+    s->normals.upload(d->normals, d->normal_count * 3, st);
+    s->uvs.upload(d->uvs, d->uv_count * 2, st);
+
+    std::vector<ShapeD> shapes(d->shape_count);
+    for (uint32_t i = 0; i < d->shape_count; i++) {
+        const rtcuda_shape& a = d->shapes[i];
+        ShapeD& b = shapes[i];
+        b.kind = a.kind; b.material = a.material; b.area_light = a.area_light;
+        b.vertex_offset = a.vertex_offset; b.vertex_count = a.vertex_count; b.tri_offset = a.tri_offset; b.tri_count = a.tri_count;
+        b.normal_offset = a.normal_offset; b.uv_offset = a.uv_offset;
+        std::memcpy(b.center, a.center, sizeof b.center);
+        b.radius = a.radius;
+    }
+    std::vector<Instance> instances(d->instance_count);
+    uint64_t n_prims = 0;
+    for (uint32_t i = 0; i < d->instance_count; i++) {
+        const rtcuda_instance& a = d->instances[i];
+        const rtcuda_shape& sh = d->shapes[a.shape];
+        Instance& b = instances[i];
+        std::memset(&b, 0, sizeof b);
+        b.o2w = to_m4(a.object_to_world.forward);
+        b.w2o = to_m4(a.object_to_world.inverse);
+        b.shape = a.shape; b.kind = sh.kind; b.material = sh.material; b.area_light = sh.area_light;
+        b.vertex_offset = sh.vertex_offset; b.tri_offset = sh.tri_offset; b.normal_offset = sh.normal_offset; b.uv_offset = sh.uv_offset;
+        b.tri_count = sh.tri_count;
+        b.prim_base = (uint32_t)n_prims;
+        std::memcpy(b.center, sh.center, sizeof b.center);
+        b.radius = sh.radius;
+        n_prims += sh.kind == RTCUDA_SHAPE_TRIANGLE_MESH ? sh.tri_count : 1;
+        REQUIRE(n_prims < 0x7fffffffull, "too many primitives");
+    }
+    // instances without primitives (empty meshes) would break the prim -> instance search: give them an
+    // empty range that the search skips (prim_base is non-decreasing; the LAST instance with base <= i wins)
+    std::vector<LightD> lights(d->light_count);
+    for (uint32_t i = 0; i < d->light_count; i++) {
+        const rtcuda_light& a = d->lights[i];
+        LightD& b = lights[i];
+        b.kind = a.kind; b.shape = a.shape;
+        std::memcpy(b.a, a.position_or_direction, sizeof b.a);
+        std::memcpy(b.b, a.intensity_or_radiance, sizeof b.b);
+        b.light_to_world = to_m4(a.light_to_world);
+    }
+    s->host_lights.assign(d->lights, d->lights + d->light_count);
+    std::vector<MaterialD> materials(d->material_count);
+    for (uint32_t i = 0; i < d->material_count; i++) {
+        const rtcuda_material& a = d->materials[i];
+        materials[i] = MaterialD{a.kind, a.remap_roughness, a.albedo, a.eta, a.kappa, a.roughness, a.thickness, a.coat_albedo};
+    }
+    std::vector<TextureD> textures(d->texture_count);
+    for (uint32_t i = 0; i < d->texture_count; i++) {
+        const rtcuda_texture& a = d->textures[i];
+        TextureD& b = textures[i];
+        b.kind = a.kind; b.image = a.image; b.filter = a.filter; b.wrap = a.wrap; b.a = a.a; b.b = a.b; b.c = a.c; b.mip_base = NONE;
+        std::memcpy(b.value, a.value, sizeof b.value);
+        std::memcpy(b.value2, a.value2, sizeof b.value2);
+    }
+    std::vector<ImageD> images(d->image_count);
+    for (uint32_t i = 0; i < d->image_count; i++) {
+        const rtcuda_image& a = d->images[i];
+        images[i] = ImageD{a.width, a.height, a.channels, a.format, a.byte_offset};
+    }
+    std::vector<MipChain> chains;
+    build_mips(s, d, images, textures, chains);
+
+    s->shapes.upload(shapes.data(), shapes.size(), st);
+    s->instances.upload(instances.data(), instances.size(), st);
+    s->lights.upload(lights.data(), lights.size(), st);
+    s->materials.upload(materials.data(), materials.size(), st);
+    s->textures.upload(textures.data(), textures.size(), st);
+    s->images.upload(images.data(), images.size(), st);
+    s->mips.upload(chains.data(), chains.size(), st);
+    CK(cudaStreamSynchronize(st));  // host vectors die at scope end
+    CK(cudaEventRecord(e1, st));
+
+    SceneD& sc = s->sc;
+    sc.instances = s->instances.p; sc.shapes = s->shapes.p; sc.lights = s->lights.p; sc.materials = s->materials.p;
+    sc.textures = s->textures.p; sc.images = s->images.p; sc.mips = s->mips.p; sc.image_bytes = s->image_bytes.p;
+    sc.vertices = s->vertices.p; sc.tris = s->tris.p; sc.normals = s->normals.p; sc.uvs = s->uvs.p;
+    sc.instance_count = d->instance_count; sc.light_count = d->light_count; sc.material_count = d->material_count;
+    sc.texture_count = d->texture_count; sc.env_texture = d->environment_light_texture;
+
+    build_bvh(s, instances, (uint32_t)n_prims);
+    sc.nodes = s->nodes.p;
+    sc.prims = s->prims.p;
+    CK(cudaEventRecord(e2, st));
+    CK(cudaStreamSynchronize(st));
+    float ms_up = 0, ms_build = 0;
+    CK(cudaEventElapsedTime(&ms_up, e0, e1));
+    CK(cudaEventElapsedTime(&ms_build, e1, e2));
+    s->stats.upload_ms = ms_up;
+    s->stats.bvh_build_ms = ms_build;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// pixel list: the pixels this context renders, in a ray-coherent order
+// ---------------------------------------------------------------------------------------------------
+// 64x64 tiles in row-major tile order (create_render_jobs, lib.rs:481-504), tile i belongs to this context
+// iff i % tile_world == tile_rank; inside a tile pixels follow a Morton curve so that a warp covers an 8x4
+// block of the image.
+void build_pixel_list(rtcuda_scene* s) {
+    const uint32_t W = s->width, H = s->height, TS = 64;
+    const uint32_t tiles_x = (W + TS - 1) / TS, tiles_y = (H + TS - 1) / TS;
+    const uint32_t world = std::max(1u, s->ctx->bs.tile_world), rank = s->ctx->bs.tile_rank;
+    std::vector<uint32_t> list;
+    list.reserve((size_t)W * H / world + TS * TS);
+    uint16_t mx[TS * TS], my[TS * TS];
+    for (uint32_t m = 0; m < TS * TS; m++) {
+        uint32_t x = 0, y = 0;
+        for (uint32_t bit = 0; bit < 6; bit++) {
+            x |= ((m >> (2 * bit)) & 1u) << bit;
+            y |= ((m >> (2 * bit + 1)) & 1u) << bit;
+        }
+        mx[m] = (uint16_t)x;
+        my[m] = (uint16_t)y;
+    }
+    for (uint32_t ty = 0; ty < tiles_y; ty++)
+        for (uint32_t tx = 0; tx < tiles_x; tx++) {
+            if ((ty * tiles_x + tx) % world != rank) continue;
+            for (uint32_t m = 0; m < TS * TS; m++) {
+                uint32_t x = tx * TS + mx[m], y = ty * TS + my[m];
+                if (x < W && y < H) list.push_back((y << 16) | x);
+            }
+        }
+    s->n_my_pixels = (uint32_t)list.size();
+    s->pixel_list.upload(list.data(), list.size(), s->ctx->stream);
+    CK(cudaStreamSynchronize(s->ctx->stream));
+}
+
+RenderParams make_params(const rtcuda_settings* st) {
+    RenderParams rp{};
+    rp.max_ray_depth = st->max_ray_depth;
+    rp.accumulate_bounces = st->accumulate_bounces;
+    rp.light_sample_count = st->light_sample_count;
+    rp.samples_per_pixel = st->samples_per_pixel;
+    rp.antialias_primary_rays = st->antialias_primary_rays;
+    rp.sampler.seed_hashed = hash_seed(st->has_seed ? st->seed : 42ull);  // sample.rs:30-35
+    rp.sampler.stratified = st->sampler_kind == RTCUDA_SAMPLER_STRATIFIED;
+    rp.sampler.jitter = st->stratified_jitter;
+    rp.sampler.x_strata = st->x_strata;
+    rp.sampler.y_strata = st->y_strata;
+    return rp;
+}
+
+uint32_t shadow_entries_per_vertex(const rtcuda_scene* s, const RenderParams& rp) {
+    uint64_t k = 0;
+    for (const rtcuda_light& l : s->host_lights) k += l.kind == RTCUDA_LIGHT_DIFFUSE_AREA ? rp.light_sample_count : 1;
+    REQUIRE(k < (1u << 20), "too many light samples per path vertex");
+    return (uint32_t)k;
+}
+
+// Allocate the wavefront state for `capacity` path slots.
+void ensure_wave(rtcuda_scene* s, uint32_t capacity, uint32_t shadow_k, uint32_t max_depth) {
+    s->rng_state.ensure(capacity);
+    s->weight.ensure(capacity);
+    s->radiance.ensure(capacity);
+    for (int i = 0; i < 2; i++) { s->ray_o[i].ensure(capacity); s->ray_d[i].ensure(capacity); }
+    s->hits.ensure(capacity);
+    s->shadow_queue.ensure(capacity);
+    s->shadow_point.ensure(capacity);
+    s->shadow_origin.ensure((size_t)capacity * std::max(1u, shadow_k));
+    s->shadow_contrib.ensure((size_t)capacity * std::max(1u, shadow_k));
+    s->counters.ensure(2 * ((size_t)max_depth + 3));
+    s->stats_dev.ensure(STAT_TOTAL);
+}
+
+// One batch of the wavefront: raygen, then per bounce extend -> shade -> shadow. All launches are sized by
+// the batch (an upper bound); kernels read the live queue length from device counters, so the host never
+// synchronises inside a batch.
+void run_batch(rtcuda_scene* s, const RenderParams& rp, Wave w, uint32_t n_paths, bool collect) {
+    cudaStream_t st = s->ctx->stream;
+    const uint32_t max_depth = rp.max_ray_depth;
+    uint32_t* rays = s->counters.p;                       // rays[d]: queue length at depth d
+    uint32_t* shadows = s->counters.p + (max_depth + 3);  // shadows[d]
+    CK(cudaMemsetAsync(s->counters.p, 0, 2 * ((size_t)max_depth + 3) * 4, st));
+    w.depth = 0;
+    w.ray_o_out = s->ray_o[0].p;
+    w.ray_d_out = s->ray_d[0].p;
+    w.n_out = rays;
+    launch_raygen(st, s->sc, rp, w, n_paths, s->lc);
+    for (uint32_t depth = 0; depth <= max_depth; depth++) {
+        const int in = depth & 1, out = in ^ 1;
+        w.depth = depth;
+        w.ray_o_in = s->ray_o[in].p; w.ray_d_in = s->ray_d[in].p;
+        w.ray_o_out = s->ray_o[out].p; w.ray_d_out = s->ray_d[out].p;
+        w.n_in = rays + depth; w.n_out = rays + depth + 1; w.n_shadow = shadows + depth;
+        launch_extend(st, s->sc, w, n_paths, depth == 0 ? s->sc.camera.near_clip : 0.0001f, collect, s->lc);
+        launch_shade(st, s->sc, rp, w, n_paths, s->lc);
+        if (depth < max_depth && w.shadow_k) launch_shadow(st, s->sc, w, n_paths, collect, s->lc);
+    }
+}
+
+void render_device(rtcuda_scene* s, const rtcuda_settings* settings, const rtcuda_outputs* out) {
+    cudaStream_t st = s->ctx->stream;
+    REQUIRE(out->width == s->width && out->height == s->height, "output size must equal the camera raster size");
+    REQUIRE(settings->samples_per_pixel >= 1, "samples_per_pixel must be >= 1");
+    if (settings->sampler_kind == RTCUDA_SAMPLER_STRATIFIED) REQUIRE(settings->x_strata >= 1 && settings->y_strata >= 1, "strata must be >= 1");
+    const RenderParams rp = make_params(settings);
+    const bool collect = s->ctx->bs.collect_stats != 0;
+    if (!s->pixel_list.p) build_pixel_list(s);
+    const uint32_t np_all = s->n_my_pixels;
+    const size_t npix_img = (size_t)s->width * s->height;
+    s->stats_dev.ensure(STAT_TOTAL);
+    CK(cudaMemsetAsync(s->stats_dev.p, 0, STAT_TOTAL * sizeof(unsigned long long), st));
+    const unsigned long long launches0 = s->lc.launches;
+
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0, st));
+
+    const uint32_t o = settings->outputs;
+    AovPlanes pl{};
+    pl.normals = (o & RTCUDA_AOV_NORMALS) ? out->normals : nullptr;
+    pl.albedo = (o & RTCUDA_AOV_ALBEDO) ? out->albedo : nullptr;
+    pl.uv = (o & RTCUDA_AOV_UV_COORDS) ? out->uv : nullptr;
+    pl.mip_level = (o & RTCUDA_AOV_MIP_LEVEL) ? out->mip_level : nullptr;
+    pl.ids = (o & RTCUDA_AOV_DEBUG_IDS) ? out->debug_ids : nullptr;
+    pl.depth = (o & RTCUDA_AOV_DEBUG_DEPTH) ? out->debug_depth : nullptr;
+    const bool partial = np_all != npix_img;
+    if (pl.normals || pl.albedo || pl.uv || pl.mip_level || pl.ids || pl.depth) {
+        if (partial) {  // pixels of other ranks stay 0 (ids: 0 too) so frames can be summed
+            if (pl.normals) CK(cudaMemsetAsync(pl.normals, 0, npix_img * 12, st));
+            if (pl.albedo) CK(cudaMemsetAsync(pl.albedo, 0, npix_img * 12, st));
+            if (pl.uv) CK(cudaMemsetAsync(pl.uv, 0, npix_img * 8, st));
+            if (pl.mip_level) CK(cudaMemsetAsync(pl.mip_level, 0, npix_img * 4, st));
+            if (pl.ids) CK(cudaMemsetAsync(pl.ids, 0, npix_img * 8, st));
+            if (pl.depth) CK(cudaMemsetAsync(pl.depth, 0, npix_img * 4, st));
+        }
+        if (np_all) launch_aov(st, s->sc, rp, s->pixel_list.p, np_all, pl, s->stats_dev.p, collect, s->lc);
+    }
+
+    uint64_t samples = 0;
+    if ((o & RTCUDA_AOV_BEAUTY) && out->beauty) {
+        if (partial) CK(cudaMemsetAsync(out->beauty, 0, npix_img * 12, st));
+        if (np_all) {
+            uint32_t capacity = s->ctx->bs.max_paths_in_flight ? s->ctx->bs.max_paths_in_flight : (1u << 22);
+            capacity = std::max(capacity, 1024u);
+            const uint32_t shadow_k = shadow_entries_per_vertex(s, rp);
+            const uint32_t np_batch = std::min(np_all, capacity);
+            const uint32_t ns_batch = std::max(1u, std::min(settings->samples_per_pixel, capacity / np_batch));
+            ensure_wave(s, np_batch * ns_batch, shadow_k, rp.max_ray_depth);
+            s->accum.ensure(np_all);
+            CK(cudaMemsetAsync(s->accum.p, 0, (size_t)np_all * sizeof(float4), st));
+            Wave w{};
+            w.pixel_list = s->pixel_list.p;
+            w.capacity = np_batch * ns_batch;
+            w.rng_state = s->rng_state.p; w.weight = s->weight.p; w.radiance = s->radiance.p; w.hits = s->hits.p;
+            w.stats = s->stats_dev.p;
+            w.shadow_k = shadow_k; w.shadow_queue = s->shadow_queue.p; w.shadow_point = s->shadow_point.p;
+            w.shadow_origin = s->shadow_origin.p; w.shadow_contrib = s->shadow_contrib.p;
+            for (uint32_t p0 = 0; p0 < np_all; p0 += np_batch) {
+                const uint32_t np = std::min(np_batch, np_all - p0);
+                for (uint32_t s0 = 0; s0 < settings->samples_per_pixel; s0 += ns_batch) {
+                    const uint32_t ns = std::min(ns_batch, settings->samples_per_pixel - s0);
+                    w.pixel_base = p0; w.n_pixels = np; w.sample_base = s0; w.n_samples = ns;
+                    run_batch(s, rp, w, np * ns, collect);
+                    launch_resolve(st, w, s->accum.p, s->lc);
+                    samples += (uint64_t)np * ns;
+                }
+            }
+            launch_finalize(st, s->pixel_list.p, np_all, s->width, s->accum.p, 1.0f / (float)settings->samples_per_pixel, out->beauty, s->lc);
+        }
+    }
+    CK(cudaEventRecord(e1, st));
+    unsigned long long h_stats[STAT_TOTAL];
+    CK(cudaMemcpyAsync(h_stats, s->stats_dev.p, sizeof h_stats, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    s->stats.samples = samples;
+    s->stats.primary_rays = h_stats[STAT_PRIMARY];
+    s->stats.bounce_rays = h_stats[STAT_BOUNCE];
+    s->stats.shadow_rays = h_stats[STAT_SHADOW];
+    s->stats.aov_rays = h_stats[STAT_AOV];
+    s->stats.nodes_fetched = h_stats[STAT_NODES];
+    s->stats.prims_fetched = h_stats[STAT_PRIMS];
+    s->stats.kernel_launches = s->lc.launches - launches0;
+    s->stats.render_ms = ms;
+}
+
+template <typename T>
+T* stage_plane(DevBuf<T>& buf, bool wanted, size_t count) {
+    if (!wanted) return nullptr;
+    buf.ensure(count);
+    return buf.p;
+}
+
+void render_host(rtcuda_scene* s, const rtcuda_settings* settings, rtcuda_outputs* out) {
+    cudaStream_t st = s->ctx->stream;
+    REQUIRE(out->width == s->width && out->height == s->height, "output size must equal the camera raster size");
+    const size_t n = (size_t)s->width * s->height;
+    const uint32_t o = settings->outputs;
+    rtcuda_outputs dev{};
+    dev.width = out->width; dev.height = out->height;
+    dev.beauty = stage_plane(s->d_beauty, (o & RTCUDA_AOV_BEAUTY) && out->beauty, n * 3);
+    dev.normals = stage_plane(s->d_normals, (o & RTCUDA_AOV_NORMALS) && out->normals, n * 3);
+    dev.albedo = stage_plane(s->d_albedo, (o & RTCUDA_AOV_ALBEDO) && out->albedo, n * 3);
+    dev.uv = stage_plane(s->d_uv, (o & RTCUDA_AOV_UV_COORDS) && out->uv, n * 2);
+    dev.mip_level = stage_plane(s->d_mip, (o & RTCUDA_AOV_MIP_LEVEL) && out->mip_level, n);
+    dev.debug_ids = stage_plane(s->d_ids, (o & RTCUDA_AOV_DEBUG_IDS) && out->debug_ids, n * 2);
+    dev.debug_depth = stage_plane(s->d_depth, (o & RTCUDA_AOV_DEBUG_DEPTH) && out->debug_depth, n);
+    render_device(s, settings, &dev);
+    if (dev.beauty) CK(cudaMemcpyAsync(out->beauty, dev.beauty, n * 12, cudaMemcpyDeviceToHost, st));
+    if (dev.normals) CK(cudaMemcpyAsync(out->normals, dev.normals, n * 12, cudaMemcpyDeviceToHost, st));
+    if (dev.albedo) CK(cudaMemcpyAsync(out->albedo, dev.albedo, n * 12, cudaMemcpyDeviceToHost, st));
+    if (dev.uv) CK(cudaMemcpyAsync(out->uv, dev.uv, n * 8, cudaMemcpyDeviceToHost, st));
+    if (dev.mip_level) CK(cudaMemcpyAsync(out->mip_level, dev.mip_level, n * 4, cudaMemcpyDeviceToHost, st));
+    if (dev.debug_ids) CK(cudaMemcpyAsync(out->debug_ids, dev.debug_ids, n * 8, cudaMemcpyDeviceToHost, st));
+    if (dev.debug_depth) CK(cudaMemcpyAsync(out->debug_depth, dev.debug_depth, n * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+}
+
+void render_pixel(rtcuda_scene* s, const rtcuda_settings* settings, uint32_t x, uint32_t y, uint32_t lo, uint32_t hi, rtcuda_pixel_output* out) {
+    cudaStream_t st = s->ctx->stream;
+    REQUIRE(hi >= lo, "sample_hi < sample_lo");
+    const uint32_t n = hi - lo;
+    if (!n) return;
+    REQUIRE(n <= (1u << 22), "sample range too large");
+    x = std::min(x, s->width - 1);   // lib.rs:867-876
+    y = std::min(y, s->height - 1);
+    const RenderParams rp = make_params(settings);
+    const uint32_t shadow_k = shadow_entries_per_vertex(s, rp);
+    ensure_wave(s, n, shadow_k, rp.max_ray_depth);
+    s->pixel_out.ensure(n);
+    CK(cudaMemsetAsync(s->stats_dev.p, 0, STAT_TOTAL * sizeof(unsigned long long), st));
+    DevBuf<uint32_t> one_pixel;
+    const uint32_t packed = (y << 16) | x;
+    one_pixel.upload(&packed, 1, st);
+    launch_pixel_aov(st, s->sc, rp, x, y, lo, n, s->pixel_out.p, s->lc);
+    Wave w{};
+    w.pixel_list = one_pixel.p;
+    w.pixel_base = 0; w.n_pixels = 1; w.sample_base = lo; w.n_samples = n; w.capacity = n;
+    w.rng_state = s->rng_state.p; w.weight = s->weight.p; w.radiance = s->radiance.p; w.hits = s->hits.p;
+    w.stats = s->stats_dev.p;
+    w.shadow_k = shadow_k; w.shadow_queue = s->shadow_queue.p; w.shadow_point = s->shadow_point.p;
+    w.shadow_origin = s->shadow_origin.p; w.shadow_contrib = s->shadow_contrib.p;
+    run_batch(s, rp, w, n, false);
+    launch_pixel_radiance(st, s->radiance.p, n, s->pixel_out.p, s->lc);
+    static_assert(sizeof(PixelOut) == sizeof(rtcuda_pixel_output), "pixel output layout");
+    CK(cudaMemcpyAsync(out, s->pixel_out.p, (size_t)n * sizeof(PixelOut), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+}
+
+template <typename F>
+rtcuda_status guarded(F&& f) {
+    try {
+        f();
+        g_last_error.clear();
+        return RTCUDA_OK;
+    } catch (const RtError& e) {
+        g_last_error = e.msg;
+        return e.status;
+    } catch (const std::bad_alloc&) {
+        g_last_error = "host allocation failed";
+        return RTCUDA_ERR_OUT_OF_MEMORY;
+    } catch (const std::exception& e) {
+        g_last_error = e.what();
+        return RTCUDA_ERR_CUDA;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+RTCUDA_API rtcuda_status rtcuda_init(const rtcuda_backend_settings* settings, rtcuda_ctx** out_ctx) {
+    return guarded([&] {
+        REQUIRE(settings && out_ctx, "null argument");
+        *out_ctx = nullptr;
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count == 0) throw RtError{RTCUDA_ERR_NO_DEVICE, "no CUDA device: the cuda backend has no CPU fallback"};
+        REQUIRE(settings->device_id >= 0 && settings->device_id < count, "device_id out of range");
+        REQUIRE(settings->tile_world <= 1 || settings->tile_rank < settings->tile_world, "tile_rank >= tile_world");
+        auto ctx = std::make_unique<rtcuda_ctx>();
+        ctx->device = settings->device_id;
+        ctx->bs = *settings;
+        CK(cudaSetDevice(ctx->device));
+        CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        *out_ctx = ctx.release();
+    });
+}
+
+RTCUDA_API void rtcuda_shutdown(rtcuda_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+RTCUDA_API rtcuda_status rtcuda_scene_upload(rtcuda_ctx* ctx, const rtcuda_scene_desc* desc, rtcuda_scene** out_scene) {
+    return guarded([&] {
+        REQUIRE(ctx && desc && out_scene, "null argument");
+        *out_scene = nullptr;
+        CK(cudaSetDevice(ctx->device));
+        auto s = std::make_unique<rtcuda_scene>();
+        s->ctx = ctx;
+        upload_scene(s.get(), desc);
+        *out_scene = s.release();
+    });
+}
+
+RTCUDA_API void rtcuda_scene_release(rtcuda_scene* scene) {
+    if (!scene) return;
+    cudaSetDevice(scene->ctx->device);
+    cudaStreamSynchronize(scene->ctx->stream);
+    delete scene;
+}
+
+RTCUDA_API rtcuda_status rtcuda_render(rtcuda_scene* scene, const rtcuda_settings* settings, rtcuda_outputs* outputs) {
+    return guarded([&] {
+        REQUIRE(scene && settings && outputs, "null argument");
+        CK(cudaSetDevice(scene->ctx->device));
+        render_host(scene, settings, outputs);
+    });
+}
+
+RTCUDA_API rtcuda_status rtcuda_render_device(rtcuda_scene* scene, const rtcuda_settings* settings, rtcuda_outputs* device_outputs) {
+    return guarded([&] {
+        REQUIRE(scene && settings && device_outputs, "null argument");
+        CK(cudaSetDevice(scene->ctx->device));
+        render_device(scene, settings, device_outputs);
+    });
+}
+
+RTCUDA_API rtcuda_status rtcuda_render_pixel(rtcuda_scene* scene, const rtcuda_settings* settings, uint32_t x, uint32_t y,
+                                             uint32_t sample_lo, uint32_t sample_hi, rtcuda_pixel_output* out) {
+    return guarded([&] {
+        REQUIRE(scene && settings && (out || sample_hi == sample_lo), "null argument");
+        CK(cudaSetDevice(scene->ctx->device));
+        render_pixel(scene, settings, x, y, sample_lo, sample_hi, out);
+    });
+}
+
+RTCUDA_API rtcuda_status rtcuda_get_stats(const rtcuda_scene* scene, rtcuda_stats* out) {
+    return guarded([&] {
+        REQUIRE(scene && out, "null argument");
+        *out = scene->stats;
+    });
+}
+
+RTCUDA_API const char* rtcuda_last_error(void) { return g_last_error.c_str(); }
+RTCUDA_API uint32_t rtcuda_abi_version(void) { return RTCUDA_ABI_VERSION; }
+
+RTCUDA_API uint32_t rtcuda_abi_struct_sizes(uint32_t* out, uint32_t capacity) {
+    const uint32_t sizes[] = {sizeof(rtcuda_camera), sizeof(rtcuda_shape), sizeof(rtcuda_instance), sizeof(rtcuda_light),
+                              sizeof(rtcuda_material), sizeof(rtcuda_texture), sizeof(rtcuda_image), sizeof(rtcuda_scene_desc),
+                              sizeof(rtcuda_settings), sizeof(rtcuda_backend_settings), sizeof(rtcuda_outputs),
+                              sizeof(rtcuda_pixel_output), sizeof(rtcuda_stats)};
+    const uint32_t n = sizeof(sizes) / sizeof(sizes[0]);
+    for (uint32_t i = 0; i < n && i < capacity; i++) out[i] = sizes[i];
+    return n;
+}
+
+}  // extern "C"

@@ -1,0 +1,269 @@
+// kernels.cu — the sm_100a kernels of the wavefront path tracer and of the device BVH / mip builders.
+//
+// Each __global__ function is a thin wrapper around a per-thread body from rt_*.h; what lives here is the
+// data-parallel plumbing: grid-stride-free one-thread-per-item launches sized from device counters,
+// warp-ballot + block-aggregated queue compaction, and warp-reduced statistics.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "kernels.cuh"
+
+namespace rt {
+
+constexpr int BLOCK = 256;
+static inline uint32_t grid_for(uint32_t n, int block = BLOCK) { return n ? (n + block - 1) / block : 1; }
+
+// ---------------------------------------------------------------------------------------------------
+// queue compaction: one global atomic per block per queue
+// ---------------------------------------------------------------------------------------------------
+// Returns the queue position of this thread's item (valid only when `push`). All threads of the block must call.
+__device__ __forceinline__ uint32_t block_push(bool push, uint32_t* global_counter, uint32_t* s_count, uint32_t* s_base) {
+    const unsigned mask = __ballot_sync(0xffffffffu, push);
+    const unsigned lane = threadIdx.x & 31u;
+    uint32_t warp_off = 0;
+    if (lane == 0 && mask) warp_off = atomicAdd(s_count, (uint32_t)__popc(mask));
+    warp_off = __shfl_sync(0xffffffffu, warp_off, 0);
+    __syncthreads();
+    if (threadIdx.x == 0) *s_base = *s_count ? atomicAdd(global_counter, *s_count) : 0u;
+    __syncthreads();
+    return *s_base + warp_off + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+}
+
+__device__ __forceinline__ void warp_add_stat(unsigned long long* dst, uint32_t v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31u) == 0 && v) atomicAdd(dst, (unsigned long long)v);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// wavefront kernels
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BLOCK) k_raygen(SceneD sc, RenderParams rp, Wave w, uint32_t n) {
+    const uint32_t i = blockIdx.x * BLOCK + threadIdx.x;
+    if (i == 0) *w.n_out = n;
+    if (i < n) raygen_body(i, sc, rp, w);
+}
+
+template <bool STATS>
+__global__ void __launch_bounds__(BLOCK) k_extend(SceneD sc, Wave w, float t_min) {
+    const uint32_t n = *w.n_in;
+    const uint32_t q = blockIdx.x * BLOCK + threadIdx.x;
+    if (blockIdx.x * BLOCK >= n) return;
+    TraverseStats ts;
+    ts.nodes = ts.prims = 0;
+    if (q < n) {
+        const float4 o4 = w.ray_o_in[q], d4 = w.ray_d_in[q];
+        Hit h;
+        traverse<false, STATS>(sc, xyz(o4), xyz(d4), t_min, o4.w, h, &ts);
+        w.hits[q] = make_float4(h.t, u2f(h.prim), h.u, h.v);
+    }
+    if (q == 0) atomicAdd(&w.stats[w.depth == 0 ? STAT_PRIMARY : STAT_BOUNCE], (unsigned long long)n);
+    if (STATS) {
+        warp_add_stat(&w.stats[STAT_NODES], ts.nodes);
+        warp_add_stat(&w.stats[STAT_PRIMS], ts.prims);
+    }
+}
+
+__global__ void __launch_bounds__(BLOCK) k_shade(SceneD sc, RenderParams rp, Wave w) {
+    __shared__ uint32_t s_count[2], s_base[2];
+    const uint32_t n = *w.n_in;
+    if (blockIdx.x * BLOCK >= n) return;
+    if (threadIdx.x < 2) s_count[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t q = blockIdx.x * BLOCK + threadIdx.x;
+    ShadeOut o;
+    o.continue_path = false;
+    o.n_shadow = 0;
+    o.slot = 0;
+    if (q < n) shade_body(q, sc, rp, w, o);
+    const uint32_t rpos = block_push(o.continue_path, w.n_out, &s_count[0], &s_base[0]);
+    if (o.continue_path) {
+        w.ray_o_out[rpos] = make_float4(o.next.o.x, o.next.o.y, o.next.o.z, RT_INF);
+        w.ray_d_out[rpos] = make_float4(o.next.d.x, o.next.d.y, o.next.d.z, u2f(o.slot));
+    }
+    const uint32_t spos = block_push(o.n_shadow != 0, w.n_shadow, &s_count[1], &s_base[1]);
+    if (o.n_shadow != 0) w.shadow_queue[spos] = o.slot;
+}
+
+template <bool STATS>
+__global__ void __launch_bounds__(BLOCK) k_shadow(SceneD sc, Wave w) {
+    const uint32_t n = *w.n_shadow;
+    if (blockIdx.x * BLOCK >= n) return;
+    const uint32_t i = blockIdx.x * BLOCK + threadIdx.x;
+    TraverseStats ts;
+    ts.nodes = ts.prims = 0;
+    uint32_t n_rays = 0;
+    if (i < n) shadow_body<STATS>(i, sc, w, &ts, &n_rays);
+    warp_add_stat(&w.stats[STAT_SHADOW], n_rays);
+    if (STATS) {
+        warp_add_stat(&w.stats[STAT_NODES], ts.nodes);
+        warp_add_stat(&w.stats[STAT_PRIMS], ts.prims);
+    }
+}
+
+__global__ void __launch_bounds__(BLOCK) k_resolve(Wave w, float4* accum) {
+    const uint32_t i = blockIdx.x * BLOCK + threadIdx.x;
+    if (i < w.n_pixels) resolve_body(i, w, accum);
+}
+
+__global__ void __launch_bounds__(BLOCK) k_finalize(const uint32_t* pixel_list, uint32_t n, uint32_t width, const float4* accum,
+                                                     float inv_spp, float* beauty) {
+    const uint32_t i = blockIdx.x * BLOCK + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t packed = pixel_list[i];
+    const size_t idx = (size_t)(packed >> 16) * width + (packed & 0xffffu);
+    const float4 a = accum[i];
+    beauty[3 * idx] = a.x * inv_spp;  // `radiance /= spp` is a multiply by the reciprocal (vec3.rs:122-126)
+    beauty[3 * idx + 1] = a.y * inv_spp;
+    beauty[3 * idx + 2] = a.z * inv_spp;
+}
+
+template <bool STATS>
+__global__ void __launch_bounds__(BLOCK) k_aov(SceneD sc, RenderParams rp, const uint32_t* pixel_list, uint32_t n, AovPlanes pl,
+                                                unsigned long long* stats) {
+    const uint32_t i = blockIdx.x * BLOCK + threadIdx.x;
+    TraverseStats ts;
+    ts.nodes = ts.prims = 0;
+    if (i < n) aov_body<STATS>(i, sc, rp, pixel_list, pl, &ts);
+    if (i == 0) atomicAdd(&stats[STAT_AOV], (unsigned long long)n);
+    if (STATS) {
+        warp_add_stat(&stats[STAT_NODES], ts.nodes);
+        warp_add_stat(&stats[STAT_PRIMS], ts.prims);
+    }
+}
+
+__global__ void k_pixel_aov(SceneD sc, RenderParams rp, uint32_t x, uint32_t y, uint32_t lo, uint32_t n, PixelOut* out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    TraverseStats ts;
+    FirstHit fh = first_hit<false>(sc, rp, x, y, lo + i, &ts);
+    PixelOut& o = out[i];
+    o.sample_index = lo + i;
+    o.hit = fh.hit ? 1u : 0u;
+    o.uv[0] = fh.uv.x; o.uv[1] = fh.uv.y;
+    o.normal[0] = fh.normal.x; o.normal[1] = fh.normal.y; o.normal[2] = fh.normal.z;
+}
+__global__ void k_pixel_radiance(const float4* radiance, uint32_t n, PixelOut* out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i].radiance[0] = radiance[i].x; out[i].radiance[1] = radiance[i].y; out[i].radiance[2] = radiance[i].z;
+}
+
+void launch_raygen(cudaStream_t st, const SceneD& sc, const RenderParams& rp, const Wave& w, uint32_t n, LaunchCounter& lc) {
+    k_raygen<<<grid_for(n), BLOCK, 0, st>>>(sc, rp, w, n);
+    lc.launches++;
+}
+void launch_extend(cudaStream_t st, const SceneD& sc, const Wave& w, uint32_t n_max, float t_min, bool stats, LaunchCounter& lc) {
+    if (stats) k_extend<true><<<grid_for(n_max), BLOCK, 0, st>>>(sc, w, t_min);
+    else k_extend<false><<<grid_for(n_max), BLOCK, 0, st>>>(sc, w, t_min);
+    lc.launches++;
+}
+void launch_shade(cudaStream_t st, const SceneD& sc, const RenderParams& rp, const Wave& w, uint32_t n_max, LaunchCounter& lc) {
+    k_shade<<<grid_for(n_max), BLOCK, 0, st>>>(sc, rp, w);
+    lc.launches++;
+}
+void launch_shadow(cudaStream_t st, const SceneD& sc, const Wave& w, uint32_t n_max, bool stats, LaunchCounter& lc) {
+    if (stats) k_shadow<true><<<grid_for(n_max), BLOCK, 0, st>>>(sc, w);
+    else k_shadow<false><<<grid_for(n_max), BLOCK, 0, st>>>(sc, w);
+    lc.launches++;
+}
+void launch_resolve(cudaStream_t st, const Wave& w, float4* accum, LaunchCounter& lc) {
+    k_resolve<<<grid_for(w.n_pixels), BLOCK, 0, st>>>(w, accum);
+    lc.launches++;
+}
+void launch_finalize(cudaStream_t st, const uint32_t* pixel_list, uint32_t n_pixels, uint32_t width, const float4* accum, float inv_spp,
+                     float* beauty, LaunchCounter& lc) {
+    k_finalize<<<grid_for(n_pixels), BLOCK, 0, st>>>(pixel_list, n_pixels, width, accum, inv_spp, beauty);
+    lc.launches++;
+}
+void launch_aov(cudaStream_t st, const SceneD& sc, const RenderParams& rp, const uint32_t* pixel_list, uint32_t n_pixels,
+                const AovPlanes& planes, unsigned long long* stats, bool collect, LaunchCounter& lc) {
+    if (collect) k_aov<true><<<grid_for(n_pixels), BLOCK, 0, st>>>(sc, rp, pixel_list, n_pixels, planes, stats);
+    else k_aov<false><<<grid_for(n_pixels), BLOCK, 0, st>>>(sc, rp, pixel_list, n_pixels, planes, stats);
+    lc.launches++;
+}
+void launch_pixel_aov(cudaStream_t st, const SceneD& sc, const RenderParams& rp, uint32_t x, uint32_t y, uint32_t sample_lo, uint32_t n,
+                      PixelOut* out, LaunchCounter& lc) {
+    k_pixel_aov<<<grid_for(n, 64), 64, 0, st>>>(sc, rp, x, y, sample_lo, n, out);
+    lc.launches++;
+}
+void launch_pixel_radiance(cudaStream_t st, const float4* radiance, uint32_t n, PixelOut* out, LaunchCounter& lc) {
+    k_pixel_radiance<<<grid_for(n, 64), 64, 0, st>>>(radiance, n, out);
+    lc.launches++;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// BVH build kernels
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BLOCK) k_prim_setup(BuildCtx b) {
+    const uint32_t i = blockIdx.x * BLOCK + threadIdx.x;
+    if (i < b.n) prim_setup_body(i, b);
+}
+__global__ void __launch_bounds__(BLOCK) k_morton(BuildCtx b) {
+    const uint32_t i = blockIdx.x * BLOCK + threadIdx.x;
+    if (i < b.n) morton_body(i, b);
+}
+__global__ void __launch_bounds__(BLOCK) k_karras(BuildCtx b) {
+    const uint32_t i = blockIdx.x * BLOCK + threadIdx.x;
+    if (i + 1 < b.n) karras_body(i, b);
+}
+__global__ void __launch_bounds__(BLOCK) k_refit(BuildCtx b) {
+    const uint32_t i = blockIdx.x * BLOCK + threadIdx.x;
+    if (i < b.n) refit_body(i, b);
+}
+__global__ void __launch_bounds__(128) k_collapse(BuildCtx b, uint32_t n_items) {
+    const uint32_t i = blockIdx.x * 128 + threadIdx.x;
+    if (i < n_items) collapse_body(i, b);
+}
+
+void launch_prim_setup(cudaStream_t st, const BuildCtx& b, LaunchCounter& lc) { k_prim_setup<<<grid_for(b.n), BLOCK, 0, st>>>(b); lc.launches++; }
+void launch_morton(cudaStream_t st, const BuildCtx& b, LaunchCounter& lc) { k_morton<<<grid_for(b.n), BLOCK, 0, st>>>(b); lc.launches++; }
+void launch_karras(cudaStream_t st, const BuildCtx& b, LaunchCounter& lc) { if (b.n > 1) { k_karras<<<grid_for(b.n - 1), BLOCK, 0, st>>>(b); lc.launches++; } }
+void launch_refit(cudaStream_t st, const BuildCtx& b, LaunchCounter& lc) { k_refit<<<grid_for(b.n), BLOCK, 0, st>>>(b); lc.launches++; }
+void launch_collapse(cudaStream_t st, const BuildCtx& b, uint32_t n_items, LaunchCounter& lc) {
+    k_collapse<<<grid_for(n_items, 128), 128, 0, st>>>(b, n_items);
+    lc.launches++;
+}
+
+// The Morton keys are sorted with the toolkit's radix sort (a library call, like cuBLAS for a GEMM);
+// everything else in the build is hand-written.
+size_t sort_temp_bytes(uint32_t n) {
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr, (const uint32_t*)nullptr,
+                                    (uint32_t*)nullptr, (int)n, 0, 63);
+    return bytes;
+}
+void launch_sort(cudaStream_t st, void* temp, size_t temp_bytes, const uint64_t* keys_in, uint64_t* keys_out, const uint32_t* vals_in,
+                 uint32_t* vals_out, uint32_t n, LaunchCounter& lc) {
+    cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, vals_in, vals_out, (int)n, 0, 63, st);
+    lc.launches += 4;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// mip pyramid kernels
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_to_f32(const uint8_t* src, uint32_t format, float* dst, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) to_f32_body(i, src, format, dst);
+}
+__global__ void k_resize(const float* src, float* dst, uint32_t w, uint32_t h, uint32_t ch, uint32_t n_out, int axis, uint32_t total) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < total) resize_body(i, src, dst, w, h, ch, n_out, axis);
+}
+__global__ void k_cast(const float* src, uint32_t format, uint8_t* dst, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) cast_body(i, src, format, dst);
+}
+void launch_to_f32(cudaStream_t st, const uint8_t* src, uint32_t format, float* dst, uint32_t n, LaunchCounter& lc) {
+    k_to_f32<<<grid_for(n), BLOCK, 0, st>>>(src, format, dst, n);
+    lc.launches++;
+}
+void launch_resize(cudaStream_t st, const float* src, float* dst, uint32_t w, uint32_t h, uint32_t ch, uint32_t n_out, int axis, LaunchCounter& lc) {
+    const uint32_t total = axis == 0 ? n_out * w * ch : h * n_out * ch;
+    k_resize<<<grid_for(total), BLOCK, 0, st>>>(src, dst, w, h, ch, n_out, axis, total);
+    lc.launches++;
+}
+void launch_cast(cudaStream_t st, const float* src, uint32_t format, uint8_t* dst, uint32_t n, LaunchCounter& lc) {
+    k_cast<<<grid_for(n), BLOCK, 0, st>>>(src, format, dst, n);
+    lc.launches++;
+}
+
+}  // namespace rt

@@ -1,0 +1,41 @@
+// kernels.cuh — launch interface of the sm_100a kernels (implemented in kernels.cu, driven by api.cu).
+#pragma once
+#include "rt_build.h"
+#include "rt_integrator.h"
+
+namespace rt {
+
+struct LaunchCounter { unsigned long long launches = 0; };
+
+// wavefront
+void launch_raygen(cudaStream_t st, const SceneD& sc, const RenderParams& rp, const Wave& w, uint32_t n, LaunchCounter& lc);
+void launch_extend(cudaStream_t st, const SceneD& sc, const Wave& w, uint32_t n_max, float t_min, bool stats, LaunchCounter& lc);
+void launch_shade(cudaStream_t st, const SceneD& sc, const RenderParams& rp, const Wave& w, uint32_t n_max, LaunchCounter& lc);
+void launch_shadow(cudaStream_t st, const SceneD& sc, const Wave& w, uint32_t n_max, bool stats, LaunchCounter& lc);
+void launch_resolve(cudaStream_t st, const Wave& w, float4* accum, LaunchCounter& lc);
+void launch_finalize(cudaStream_t st, const uint32_t* pixel_list, uint32_t n_pixels, uint32_t width, const float4* accum,
+                     float inv_spp, float* beauty, LaunchCounter& lc);
+void launch_aov(cudaStream_t st, const SceneD& sc, const RenderParams& rp, const uint32_t* pixel_list, uint32_t n_pixels,
+                const AovPlanes& planes, unsigned long long* stats, bool collect, LaunchCounter& lc);
+// single-pixel diagnostics (render_single_pixel): one thread per sample index
+struct PixelOut { uint32_t sample_index, hit; float uv[2]; float normal[3]; float radiance[3]; };
+void launch_pixel_aov(cudaStream_t st, const SceneD& sc, const RenderParams& rp, uint32_t x, uint32_t y, uint32_t sample_lo,
+                      uint32_t n, PixelOut* out, LaunchCounter& lc);
+void launch_pixel_radiance(cudaStream_t st, const float4* radiance, uint32_t n, PixelOut* out, LaunchCounter& lc);
+
+// BVH build
+void launch_prim_setup(cudaStream_t st, const BuildCtx& b, LaunchCounter& lc);
+void launch_morton(cudaStream_t st, const BuildCtx& b, LaunchCounter& lc);
+size_t sort_temp_bytes(uint32_t n);
+void launch_sort(cudaStream_t st, void* temp, size_t temp_bytes, const uint64_t* keys_in, uint64_t* keys_out, const uint32_t* vals_in,
+                 uint32_t* vals_out, uint32_t n, LaunchCounter& lc);
+void launch_karras(cudaStream_t st, const BuildCtx& b, LaunchCounter& lc);
+void launch_refit(cudaStream_t st, const BuildCtx& b, LaunchCounter& lc);
+void launch_collapse(cudaStream_t st, const BuildCtx& b, uint32_t n_items, LaunchCounter& lc);
+
+// mip pyramids
+void launch_to_f32(cudaStream_t st, const uint8_t* src, uint32_t format, float* dst, uint32_t n, LaunchCounter& lc);
+void launch_resize(cudaStream_t st, const float* src, float* dst, uint32_t w, uint32_t h, uint32_t ch, uint32_t n_out, int axis, LaunchCounter& lc);
+void launch_cast(cudaStream_t st, const float* src, uint32_t format, uint8_t* dst, uint32_t n, LaunchCounter& lc);
+
+}  // namespace rt

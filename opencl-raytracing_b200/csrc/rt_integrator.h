@@ -1,0 +1,502 @@
+// rt_integrator.h — per-thread bodies of the wavefront kernels: raygen, shade (material + NEE + BSDF
+// sampling), shadow, resolve, and the first-hit AOV pass.
+//
+// Replaces camera_ray / generate_ray / ray_radiance / first_hit_aovs / render_aovs / render_tile
+// (crates/raytracing-cpu/src/lib.rs:145-625), intersect_shape / ray_mesh_intersect hit-record construction
+// (geometry.rs:92-136, 229-298), sample_light / light_radiance / environment_light_radiance / occluded
+// (lights.rs:14-168) and MaterialEvalContext (materials.rs:702-809).
+//
+// The reference walks one path to completion per loop iteration; here a path is a slot of SoA state that
+// moves through raygen -> [extend -> shade -> shadow]* one bounce per launch. All paths of a batch are
+// at the same depth, so t_min / t_max and the "add emitted / add direct" predicates are launch constants.
+#pragma once
+#include "rt_bsdf.h"
+#include "rt_traverse.h"
+
+namespace rt {
+
+struct RenderParams {  // RaytracerSettings (renderer/mod.rs:84-98)
+    uint32_t max_ray_depth, accumulate_bounces, light_sample_count, samples_per_pixel;
+    uint32_t antialias_primary_rays;
+    SamplerParams sampler;
+};
+
+// Wavefront state of one batch (all pointers device memory; DESIGN.md "Path state").
+struct Wave {
+    // batch shape: slot = s_local * n_pixels + p_local
+    const uint32_t* pixel_list;  // packed (y << 16 | x) of the pixels this context renders, coherent order
+    uint32_t pixel_base, n_pixels, sample_base, n_samples;
+    uint32_t capacity;           // slots allocated (>= n_pixels * n_samples)
+    uint32_t depth;              // bounce index of the rays in the current queue
+    // path state, by slot
+    uint64_t* rng_state;
+    float4* weight;              // xyz path weight | w: bit0 specular_bounce, bits 8.. stratified dimension
+    float4* radiance;            // xyz accumulated radiance of this sample
+    // ray queue (compacted), by queue position
+    const float4* ray_o_in;      // origin.xyz | t_max
+    const float4* ray_d_in;      // direction.xyz | slot
+    float4* ray_o_out;
+    float4* ray_d_out;
+    float4* hits;                // t | prim | u | v
+    const uint32_t* n_in;        // rays in the current queue (device counter of this depth)
+    uint32_t* n_out;             // rays pushed for the next bounce
+    uint32_t* n_shadow;          // paths pushed to the shadow queue at this depth
+    unsigned long long* stats;   // STAT_* counters (rays per class, BVH fetches)
+    // next-event estimation, by slot; K = sum over lights of their sample counts
+    uint32_t shadow_k;
+    uint32_t* shadow_queue;      // slots with at least one pending shadow ray
+    float4* shadow_point;        // shading point.xyz | number of entries
+    float4* shadow_origin;       // [k * capacity + slot]: light-side ray origin.xyz | flags (bit0: skip occlusion test)
+    float4* shadow_contrib;      // [k * capacity + slot]: weighted contribution.xyz
+};
+
+enum { STAT_PRIMARY = 0, STAT_BOUNCE = 1, STAT_SHADOW = 2, STAT_AOV = 3, STAT_NODES = 4, STAT_PRIMS = 5, STAT_SHADED = 6, STAT_TOTAL = 8 };
+
+struct Ray { V3 o, d; };
+struct RayDiff { V3 x_origin, y_origin, x_direction, y_direction; };
+
+// lib.rs:145-195
+RT_HD_CALL Ray camera_ray(const CameraD& cam, float x, float y, bool has_lens, V2 lens) {
+    V3 raster = mk3(x, y, 0.0f);
+    Ray r;
+    V3 cp = apply_point(cam.raster_to_camera, raster);
+    if (cam.kind == 0) {
+        r.o = apply_point(cam.camera_to_world, cp);
+        r.d = unit(apply_vector(cam.camera_to_world, mk3(0, 0, 1)));
+        return r;
+    }
+    if (cam.kind == 1) {
+        r.o = apply_point(cam.camera_to_world, mk3(0, 0, 0));
+        r.d = unit(apply_vector(cam.camera_to_world, unit(cp)));
+        return r;
+    }
+    float t = cam.focal_distance / cp.z;
+    V3 focus = cp * t;
+    V3 co = mk3(0, 0, 0), cd;
+    if (has_lens) {
+        co = mk3(lens.x * cam.aperture_radius, lens.y * cam.aperture_radius, 0.0f);
+        cd = unit(focus - co);
+    } else cd = unit(cp);
+    r.o = apply_point(cam.camera_to_world, co);
+    r.d = unit(apply_vector(cam.camera_to_world, cd));
+    return r;
+}
+
+// lib.rs:198-245
+template <bool WITH_DIFF>
+RT_HD void generate_ray(const CameraD& cam, uint32_t px, uint32_t py, Sampler& s, uint32_t spp, bool jitter, Ray& ray, RayDiff& rd) {
+    float x, y;
+    if (jitter) { V2 d = s.uniform2(); x = (float)px + d.x; y = (float)py + d.y; }
+    else { x = (float)px + 0.5f; y = (float)py + 0.5f; }
+    bool has_lens = cam.kind == 2;
+    V2 lens = mk2(0, 0);
+    if (has_lens) lens = sample_unit_disk_concentric(s.uniform2());
+    ray = camera_ray(cam, x, y, has_lens, lens);
+    if (WITH_DIFF) {
+        Ray rx = camera_ray(cam, x + 1.0f, y, has_lens, lens);
+        Ray ry = camera_ray(cam, x, y + 1.0f, has_lens, lens);
+        float scale = fmaxf(0.125f, sqrtf(1.0f / (float)spp));
+        V3 sx = ray.d + (rx.d - ray.d) * scale;
+        V3 sy = ray.d + (ry.d - ray.d) * scale;
+        rd.x_origin = rx.o - ray.o;
+        rd.y_origin = ry.o - ray.o;
+        rd.x_direction = unit(sx) - ray.d;
+        rd.y_direction = unit(sy) - ray.d;
+    }
+}
+
+struct HitInfo {  // accel.rs:13-25 (+ ids for the debug planes)
+    float t;
+    V2 uv;
+    V3 point, normal, dpdu, dpdv;
+    uint32_t material, light, geom_id, prim_id;
+};
+
+// intersect_shape + ray_mesh_intersect / ray_sphere_intersect + the identity local_to_root step of
+// traverse_bvh (accel.rs:144-164), from the (t, prim, u, v) record the traversal kernel wrote.
+RT_HD_CALL void reconstruct_hit(const SceneD& sc, V3 o, V3 d, const Hit& h, bool need_derivs, HitInfo& out) {
+    const Prim* pr = sc.prims + h.prim;
+    const uint32_t geom = f2u(ldg(&pr->a).w), prim_id = f2u(ldg(&pr->b).w), kind = f2u(ldg(&pr->c).w);
+    const Instance& inst = sc.instances[geom];
+    out.t = h.t;
+    out.geom_id = geom;
+    out.prim_id = prim_id;
+    out.material = inst.material;
+    out.light = inst.area_light;
+    V3 n_obj, dpdu = mk3(0.0f), dpdv = mk3(0.0f);
+    if (kind == 0) {
+        const uint32_t* t = sc.tris + 3 * (size_t)(inst.tri_offset + prim_id);
+        const uint32_t i0 = ldg(t), i1 = ldg(t + 1), i2 = ldg(t + 2);
+        const float u = h.u, v = h.v, w = 1.0f - u - v;
+        V3 p0 = mk3(0.0f), p1 = mk3(0.0f), p2 = mk3(0.0f);
+        const bool has_n = inst.normal_offset != NONE;
+        if (!has_n || need_derivs) {
+            p0 = load3(sc.vertices, inst.vertex_offset + i0);
+            p1 = load3(sc.vertices, inst.vertex_offset + i1);
+            p2 = load3(sc.vertices, inst.vertex_offset + i2);
+        }
+        if (!has_n) n_obj = unit(cross(p2 - p0, p1 - p0));
+        else n_obj = unit(w * load3(sc.normals, inst.normal_offset + i0) + u * load3(sc.normals, inst.normal_offset + i1) +
+                          v * load3(sc.normals, inst.normal_offset + i2));
+        V2 uv0 = mk2(0, 0), uv1 = mk2(1, 0), uv2 = mk2(0, 1);
+        if (inst.uv_offset != NONE) {
+            uv0 = load2(sc.uvs, inst.uv_offset + i0);
+            uv1 = load2(sc.uvs, inst.uv_offset + i1);
+            uv2 = load2(sc.uvs, inst.uv_offset + i2);
+        }
+        out.uv = w * uv0 + u * uv1 + v * uv2;
+        if (need_derivs) {
+            V2 duv02 = uv0 - uv2, duv12 = uv1 - uv2;
+            V3 dp02 = p0 - p2, dp12 = p1 - p2;
+            float det = duv02.x * duv12.y - duv02.y * duv12.x;
+            if (!(fabsf(det) < 1.0e-9f)) {
+                float inv_det = 1.0f / det;
+                dpdu = inv_det * (duv12.y * dp02 - duv02.y * dp12);
+                dpdv = inv_det * (duv02.x * dp12 - duv12.x * dp02);
+            }
+        }
+        out.point = o + d * h.t;
+    } else {
+        V3 center = mk3(inst.center[0], inst.center[1], inst.center[2]);
+        float radius = inst.radius;
+        V3 oo = apply_point(inst.w2o, o), od = apply_vector(inst.w2o, d);
+        V3 point = oo + od * h.t;
+        V3 local = point - center;
+        float theta = acosf(local.z / radius);
+        float sin_theta = sinf(theta);
+        float cos_phi = local.x / (radius * sin_theta);
+        float sin_phi = local.y / (radius * sin_theta);
+        float phi = local.y > 0.0f ? acosf(cos_phi) : 2.0f * PI - acosf(cos_phi);
+        out.uv = mk2(phi / (2.0f * PI), theta / PI);
+        dpdu = mk3(-2.0f * PI * local.y, 2.0f * PI * local.x, 0.0f);
+        dpdv = PI * mk3(local.z * cos_phi, local.z * sin_phi, -radius * sin_theta);
+        n_obj = local / radius;
+        out.point = apply_point(inst.o2w, point);
+    }
+    // Transform::apply_normal = inverse^T (transform.rs:68-73); re-unit twice as the reference does
+    // (geometry.rs:127 and accel.rs:152)
+    out.normal = unit(unit(apply_vector_transposed(inst.w2o, n_obj)));
+    out.dpdu = apply_vector(inst.o2w, dpdu);
+    out.dpdv = apply_vector(inst.o2w, dpdv);
+}
+
+// materials.rs:715-796
+RT_HD_CALL MatCtx matctx_from_differentials(const HitInfo& hit, const Ray& ray, const RayDiff& rd) {
+    V3 n = hit.normal, p = hit.point;
+    V3 rx_o = ray.o + rd.x_origin, rx_d = ray.d + rd.x_direction;
+    V3 ry_o = ray.o + rd.y_origin, ry_d = ray.d + rd.y_direction;
+    float dd = -dot(n, p);
+    float tx = -(dot(n, rx_o) + dd) / dot(n, rx_d);
+    float ty = -(dot(n, ry_o) + dd) / dot(n, ry_d);
+    V3 px = rx_o + tx * rx_d, py = ry_o + ty * ry_d;
+    V3 dpdx = px - hit.point, dpdy = py - hit.point;
+    V3 dpdu = hit.dpdu, dpdv = hit.dpdv;
+    float ata00 = dot(dpdu, dpdu), ata11 = dot(dpdv, dpdv), ata01 = dot(dpdu, dpdv);
+    float det = ata00 * ata11 - ata01 * ata01;
+    float inv_det = 1.0f / det;
+    float atb0x = dot(dpdu, dpdx), atb1x = dot(dpdv, dpdx), atb0y = dot(dpdu, dpdy), atb1y = dot(dpdv, dpdy);
+    float dudx = inv_det * (ata11 * atb0x - ata01 * atb1x);
+    float dvdx = inv_det * (ata00 * atb1x - ata01 * atb0x);
+    float dudy = inv_det * (ata11 * atb0y - ata01 * atb1y);
+    float dvdy = inv_det * (ata00 * atb1y - ata01 * atb0y);
+    MatCtx c;
+    c.uv = hit.uv;
+    c.dudx = finite_f(dudx) ? rs_clamp(dudx, -1.0e8f, 1.0e8f) : 0.0f;
+    c.dudy = finite_f(dudy) ? rs_clamp(dudy, -1.0e8f, 1.0e8f) : 0.0f;
+    c.dvdx = finite_f(dvdx) ? rs_clamp(dvdx, -1.0e8f, 1.0e8f) : 0.0f;
+    c.dvdy = finite_f(dvdy) ? rs_clamp(dvdy, -1.0e8f, 1.0e8f) : 0.0f;
+    return c;
+}
+
+struct LightSample { V3 radiance; V3 origin; V3 dir; float distance, pdf; };
+
+// lights.rs:14-122 (quirks kept: object-space triangle area and normal, un-normalised dir_world in the cosine)
+RT_HD_CALL LightSample sample_light(const SceneD& sc, const LightD& l, V3 point, Sampler& s) {
+    LightSample ls;
+    V3 a = mk3(l.a[0], l.a[1], l.a[2]), b = mk3(l.b[0], l.b[1], l.b[2]);
+    if (l.kind == 0) {
+        V3 dir = point - a;
+        float d = length(dir), d2 = d * d;
+        ls.radiance = b / d2; ls.origin = a; ls.dir = dir / d; ls.distance = d; ls.pdf = 1.0f;
+        return ls;
+    }
+    if (l.kind == 1) {
+        float diam = sc.scene_radius * 2.0f;
+        ls.radiance = b; ls.origin = point - a * diam; ls.dir = unit(a); ls.distance = diam; ls.pdf = 1.0f;
+        return ls;
+    }
+    const ShapeD& em = sc.shapes[l.shape];
+    float pdf = 1.0f;
+    pdf /= (float)em.tri_count;
+    uint32_t tri = s.u32_range(0, em.tri_count);
+    V2 smp = s.uniform2();
+    V3 bary;
+    if (smp.x < smp.y) { float b0 = smp.x / 2.0f, b1 = smp.y - smp.x / 2.0f; bary = mk3(b0, b1, 1.0f - b0 - b1); }
+    else { float b0 = smp.x - smp.y / 2.0f, b1 = smp.y / 2.0f; bary = mk3(b0, b1, 1.0f - b0 - b1); }
+    const uint32_t* t = sc.tris + 3 * (size_t)(em.tri_offset + tri);
+    uint32_t i0 = ldg(t), i1 = ldg(t + 1), i2 = ldg(t + 2);
+    V3 p0 = load3(sc.vertices, em.vertex_offset + i0), p1 = load3(sc.vertices, em.vertex_offset + i1),
+       p2 = load3(sc.vertices, em.vertex_offset + i2);
+    pdf /= length(cross(p1 - p0, p2 - p0)) / 2.0f;  // Mesh::tri_area, mesh.rs:271-278
+    V3 p_local = bary.x * p0 + bary.y * p1 + bary.z * p2;
+    V3 p_world = apply_point(l.light_to_world, p_local);
+    V3 dir_world = point - p_world;
+    float d = length(dir_world);
+    V3 n = em.normal_offset == NONE
+               ? unit(cross(p2 - p0, p1 - p0))
+               : unit(bary.x * load3(sc.normals, em.normal_offset + i0) + bary.y * load3(sc.normals, em.normal_offset + i1) +
+                      bary.z * load3(sc.normals, em.normal_offset + i2));
+    ls.radiance = dot(dir_world, n) < 0.0f ? mk3(0.0f) : b;
+    pdf *= (d * d) / fabsf(dot(dir_world, n));
+    ls.origin = p_world; ls.dir = dir_world / d; ls.distance = d; ls.pdf = pdf;
+    return ls;
+}
+
+RT_HD_CALL V3 environment_radiance(const SceneD& sc, V3 direction) {  // lights.rs:137-157
+    direction = unit(direction);
+    float t = acosf(direction.z) * FRAC_1_PI;
+    float s = (atan2f(direction.x, direction.y) + PI) * FRAC_1_PI * 0.5f;
+    return xyz(tex(sc, sc.env_texture, matctx_no_aa(mk2(s, t))));
+}
+
+RT_HD void slot_to_sample(const Wave& w, uint32_t slot, uint32_t& px, uint32_t& py, uint32_t& sidx) {
+    uint32_t p_local = slot % w.n_pixels;
+    uint32_t packed = ldg(w.pixel_list + w.pixel_base + p_local);
+    px = packed & 0xffffu;
+    py = packed >> 16;
+    sidx = w.sample_base + slot / w.n_pixels;
+}
+
+// ---- raygen: CpuSampler::start_sample + generate_ray(jitter = true) (lib.rs:527-536) -----------------
+RT_HD void raygen_body(uint32_t slot, const SceneD& sc, const RenderParams& rp, const Wave& w) {
+    uint32_t px, py, sidx;
+    slot_to_sample(w, slot, px, py, sidx);
+    Sampler s;
+    s.init(rp.sampler);
+    s.start_sample(px, py, sidx);
+    Ray ray;
+    RayDiff rd;
+    generate_ray<false>(sc.camera, px, py, s, rp.samples_per_pixel, true, ray, rd);
+    w.rng_state[slot] = s.rng.state;
+    w.weight[slot] = make_float4(1.0f, 1.0f, 1.0f, u2f(1u | (s.dimension << 8)));
+    w.radiance[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    w.ray_o_out[slot] = make_float4(ray.o.x, ray.o.y, ray.o.z, sc.camera.far_clip);
+    w.ray_d_out[slot] = make_float4(ray.d.x, ray.d.y, ray.d.z, u2f(slot));
+}
+
+// Result of shading one path vertex; the kernel wrapper turns `continue_path` / `n_shadow` into
+// compacted queue pushes (warp-aggregated on the device, sequential in the CPU harness).
+struct ShadeOut {
+    bool continue_path;
+    Ray next;
+    uint32_t n_shadow;   // entries written to shadow_origin / shadow_contrib for this slot
+    uint32_t slot;
+};
+
+// ---- shade: one iteration of the ray_radiance loop after traverse_bvh (lib.rs:284-391) ------------------
+RT_HD void shade_body(uint32_t q, const SceneD& sc, const RenderParams& rp, const Wave& w, ShadeOut& out) {
+    const float4 ro4 = w.ray_o_in[q], rd4 = w.ray_d_in[q], h4 = w.hits[q];
+    const uint32_t slot = f2u(rd4.w);
+    Ray ray;
+    ray.o = xyz(ro4);
+    ray.d = xyz(rd4);
+    Hit h;
+    h.t = h4.x; h.prim = f2u(h4.y); h.u = h4.z; h.v = h4.w;
+    out.continue_path = false;
+    out.n_shadow = 0;
+    out.slot = slot;
+
+    float4 rad4 = w.radiance[slot];
+    V3 radiance = xyz(rad4);
+    const float4 wt4 = w.weight[slot];
+    V3 path_weight = xyz(wt4);
+    const uint32_t flags = f2u(wt4.w);
+    const bool specular_bounce = (flags & 1u) != 0;
+    const uint32_t depth = w.depth;
+
+    if (h.prim == NONE) {
+        if (sc.env_texture != NONE) {
+            radiance += path_weight * environment_radiance(sc, ray.d);
+            w.radiance[slot] = make_float4(radiance.x, radiance.y, radiance.z, 0.0f);
+        }
+        return;
+    }
+
+    uint32_t px, py, sidx;
+    slot_to_sample(w, slot, px, py, sidx);
+    Sampler s;
+    s.init(rp.sampler);
+    s.resume(px, py, sidx, w.rng_state[slot], flags >> 8);
+
+    const bool aa = depth == 0 && rp.antialias_primary_rays;
+    HitInfo hit;
+    reconstruct_hit(sc, ray.o, ray.d, h, aa, hit);
+
+    bool dirty = false;
+    const bool add_zero_bounce = rp.accumulate_bounces || rp.max_ray_depth == depth;
+    if (specular_bounce && add_zero_bounce && hit.light != NONE) {
+        const LightD& l = sc.lights[hit.light];
+        if (l.kind == 2) { radiance += path_weight * mk3(l.b[0], l.b[1], l.b[2]); dirty = true; }
+    }
+
+    MatCtx mc;
+    if (aa) {
+        // the camera-ray differentials are a pure function of (pixel, sample): re-derive them from a fresh
+        // stream instead of carrying 48 bytes per path (lib.rs:206-243)
+        Sampler s0;
+        s0.init(rp.sampler);
+        s0.start_sample(px, py, sidx);
+        Ray cam_ray;
+        RayDiff rdiff;
+        generate_ray<true>(sc.camera, px, py, s0, rp.samples_per_pixel, true, cam_ray, rdiff);
+        mc = matctx_from_differentials(hit, ray, rdiff);
+    } else mc = matctx_no_aa(hit.uv);
+
+    Surface surf;
+    get_surface(sc, sc.materials[hit.material], mc, surf);
+    Frame fr;
+    fr.n = hit.normal;
+    make_orthonormal_basis(hit.normal, fr.x, fr.y);
+    const V3 wo = fr.to_local(-ray.d);
+
+    const uint32_t depth1 = depth + 1;
+    if (depth1 > rp.max_ray_depth) {
+        if (dirty) w.radiance[slot] = make_float4(radiance.x, radiance.y, radiance.z, 0.0f);
+        return;
+    }
+
+    const bool add_direct = rp.accumulate_bounces || rp.max_ray_depth == depth1;
+    if (!surface_is_delta(surf) && add_direct) {
+        uint32_t k = 0;
+        for (uint32_t li = 0; li < sc.light_count; li++) {
+            const LightD& light = sc.lights[li];
+            const uint32_t n = light.kind == 2 ? rp.light_sample_count : 1u;
+            const float inv_n = 1.0f / (float)n;
+            for (uint32_t j = 0; j < n; j++) {
+                LightSample ls = sample_light(sc, light, hit.point, s);
+                V3 wi = fr.to_local(-ls.dir);
+                // contribution if unoccluded (lib.rs:337-343); zero contributions never need a shadow ray
+                V3 c = mk3(0.0f);
+                float cosv = fmaxf(0.0f, wi.z);
+                if (!(is_zero(ls.radiance) || cosv == 0.0f) || !(ls.pdf > 0.0f)) {
+                    V3 bv = surface_eval(surf, wo, wi);
+                    c = path_weight * ((bv * ls.radiance * cosv / ls.pdf) * inv_n);
+                }
+                if (!is_zero(c)) {
+                    // a non-finite origin (directional light with an infinite scene radius: single-primitive
+                    // scenes, bvh2.rs:448-452) can never be occluded in the reference: NaN slab test
+                    bool skip_test = !(finite_f(ls.origin.x) && finite_f(ls.origin.y) && finite_f(ls.origin.z));
+                    size_t e = (size_t)k * w.capacity + slot;
+                    w.shadow_origin[e] = make_float4(ls.origin.x, ls.origin.y, ls.origin.z, u2f(skip_test ? 1u : 0u));
+                    w.shadow_contrib[e] = make_float4(c.x, c.y, c.z, ls.distance);
+                    k++;
+                }
+            }
+        }
+        if (k) {
+            w.shadow_point[slot] = make_float4(hit.point.x, hit.point.y, hit.point.z, u2f(k));
+            out.n_shadow = k;
+        }
+    }
+
+    BsdfSample bs;
+    bool alive = surface_sample(surf, wo, s, bs) == S_VALID;
+    if (alive && (is_zero(bs.f) || bs.pdf == 0.0f)) alive = false;
+    if (dirty) w.radiance[slot] = make_float4(radiance.x, radiance.y, radiance.z, 0.0f);
+    if (!alive) return;
+    path_weight *= bs.f * fabsf(bs.wi.z) / bs.pdf;
+    const uint32_t spec = (bs.component & SPECULAR) ? 1u : 0u;
+    w.weight[slot] = make_float4(path_weight.x, path_weight.y, path_weight.z, u2f(spec | (s.dimension << 8)));
+    w.rng_state[slot] = s.rng.state;
+    out.continue_path = true;
+    out.next.o = hit.point;
+    out.next.d = fr.to_world(bs.wi);
+}
+
+// ---- shadow: `occluded` (lights.rs:159-168) for every pending light sample of one path vertex -----------
+template <bool STATS>
+RT_HD void shadow_body(uint32_t i, const SceneD& sc, const Wave& w, TraverseStats* stats, uint32_t* n_rays) {
+    const uint32_t slot = w.shadow_queue[i];
+    const float4 p4 = w.shadow_point[slot];
+    const V3 point = xyz(p4);
+    const uint32_t k = f2u(p4.w);
+    V3 sum = mk3(0.0f);
+    for (uint32_t j = 0; j < k; j++) {
+        const size_t e = (size_t)j * w.capacity + slot;
+        const float4 o4 = w.shadow_origin[e], c4 = w.shadow_contrib[e];
+        bool occ = false;
+        if (!(f2u(o4.w) & 1u)) {
+            const V3 origin = xyz(o4);
+            const V3 dir_world = point - origin;
+            const float d = length(dir_world);
+            const V3 dir = dir_world / d;
+            const float distance = c4.w;
+            Hit h;
+            (*n_rays)++;
+            occ = traverse<true, STATS>(sc, origin, dir, 0.001f, distance - 0.001f, h, stats);
+        }
+        if (!occ) sum += xyz(c4);
+    }
+    float4 r = w.radiance[slot];
+    w.radiance[slot] = make_float4(r.x + sum.x, r.y + sum.y, r.z + sum.z, 0.0f);
+}
+
+// ---- resolve: render_tile's per-pixel sample loop tail (lib.rs:538-548) — sum in sample order -----------
+RT_HD void resolve_body(uint32_t p_local, const Wave& w, float4* accum) {
+    float4 a = accum[w.pixel_base + p_local];
+    for (uint32_t s = 0; s < w.n_samples; s++) {
+        float4 r = w.radiance[(size_t)s * w.n_pixels + p_local];
+        a.x += r.x; a.y += r.y; a.z += r.z;
+    }
+    accum[w.pixel_base + p_local] = a;
+}
+
+// ---- first-hit AOVs: render_aovs / first_hit_aovs (lib.rs:395-444, 556-625) ------------------------------
+struct AovPlanes {  // device planes, row-major y*W+x; null = not requested
+    float* normals; float* albedo; float* uv; float* mip_level; uint32_t* ids; float* depth;
+};
+struct FirstHit { bool hit; V2 uv; V3 normal, albedo; bool has_mip; float mip; uint32_t geom, prim; float t; };
+
+template <bool STATS>
+RT_HD FirstHit first_hit(const SceneD& sc, const RenderParams& rp, uint32_t px, uint32_t py, uint32_t sidx, TraverseStats* stats) {
+    Sampler s;
+    s.init(rp.sampler);
+    s.start_sample(px, py, sidx);
+    Ray ray;
+    RayDiff rd;
+    generate_ray<true>(sc.camera, px, py, s, rp.samples_per_pixel, false, ray, rd);
+    FirstHit r;
+    r.hit = false; r.uv = mk2(0, 0); r.normal = mk3(0.0f); r.albedo = mk3(0.0f); r.has_mip = false; r.mip = 0.0f;
+    r.geom = NONE; r.prim = NONE; r.t = 0.0f;
+    Hit h;
+    if (!traverse<false, STATS>(sc, ray.o, ray.d, sc.camera.near_clip, sc.camera.far_clip, h, stats)) return r;
+    HitInfo hit;
+    reconstruct_hit(sc, ray.o, ray.d, h, true, hit);
+    MatCtx mc = matctx_from_differentials(hit, ray, rd);
+    const MaterialD& m = sc.materials[hit.material];
+    r.hit = true;
+    r.uv = hit.uv;
+    r.normal = hit.normal;
+    r.albedo = get_albedo(sc, m, mc);
+    r.has_mip = get_mip_level(sc, m, mc, r.mip);
+    r.geom = hit.geom_id;
+    r.prim = hit.prim_id;
+    r.t = hit.t;
+    return r;
+}
+
+template <bool STATS>
+RT_HD void aov_body(uint32_t i, const SceneD& sc, const RenderParams& rp, const uint32_t* pixel_list, const AovPlanes& pl, TraverseStats* stats) {
+    uint32_t packed = pixel_list[i];
+    uint32_t px = packed & 0xffffu, py = packed >> 16;
+    FirstHit fh = first_hit<STATS>(sc, rp, px, py, 0u, stats);
+    size_t idx = (size_t)py * sc.camera.width + px;
+    if (pl.normals) { pl.normals[3 * idx] = fh.normal.x; pl.normals[3 * idx + 1] = fh.normal.y; pl.normals[3 * idx + 2] = fh.normal.z; }
+    if (pl.albedo) { pl.albedo[3 * idx] = fh.albedo.x; pl.albedo[3 * idx + 1] = fh.albedo.y; pl.albedo[3 * idx + 2] = fh.albedo.z; }
+    if (pl.uv) { pl.uv[2 * idx] = fh.uv.x; pl.uv[2 * idx + 1] = fh.uv.y; }
+    if (pl.mip_level) pl.mip_level[idx] = fh.has_mip ? fh.mip : 0.0f;
+    if (pl.ids) { pl.ids[2 * idx] = fh.geom; pl.ids[2 * idx + 1] = fh.prim; }
+    if (pl.depth) pl.depth[idx] = fh.hit ? fh.t : 0.0f;
+}
+
+}  // namespace rt

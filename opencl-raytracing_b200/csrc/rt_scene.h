@@ -1,0 +1,105 @@
+// rt_scene.h — the scene as it lives in HBM (DESIGN.md "Data layout").
+//
+// Geometry is stored twice on purpose:
+//   * object-space mesh arrays exactly as uploaded (vertices / tris / normals / uvs): used by `shade`
+//     to reconstruct the reference's hit record (interpolated normal, uv, dpdu/dpdv, geometry.rs:229-298)
+//     and by next-event estimation (lights.rs:61-112), both of which the reference evaluates in
+//     object space;
+//   * a packed world-space primitive array (48 B / primitive, three 128-bit loads) ordered by the
+//     8-wide BVH: this is what the traversal kernels touch.
+#pragma once
+#include "rt_common.h"
+
+namespace rt {
+
+// 48-byte traversal primitive. Triangle: world-space vertices, ids in the w lanes.
+// Sphere: a = (center_obj.xyz, geom_id), b = (radius, -, -, prim_id=0), c.w = 1.
+struct Prim {
+    float4 a;  // v0.xyz | geom_id
+    float4 b;  // v1.xyz | prim_id
+    float4 c;  // v2.xyz | kind (0 triangle, 1 sphere)
+};
+
+// One child of the root aggregate (rtcuda_instance + the rtcuda_shape it refers to).
+struct Instance {
+    M4 o2w;       // Transform::forward
+    M4 w2o;       // Transform::inverse
+    uint32_t shape, kind, material, area_light;
+    uint32_t vertex_offset, tri_offset, normal_offset, uv_offset;
+    uint32_t tri_count, prim_base, _p0, _p1;   // prim_base: first build-primitive of this instance
+    float center[3];
+    float radius;
+};
+
+struct ShapeD {  // rtcuda_shape (lights address emitters by shape index)
+    uint32_t kind, material, area_light, vertex_offset, vertex_count, tri_offset, tri_count, normal_offset, uv_offset;
+    float center[3];
+    float radius;
+};
+
+struct LightD {
+    uint32_t kind, shape;
+    float a[3];   // position / direction
+    float b[3];   // intensity / radiance
+    M4 light_to_world;
+};
+
+struct MaterialD { uint32_t kind, remap_roughness, albedo, eta, kappa, roughness, thickness, coat_albedo; };
+
+struct TextureD {
+    uint32_t kind, image, filter, wrap, a, b, c, mip_base;  // mip_base: index into mips[] or NONE
+    float value[4];
+    float value2[4];
+};
+
+struct ImageD {  // also used for generated mip levels
+    uint32_t width, height, channels, format;
+    uint64_t byte_offset;  // into image_bytes
+};
+
+struct MipChain {  // CpuMipmap (texture.rs:114-165): level 0 = resized mip0, then halvings down to 1x1
+    uint32_t first_image;  // index into images[] of mip0
+    uint32_t level_count;  // mips.len() + 1
+};
+
+struct CameraD {
+    uint32_t kind, width, height;
+    float near_clip, far_clip, aperture_radius, focal_distance;
+    M4 raster_to_camera, camera_to_world;  // forward matrices only (lib.rs:145-195)
+};
+
+// 80-byte compressed 8-wide node (DESIGN.md "BVH8 node"): five 128-bit loads.
+//   n0 = origin.xyz | ex | ey<<8 | ez<<16 | imask<<24
+//   n1 = child_base | prim_base | meta[0..3] | meta[4..7]
+//   n2 = qlo_x[0..7] qlo_y[0..7]   n3 = qlo_z[0..7] qhi_x[0..7]   n4 = qhi_y[0..7] qhi_z[0..7]
+// meta[i]: 0 = empty; internal child: (1<<5) | (24+i); leaf child: (unary count: 1,3,7)<<5 | prim offset.
+struct Node8 { float4 n0, n1, n2, n3, n4; };
+
+struct SceneD {
+    CameraD camera;
+    const Node8* nodes;
+    const Prim* prims;
+    uint32_t prim_count;
+    uint32_t node_count;
+    const Instance* instances;
+    const ShapeD* shapes;
+    const LightD* lights;
+    const MaterialD* materials;
+    const TextureD* textures;
+    const ImageD* images;
+    const MipChain* mips;
+    const uint8_t* image_bytes;
+    const float* vertices;
+    const uint32_t* tris;
+    const float* normals;
+    const float* uvs;
+    uint32_t instance_count, light_count, material_count, texture_count;
+    uint32_t env_texture;
+    float scene_center[3];
+    float scene_radius;       // +inf when the BVH root is a leaf (bvh2.rs:448-452 quirk, see rt_shade.h)
+};
+
+RT_HD V3 load3(const float* p, uint32_t i) { return mk3(ldg(p + 3 * (size_t)i), ldg(p + 3 * (size_t)i + 1), ldg(p + 3 * (size_t)i + 2)); }
+RT_HD V2 load2(const float* p, uint32_t i) { return mk2(ldg(p + 2 * (size_t)i), ldg(p + 2 * (size_t)i + 1)); }
+
+}  // namespace rt

@@ -1,0 +1,306 @@
+// hostsim.cpp — TEST INFRASTRUCTURE ONLY. Compiles the per-thread kernel bodies of libraytracing_cuda
+// (opencl-raytracing_b200/csrc/rt_*.h) with g++ and runs them sequentially on the CPU, so the builder,
+// traversal and shading logic can be debugged and checked against the oracle in the build container,
+// which has no GPU. It is never linked into or loaded by the product library; the GPU tests call
+// libraytracing_cuda.so through the C ABI. Mirrors the launch sequence of api.cu.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+#include "../../include/rtcuda.h"
+#include "../../opencl-raytracing_b200/csrc/rt_build.h"
+#include "../../opencl-raytracing_b200/csrc/rt_integrator.h"
+
+using namespace rt;
+
+namespace {
+
+M4 to_m4(const rtcuda_mat4& m) { M4 r; std::memcpy(r.m, m.m, sizeof r.m); return r; }
+uint32_t next_pow2(uint32_t v) { uint32_t p = 1; while (p < v) p <<= 1; return p; }
+bool is_pow2(uint32_t v) { return v && !(v & (v - 1)); }
+uint32_t bps(uint32_t fmt) { return fmt == 0 ? 1 : (fmt == 1 ? 2 : 4); }
+
+struct HostScene {
+    SceneD sc{};
+    std::vector<Instance> instances;
+    std::vector<ShapeD> shapes;
+    std::vector<LightD> lights;
+    std::vector<MaterialD> materials;
+    std::vector<TextureD> textures;
+    std::vector<ImageD> images;
+    std::vector<MipChain> mips;
+    std::vector<uint8_t> image_bytes;
+    std::vector<Node8> nodes;
+    std::vector<Prim> prims;
+    uint32_t n_levels = 0;
+};
+
+void build(HostScene& hs, const rtcuda_scene_desc* d) {
+    SceneD& sc = hs.sc;
+    sc.camera.kind = d->camera.kind; sc.camera.width = d->camera.raster_width; sc.camera.height = d->camera.raster_height;
+    sc.camera.near_clip = d->camera.near_clip; sc.camera.far_clip = d->camera.far_clip;
+    sc.camera.aperture_radius = d->camera.aperture_radius; sc.camera.focal_distance = d->camera.focal_distance;
+    sc.camera.raster_to_camera = to_m4(d->camera.raster_to_camera.forward);
+    sc.camera.camera_to_world = to_m4(d->camera.camera_to_world.forward);
+    hs.shapes.resize(d->shape_count);
+    for (uint32_t i = 0; i < d->shape_count; i++) {
+        const rtcuda_shape& a = d->shapes[i];
+        ShapeD& b = hs.shapes[i];
+        b.kind = a.kind; b.material = a.material; b.area_light = a.area_light; b.vertex_offset = a.vertex_offset; b.vertex_count = a.vertex_count;
+        b.tri_offset = a.tri_offset; b.tri_count = a.tri_count; b.normal_offset = a.normal_offset; b.uv_offset = a.uv_offset;
+        std::memcpy(b.center, a.center, sizeof b.center); b.radius = a.radius;
+    }
+    hs.instances.resize(d->instance_count);
+    uint32_t n_prims = 0;
+    for (uint32_t i = 0; i < d->instance_count; i++) {
+        const rtcuda_instance& a = d->instances[i];
+        const rtcuda_shape& sh = d->shapes[a.shape];
+        Instance& b = hs.instances[i];
+        std::memset(&b, 0, sizeof b);
+        b.o2w = to_m4(a.object_to_world.forward); b.w2o = to_m4(a.object_to_world.inverse);
+        b.shape = a.shape; b.kind = sh.kind; b.material = sh.material; b.area_light = sh.area_light;
+        b.vertex_offset = sh.vertex_offset; b.tri_offset = sh.tri_offset; b.normal_offset = sh.normal_offset; b.uv_offset = sh.uv_offset;
+        b.tri_count = sh.tri_count; b.prim_base = n_prims;
+        std::memcpy(b.center, sh.center, sizeof b.center); b.radius = sh.radius;
+        n_prims += sh.kind == 0 ? sh.tri_count : 1;
+    }
+    hs.lights.resize(d->light_count);
+    for (uint32_t i = 0; i < d->light_count; i++) {
+        const rtcuda_light& a = d->lights[i];
+        LightD& b = hs.lights[i];
+        b.kind = a.kind; b.shape = a.shape;
+        std::memcpy(b.a, a.position_or_direction, sizeof b.a); std::memcpy(b.b, a.intensity_or_radiance, sizeof b.b);
+        b.light_to_world = to_m4(a.light_to_world);
+    }
+    hs.materials.resize(d->material_count);
+    for (uint32_t i = 0; i < d->material_count; i++) {
+        const rtcuda_material& a = d->materials[i];
+        hs.materials[i] = MaterialD{a.kind, a.remap_roughness, a.albedo, a.eta, a.kappa, a.roughness, a.thickness, a.coat_albedo};
+    }
+    hs.textures.resize(d->texture_count);
+    for (uint32_t i = 0; i < d->texture_count; i++) {
+        const rtcuda_texture& a = d->textures[i];
+        TextureD& b = hs.textures[i];
+        b.kind = a.kind; b.image = a.image; b.filter = a.filter; b.wrap = a.wrap; b.a = a.a; b.b = a.b; b.c = a.c; b.mip_base = NONE;
+        std::memcpy(b.value, a.value, sizeof b.value); std::memcpy(b.value2, a.value2, sizeof b.value2);
+    }
+    hs.images.resize(d->image_count);
+    for (uint32_t i = 0; i < d->image_count; i++) hs.images[i] = ImageD{d->images[i].width, d->images[i].height, d->images[i].channels, d->images[i].format, d->images[i].byte_offset};
+    hs.image_bytes.assign(d->image_bytes, d->image_bytes + d->image_byte_count);
+
+    // mip pyramids (api.cu build_mips)
+    std::vector<int> chain_of(d->image_count, -1);
+    for (uint32_t t = 0; t < d->texture_count; t++) {
+        const rtcuda_texture& tx = d->textures[t];
+        if (tx.kind != 0 || tx.filter != 2) continue;
+        if (chain_of[tx.image] < 0) {
+            const rtcuda_image im = d->images[tx.image];
+            const uint32_t ch = im.channels, fmt = im.format;
+            uint32_t w = im.width, h = im.height;
+            std::vector<float> cur((size_t)w * h * ch);
+            for (uint32_t i = 0; i < cur.size(); i++) to_f32_body(i, hs.image_bytes.data() + im.byte_offset, fmt, cur.data());
+            uint32_t size = w;
+            if (!(is_pow2(w) && is_pow2(h)) || w != h) size = std::max(next_pow2(w), next_pow2(h));
+            auto resize = [&](uint32_t nw, uint32_t nh) {
+                std::vector<float> tmp((size_t)w * nh * ch), out((size_t)nw * nh * ch);
+                for (uint32_t i = 0; i < tmp.size(); i++) resize_body(i, cur.data(), tmp.data(), w, h, ch, nh, 0);
+                for (uint32_t i = 0; i < out.size(); i++) resize_body(i, tmp.data(), out.data(), w, nh, ch, nw, 1);
+                cur.swap(out); w = nw; h = nh;
+            };
+            if (w != size || h != size) resize(size, size);
+            MipChain mc; mc.first_image = (uint32_t)hs.images.size(); mc.level_count = 0;
+            for (;;) {
+                size_t off = (hs.image_bytes.size() + 15) & ~(size_t)15;
+                hs.image_bytes.resize(off + (size_t)w * h * ch * bps(fmt));
+                for (uint32_t i = 0; i < w * h * ch; i++) cast_body(i, cur.data(), fmt, hs.image_bytes.data() + off);
+                hs.images.push_back(ImageD{w, h, ch, fmt, off});
+                mc.level_count++;
+                if (!(w > 1 && h > 1)) break;
+                resize(w / 2, h / 2);
+            }
+            chain_of[tx.image] = (int)hs.mips.size();
+            hs.mips.push_back(mc);
+        }
+        hs.textures[t].mip_base = (uint32_t)chain_of[tx.image];
+    }
+
+    sc.instances = hs.instances.data(); sc.shapes = hs.shapes.data(); sc.lights = hs.lights.data(); sc.materials = hs.materials.data();
+    sc.textures = hs.textures.data(); sc.images = hs.images.data(); sc.mips = hs.mips.data(); sc.image_bytes = hs.image_bytes.data();
+    sc.vertices = d->vertices; sc.tris = d->tris; sc.normals = d->normals; sc.uvs = d->uvs;
+    sc.instance_count = d->instance_count; sc.light_count = d->light_count; sc.material_count = d->material_count;
+    sc.texture_count = d->texture_count; sc.env_texture = d->environment_light_texture;
+    sc.prim_count = n_prims; sc.node_count = 0;
+    hs.nodes.resize(std::max(1u, n_prims)); hs.prims.resize(std::max(1u, n_prims));
+    sc.nodes = hs.nodes.data(); sc.prims = hs.prims.data();
+    if (!n_prims) return;
+
+    // BVH (api.cu build_bvh)
+    const uint32_t n = n_prims;
+    std::vector<Prim> prims_unsorted(n);
+    std::vector<float4> aabb_lo(n), aabb_hi(n), node_lo(2 * (size_t)n), node_hi(2 * (size_t)n);
+    std::vector<uint32_t> vals(n), vals_sorted(n), left(n), right(n), parent(2 * (size_t)n), range_lo(n), range_hi(n), visit(n, 0);
+    std::vector<uint64_t> keys(n), keys_sorted(n);
+    std::vector<WorkItem> qa(n), qb(n);
+    uint32_t bounds_keys[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0, 0, 0};
+    uint32_t counters[4] = {0, 1, 0, 0};
+    BuildCtx b{};
+    b.instances = hs.instances.data(); b.instance_count = d->instance_count; b.vertices = d->vertices; b.tris = d->tris; b.n = n;
+    b.prims_unsorted = prims_unsorted.data(); b.aabb_lo = aabb_lo.data(); b.aabb_hi = aabb_hi.data(); b.bounds_keys = bounds_keys;
+    b.keys = keys.data(); b.vals = vals.data(); b.keys_sorted = keys_sorted.data(); b.vals_sorted = vals_sorted.data();
+    b.left = left.data(); b.right = right.data(); b.parent = parent.data(); b.range_lo = range_lo.data(); b.range_hi = range_hi.data();
+    b.node_lo = node_lo.data(); b.node_hi = node_hi.data(); b.visit = visit.data();
+    b.nodes = hs.nodes.data(); b.prims = hs.prims.data(); b.counters = counters;
+    for (uint32_t i = 0; i < n; i++) prim_setup_body(i, b);
+    for (uint32_t i = 0; i < n; i++) morton_body(i, b);
+    std::vector<uint32_t> order(n);
+    std::iota(order.begin(), order.end(), 0u);
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return keys[x] < keys[y]; });
+    for (uint32_t i = 0; i < n; i++) { keys_sorted[i] = keys[order[i]]; vals_sorted[i] = vals[order[i]]; }
+    for (uint32_t i = 0; i + 1 < n; i++) karras_body(i, b);
+    for (uint32_t i = 0; i < n; i++) refit_body(i, b);
+    qa[0] = WorkItem{0, 0};
+    uint32_t n_items = 1;
+    WorkItem* qin = qa.data();
+    WorkItem* qout = qb.data();
+    while (n_items) {
+        b.queue_in = qin; b.queue_out = qout;
+        for (uint32_t i = 0; i < n_items; i++) collapse_body(i, b);
+        n_items = counters[0];
+        counters[0] = 0;
+        std::swap(qin, qout);
+        hs.n_levels++;
+    }
+    sc.node_count = counters[1];
+    V3 mn = mk3(key_float(bounds_keys[0]), key_float(bounds_keys[1]), key_float(bounds_keys[2]));
+    V3 mx = mk3(key_float(bounds_keys[3]), key_float(bounds_keys[4]), key_float(bounds_keys[5]));
+    V3 c = (mx + mn) / 2.0f;
+    sc.scene_center[0] = c.x; sc.scene_center[1] = c.y; sc.scene_center[2] = c.z;
+    sc.scene_radius = n == 1 ? INFINITY : length(mx - c);
+    if (counters[2] != n) sc.node_count = 0xdeadbeef;  // lost primitives: surfaced through the stats
+}
+
+RenderParams make_params(const rtcuda_settings* st) {
+    RenderParams rp{};
+    rp.max_ray_depth = st->max_ray_depth; rp.accumulate_bounces = st->accumulate_bounces; rp.light_sample_count = st->light_sample_count;
+    rp.samples_per_pixel = st->samples_per_pixel; rp.antialias_primary_rays = st->antialias_primary_rays;
+    rp.sampler.seed_hashed = hash_seed(st->has_seed ? st->seed : 42ull);
+    rp.sampler.stratified = st->sampler_kind == RTCUDA_SAMPLER_STRATIFIED; rp.sampler.jitter = st->stratified_jitter;
+    rp.sampler.x_strata = st->x_strata; rp.sampler.y_strata = st->y_strata;
+    return rp;
+}
+
+}  // namespace
+
+extern "C" {
+
+// stats_out[8]: primary, bounce, shadow, aov rays, nodes fetched, prims fetched, wide node count, collapse levels
+__attribute__((visibility("default")))
+int hostsim_render(const rtcuda_scene_desc* d, const rtcuda_settings* st, rtcuda_outputs* out, uint32_t tile_rank, uint32_t tile_world,
+                   uint32_t capacity, uint64_t* stats_out) {
+    HostScene hs;
+    build(hs, d);
+    const SceneD& sc = hs.sc;
+    const RenderParams rp = make_params(st);
+    const uint32_t W = sc.camera.width, H = sc.camera.height, TS = 64;
+    if (out->width != W || out->height != H) return 1;
+    if (tile_world == 0) tile_world = 1;
+    std::vector<uint32_t> pixels;
+    const uint32_t tiles_x = (W + TS - 1) / TS, tiles_y = (H + TS - 1) / TS;
+    for (uint32_t ty = 0; ty < tiles_y; ty++)
+        for (uint32_t tx = 0; tx < tiles_x; tx++) {
+            if ((ty * tiles_x + tx) % tile_world != tile_rank) continue;
+            for (uint32_t m = 0; m < TS * TS; m++) {
+                uint32_t x = 0, y = 0;
+                for (uint32_t bit = 0; bit < 6; bit++) { x |= ((m >> (2 * bit)) & 1u) << bit; y |= ((m >> (2 * bit + 1)) & 1u) << bit; }
+                x += tx * TS; y += ty * TS;
+                if (x < W && y < H) pixels.push_back((y << 16) | x);
+            }
+        }
+    const uint32_t np_all = (uint32_t)pixels.size();
+    const size_t npix = (size_t)W * H;
+    uint64_t stats[8] = {0};
+    TraverseStats ts{0, 0};
+    const uint32_t o = st->outputs;
+    AovPlanes pl{};
+    pl.normals = (o & RTCUDA_AOV_NORMALS) ? out->normals : nullptr; pl.albedo = (o & RTCUDA_AOV_ALBEDO) ? out->albedo : nullptr;
+    pl.uv = (o & RTCUDA_AOV_UV_COORDS) ? out->uv : nullptr; pl.mip_level = (o & RTCUDA_AOV_MIP_LEVEL) ? out->mip_level : nullptr;
+    pl.ids = (o & RTCUDA_AOV_DEBUG_IDS) ? out->debug_ids : nullptr; pl.depth = (o & RTCUDA_AOV_DEBUG_DEPTH) ? out->debug_depth : nullptr;
+    if (pl.normals || pl.albedo || pl.uv || pl.mip_level || pl.ids || pl.depth) {
+        if (pl.normals) std::memset(pl.normals, 0, npix * 12);
+        if (pl.albedo) std::memset(pl.albedo, 0, npix * 12);
+        if (pl.uv) std::memset(pl.uv, 0, npix * 8);
+        if (pl.mip_level) std::memset(pl.mip_level, 0, npix * 4);
+        if (pl.ids) std::memset(pl.ids, 0, npix * 8);
+        if (pl.depth) std::memset(pl.depth, 0, npix * 4);
+        for (uint32_t i = 0; i < np_all; i++) aov_body<true>(i, sc, rp, pixels.data(), pl, &ts);
+        stats[3] += np_all;
+    }
+    if ((o & RTCUDA_AOV_BEAUTY) && out->beauty && np_all) {
+        std::memset(out->beauty, 0, npix * 12);
+        if (!capacity) capacity = 1u << 20;
+        uint32_t shadow_k = 0;
+        for (uint32_t i = 0; i < d->light_count; i++) shadow_k += d->lights[i].kind == 2 ? rp.light_sample_count : 1;
+        const uint32_t np_batch = std::min(np_all, capacity);
+        const uint32_t ns_batch = std::max(1u, std::min(st->samples_per_pixel, capacity / np_batch));
+        const uint32_t cap = np_batch * ns_batch;
+        std::vector<uint64_t> rng(cap);
+        std::vector<float4> weight(cap), radiance(cap), ro[2], rd[2], hits(cap), spoint(cap), sorigin((size_t)cap * std::max(1u, shadow_k)), scontrib((size_t)cap * std::max(1u, shadow_k));
+        for (int i = 0; i < 2; i++) { ro[i].resize(cap); rd[i].resize(cap); }
+        std::vector<uint32_t> squeue(cap);
+        std::vector<float4> accum(np_all, make_float4(0, 0, 0, 0));
+        unsigned long long dummy_stats[STAT_TOTAL] = {0};
+        Wave w{};
+        w.pixel_list = pixels.data(); w.capacity = cap;
+        w.rng_state = rng.data(); w.weight = weight.data(); w.radiance = radiance.data(); w.hits = hits.data(); w.stats = dummy_stats;
+        w.shadow_k = shadow_k; w.shadow_queue = squeue.data(); w.shadow_point = spoint.data(); w.shadow_origin = sorigin.data(); w.shadow_contrib = scontrib.data();
+        for (uint32_t p0 = 0; p0 < np_all; p0 += np_batch) {
+            const uint32_t np = std::min(np_batch, np_all - p0);
+            for (uint32_t s0 = 0; s0 < st->samples_per_pixel; s0 += ns_batch) {
+                const uint32_t ns = std::min(ns_batch, st->samples_per_pixel - s0);
+                w.pixel_base = p0; w.n_pixels = np; w.sample_base = s0; w.n_samples = ns;
+                uint32_t n_rays = np * ns;
+                w.depth = 0; w.ray_o_out = ro[0].data(); w.ray_d_out = rd[0].data();
+                for (uint32_t i = 0; i < n_rays; i++) raygen_body(i, sc, rp, w);
+                for (uint32_t depth = 0; depth <= rp.max_ray_depth && n_rays; depth++) {
+                    const int in = depth & 1, ot = in ^ 1;
+                    w.depth = depth;
+                    w.ray_o_in = ro[in].data(); w.ray_d_in = rd[in].data(); w.ray_o_out = ro[ot].data(); w.ray_d_out = rd[ot].data();
+                    const float t_min = depth == 0 ? sc.camera.near_clip : 0.0001f;
+                    for (uint32_t q = 0; q < n_rays; q++) {
+                        Hit h;
+                        traverse<false, true>(sc, xyz(w.ray_o_in[q]), xyz(w.ray_d_in[q]), t_min, w.ray_o_in[q].w, h, &ts);
+                        hits[q] = make_float4(h.t, u2f(h.prim), h.u, h.v);
+                    }
+                    stats[depth == 0 ? 0 : 1] += n_rays;
+                    uint32_t n_out = 0, n_shadow = 0;
+                    for (uint32_t q = 0; q < n_rays; q++) {
+                        ShadeOut so;
+                        shade_body(q, sc, rp, w, so);
+                        if (so.continue_path) {
+                            w.ray_o_out[n_out] = make_float4(so.next.o.x, so.next.o.y, so.next.o.z, INFINITY);
+                            w.ray_d_out[n_out] = make_float4(so.next.d.x, so.next.d.y, so.next.d.z, u2f(so.slot));
+                            n_out++;
+                        }
+                        if (so.n_shadow) squeue[n_shadow++] = so.slot;
+                    }
+                    uint32_t shadow_rays = 0;
+                    for (uint32_t i = 0; i < n_shadow; i++) shadow_body<true>(i, sc, w, &ts, &shadow_rays);
+                    stats[2] += shadow_rays;
+                    n_rays = n_out;
+                }
+                for (uint32_t i = 0; i < np; i++) resolve_body(i, w, accum.data());
+            }
+        }
+        const float inv_spp = 1.0f / (float)st->samples_per_pixel;
+        for (uint32_t i = 0; i < np_all; i++) {
+            size_t idx = (size_t)(pixels[i] >> 16) * W + (pixels[i] & 0xffffu);
+            out->beauty[3 * idx] = accum[i].x * inv_spp; out->beauty[3 * idx + 1] = accum[i].y * inv_spp; out->beauty[3 * idx + 2] = accum[i].z * inv_spp;
+        }
+    }
+    stats[4] = ts.nodes; stats[5] = ts.prims; stats[6] = sc.node_count; stats[7] = hs.n_levels;
+    if (stats_out) std::memcpy(stats_out, stats, sizeof stats);
+    return 0;
+}
+}

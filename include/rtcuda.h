@@ -240,6 +240,11 @@ typedef struct rtcuda_settings {
     uint32_t antialias_secondary_rays;/* bool */
 } rtcuda_settings;
 
+enum {
+    RTCUDA_STATS_COUNTERS = 1u << 0,      /* count BVH node / primitive fetches (instrumented traversal kernels) */
+    RTCUDA_STATS_KERNEL_TIMES = 1u << 1   /* CUDA events around every extend / shade / shadow launch */
+};
+
 /* The analogue of CpuBackendSettings (crates/raytracing-cpu/src/lib.rs:446-457) /
  * OptixBackendSettings (crates/raytracing-optix/src/lib.rs:25-28). */
 typedef struct rtcuda_backend_settings {
@@ -250,7 +255,7 @@ typedef struct rtcuda_backend_settings {
      * i % tile_world == tile_rank; all other pixels are left 0 so frames can be summed. */
     uint32_t tile_rank;
     uint32_t tile_world;              /* 0 or 1 => whole image */
-    uint32_t collect_stats;           /* bool: count rays / BVH fetches (stats build of the traversal kernels) */
+    uint32_t collect_stats;           /* RTCUDA_STATS_* bits */
     uint32_t _pad;
 } rtcuda_backend_settings;
 
@@ -275,16 +280,22 @@ typedef struct rtcuda_pixel_output {
     float radiance[3];
 } rtcuda_pixel_output;
 
-/* Counters of the last render: rays actually traced per class, BVH fetch counts
- * (only when collect_stats), device milliseconds of the render window and of the BVH build. */
+/* Counters of the last render: rays actually traced per class; BVH fetch counts per
+ * traversal kernel (only with RTCUDA_STATS_COUNTERS); device milliseconds of the render window, of the BVH
+ * build, and per kernel class (only with RTCUDA_STATS_KERNEL_TIMES: CUDA events around every launch). */
 typedef struct rtcuda_stats {
     uint64_t samples;
     uint64_t primary_rays, bounce_rays, shadow_rays, aov_rays;
-    uint64_t nodes_fetched, prims_fetched;      /* collect_stats only */
+    uint64_t nodes_fetched, prims_fetched;      /* all traversal kernels */
+    uint64_t extend_nodes, extend_prims;        /* closest-hit `extend` kernel */
+    uint64_t shadow_nodes, shadow_prims;        /* any-hit `shadow` kernel */
+    uint64_t shaded_vertices;                   /* path vertices that reached material evaluation */
     uint64_t kernel_launches;
+    uint64_t extend_launches, shade_launches, shadow_launches;
     double render_ms;                 /* CUDA-event time, inputs resident, excludes D2H */
     double bvh_build_ms;              /* last scene upload */
     double upload_ms;
+    double extend_ms, shade_ms, shadow_ms, other_ms;   /* RTCUDA_STATS_KERNEL_TIMES */
     uint64_t bvh_node_count, bvh_prim_count;
 } rtcuda_stats;
 

@@ -7,6 +7,7 @@ from .scene import (Camera, Light, Material, Mesh, Scene, SceneBuilder, Sphere, 
                     mesh_from_ply_bytes)
 from .backend import CudaBackendSettings, CudaRenderer, render, render_single_pixel
 from . import test_scenes
+from . import multi_gpu
 
 __all__ = ["AovFlags", "RaytracerSettings", "RenderOutput", "Sampler", "SinglePixelOutput", "Camera", "Light",
            "Material", "Mesh", "Scene", "SceneBuilder", "Sphere", "Texture", "scene_from_gltf_file",

@@ -120,10 +120,16 @@ class PixelOutput(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("samples", C.c_uint64), ("primary_rays", C.c_uint64), ("bounce_rays", C.c_uint64),
                 ("shadow_rays", C.c_uint64), ("aov_rays", C.c_uint64), ("nodes_fetched", C.c_uint64),
-                ("prims_fetched", C.c_uint64), ("kernel_launches", C.c_uint64), ("render_ms", C.c_double),
-                ("bvh_build_ms", C.c_double), ("upload_ms", C.c_double), ("bvh_node_count", C.c_uint64),
+                ("prims_fetched", C.c_uint64), ("extend_nodes", C.c_uint64), ("extend_prims", C.c_uint64),
+                ("shadow_nodes", C.c_uint64), ("shadow_prims", C.c_uint64), ("shaded_vertices", C.c_uint64),
+                ("kernel_launches", C.c_uint64), ("extend_launches", C.c_uint64), ("shade_launches", C.c_uint64),
+                ("shadow_launches", C.c_uint64), ("render_ms", C.c_double), ("bvh_build_ms", C.c_double),
+                ("upload_ms", C.c_double), ("extend_ms", C.c_double), ("shade_ms", C.c_double),
+                ("shadow_ms", C.c_double), ("other_ms", C.c_double), ("bvh_node_count", C.c_uint64),
                 ("bvh_prim_count", C.c_uint64)]
 
+
+STATS_COUNTERS, STATS_KERNEL_TIMES = 1, 2
 
 ABI_STRUCTS = [Camera, Shape, Instance, Light, Material, Texture, Image, SceneDesc, Settings, BackendSettings,
                Outputs, PixelOutput, Stats]

@@ -24,7 +24,7 @@ class CudaBackendSettings:
     max_paths_in_flight: int = 0       # 0 => backend default
     tile_rank: int = 0                 # this context renders 64x64 tiles i with i % tile_world == tile_rank
     tile_world: int = 1
-    collect_stats: bool = False
+    collect_stats: int = 0             # _ffi.STATS_COUNTERS | _ffi.STATS_KERNEL_TIMES (True == counters)
 
     def to_c(self) -> _ffi.BackendSettings:
         b = _ffi.BackendSettings()

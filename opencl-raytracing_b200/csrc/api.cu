@@ -123,6 +123,14 @@ struct rtcuda_scene {
     DevBuf<uint32_t> d_ids;
     rtcuda_stats stats{};
     LaunchCounter lc;
+    // RTCUDA_STATS_KERNEL_TIMES: CUDA events around every extend / shade / shadow launch
+    std::vector<cudaEvent_t> ev_pool;
+    struct Span { int cls; size_t e0, e1; };
+    std::vector<Span> spans;
+    size_t ev_used = 0;
+    ~rtcuda_scene() {
+        for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
+    }
 };
 
 namespace {
@@ -548,11 +556,32 @@ void ensure_wave(rtcuda_scene* s, uint32_t capacity, uint32_t shadow_k, uint32_t
     s->stats_dev.ensure(STAT_TOTAL);
 }
 
+enum { CLS_EXTEND = 0, CLS_SHADE = 1, CLS_SHADOW = 2, CLS_OTHER = 3, CLS_COUNT = 4 };
+
+size_t record_event(rtcuda_scene* s) {
+    if (s->ev_used == s->ev_pool.size()) {
+        cudaEvent_t e;
+        CK(cudaEventCreate(&e));
+        s->ev_pool.push_back(e);
+    }
+    CK(cudaEventRecord(s->ev_pool[s->ev_used], s->ctx->stream));
+    return s->ev_used++;
+}
+struct SpanGuard {  // times one launch when kernel timing is on
+    rtcuda_scene* s;
+    int cls;
+    size_t e0 = 0;
+    bool on;
+    SpanGuard(rtcuda_scene* s_, int cls_, bool on_) : s(s_), cls(cls_), on(on_) { if (on) e0 = record_event(s); }
+    ~SpanGuard() noexcept(false) { if (on) s->spans.push_back({cls, e0, record_event(s)}); }
+};
+
 // One batch of the wavefront: raygen, then per bounce extend -> shade -> shadow. All launches are sized by
 // the batch (an upper bound); kernels read the live queue length from device counters, so the host never
 // synchronises inside a batch.
 void run_batch(rtcuda_scene* s, const RenderParams& rp, Wave w, uint32_t n_paths, bool collect) {
     cudaStream_t st = s->ctx->stream;
+    const bool timing = (s->ctx->bs.collect_stats & RTCUDA_STATS_KERNEL_TIMES) != 0;
     const uint32_t max_depth = rp.max_ray_depth;
     uint32_t* rays = s->counters.p;                       // rays[d]: queue length at depth d
     uint32_t* shadows = s->counters.p + (max_depth + 3);  // shadows[d]
@@ -561,16 +590,16 @@ void run_batch(rtcuda_scene* s, const RenderParams& rp, Wave w, uint32_t n_paths
     w.ray_o_out = s->ray_o[0].p;
     w.ray_d_out = s->ray_d[0].p;
     w.n_out = rays;
-    launch_raygen(st, s->sc, rp, w, n_paths, s->lc);
+    { SpanGuard g(s, CLS_OTHER, timing); launch_raygen(st, s->sc, rp, w, n_paths, s->lc); }
     for (uint32_t depth = 0; depth <= max_depth; depth++) {
         const int in = depth & 1, out = in ^ 1;
         w.depth = depth;
         w.ray_o_in = s->ray_o[in].p; w.ray_d_in = s->ray_d[in].p;
         w.ray_o_out = s->ray_o[out].p; w.ray_d_out = s->ray_d[out].p;
         w.n_in = rays + depth; w.n_out = rays + depth + 1; w.n_shadow = shadows + depth;
-        launch_extend(st, s->sc, w, n_paths, depth == 0 ? s->sc.camera.near_clip : 0.0001f, collect, s->lc);
-        launch_shade(st, s->sc, rp, w, n_paths, s->lc);
-        if (depth < max_depth && w.shadow_k) launch_shadow(st, s->sc, w, n_paths, collect, s->lc);
+        { SpanGuard g(s, CLS_EXTEND, timing); launch_extend(st, s->sc, w, n_paths, depth == 0 ? s->sc.camera.near_clip : 0.0001f, collect, s->lc); }
+        { SpanGuard g(s, CLS_SHADE, timing); launch_shade(st, s->sc, rp, w, n_paths, s->lc); }
+        if (depth < max_depth && w.shadow_k) { SpanGuard g(s, CLS_SHADOW, timing); launch_shadow(st, s->sc, w, n_paths, collect, s->lc); }
     }
 }
 
@@ -580,7 +609,9 @@ void render_device(rtcuda_scene* s, const rtcuda_settings* settings, const rtcud
     REQUIRE(settings->samples_per_pixel >= 1, "samples_per_pixel must be >= 1");
     if (settings->sampler_kind == RTCUDA_SAMPLER_STRATIFIED) REQUIRE(settings->x_strata >= 1 && settings->y_strata >= 1, "strata must be >= 1");
     const RenderParams rp = make_params(settings);
-    const bool collect = s->ctx->bs.collect_stats != 0;
+    const bool collect = (s->ctx->bs.collect_stats & RTCUDA_STATS_COUNTERS) != 0;
+    s->spans.clear();
+    s->ev_used = 0;
     if (!s->pixel_list.p) build_pixel_list(s);
     const uint32_t np_all = s->n_my_pixels;
     const size_t npix_img = (size_t)s->width * s->height;
@@ -657,10 +688,26 @@ void render_device(rtcuda_scene* s, const rtcuda_settings* settings, const rtcud
     s->stats.bounce_rays = h_stats[STAT_BOUNCE];
     s->stats.shadow_rays = h_stats[STAT_SHADOW];
     s->stats.aov_rays = h_stats[STAT_AOV];
-    s->stats.nodes_fetched = h_stats[STAT_NODES];
-    s->stats.prims_fetched = h_stats[STAT_PRIMS];
+    s->stats.extend_nodes = h_stats[STAT_EXT_NODES];
+    s->stats.extend_prims = h_stats[STAT_EXT_PRIMS];
+    s->stats.shadow_nodes = h_stats[STAT_SH_NODES];
+    s->stats.shadow_prims = h_stats[STAT_SH_PRIMS];
+    s->stats.nodes_fetched = h_stats[STAT_EXT_NODES] + h_stats[STAT_SH_NODES] + h_stats[STAT_AOV_NODES];
+    s->stats.prims_fetched = h_stats[STAT_EXT_PRIMS] + h_stats[STAT_SH_PRIMS] + h_stats[STAT_AOV_PRIMS];
+    s->stats.shaded_vertices = h_stats[STAT_SHADED];
     s->stats.kernel_launches = s->lc.launches - launches0;
     s->stats.render_ms = ms;
+    double cls_ms[CLS_COUNT] = {0, 0, 0, 0};
+    uint64_t cls_n[CLS_COUNT] = {0, 0, 0, 0};
+    for (const rtcuda_scene::Span& sp : s->spans) {
+        float t = 0;
+        CK(cudaEventElapsedTime(&t, s->ev_pool[sp.e0], s->ev_pool[sp.e1]));
+        cls_ms[sp.cls] += t;
+        cls_n[sp.cls]++;
+    }
+    s->stats.extend_ms = cls_ms[CLS_EXTEND]; s->stats.shade_ms = cls_ms[CLS_SHADE]; s->stats.shadow_ms = cls_ms[CLS_SHADOW];
+    s->stats.other_ms = cls_ms[CLS_OTHER];
+    s->stats.extend_launches = cls_n[CLS_EXTEND]; s->stats.shade_launches = cls_n[CLS_SHADE]; s->stats.shadow_launches = cls_n[CLS_SHADOW];
 }
 
 template <typename T>
@@ -719,6 +766,8 @@ void render_pixel(rtcuda_scene* s, const rtcuda_settings* settings, uint32_t x, 
     w.stats = s->stats_dev.p;
     w.shadow_k = shadow_k; w.shadow_queue = s->shadow_queue.p; w.shadow_point = s->shadow_point.p;
     w.shadow_origin = s->shadow_origin.p; w.shadow_contrib = s->shadow_contrib.p;
+    s->spans.clear();
+    s->ev_used = 0;
     run_batch(s, rp, w, n, false);
     launch_pixel_radiance(st, s->radiance.p, n, s->pixel_out.p, s->lc);
     static_assert(sizeof(PixelOut) == sizeof(rtcuda_pixel_output), "pixel output layout");

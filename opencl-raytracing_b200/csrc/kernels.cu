@@ -57,8 +57,8 @@ __global__ void __launch_bounds__(BLOCK) k_extend(SceneD sc, Wave w, float t_min
     }
     if (q == 0) atomicAdd(&w.stats[w.depth == 0 ? STAT_PRIMARY : STAT_BOUNCE], (unsigned long long)n);
     if (STATS) {
-        warp_add_stat(&w.stats[STAT_NODES], ts.nodes);
-        warp_add_stat(&w.stats[STAT_PRIMS], ts.prims);
+        warp_add_stat(&w.stats[STAT_EXT_NODES], ts.nodes);
+        warp_add_stat(&w.stats[STAT_EXT_PRIMS], ts.prims);
     }
 }
 
@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(BLOCK) k_shade(SceneD sc, RenderParams rp, Wav
     o.n_shadow = 0;
     o.slot = 0;
     if (q < n) shade_body(q, sc, rp, w, o);
+    if (q == 0) atomicAdd(&w.stats[STAT_SHADED], (unsigned long long)n);
     const uint32_t rpos = block_push(o.continue_path, w.n_out, &s_count[0], &s_base[0]);
     if (o.continue_path) {
         w.ray_o_out[rpos] = make_float4(o.next.o.x, o.next.o.y, o.next.o.z, RT_INF);
@@ -94,8 +95,8 @@ __global__ void __launch_bounds__(BLOCK) k_shadow(SceneD sc, Wave w) {
     if (i < n) shadow_body<STATS>(i, sc, w, &ts, &n_rays);
     warp_add_stat(&w.stats[STAT_SHADOW], n_rays);
     if (STATS) {
-        warp_add_stat(&w.stats[STAT_NODES], ts.nodes);
-        warp_add_stat(&w.stats[STAT_PRIMS], ts.prims);
+        warp_add_stat(&w.stats[STAT_SH_NODES], ts.nodes);
+        warp_add_stat(&w.stats[STAT_SH_PRIMS], ts.prims);
     }
 }
 
@@ -125,8 +126,8 @@ __global__ void __launch_bounds__(BLOCK) k_aov(SceneD sc, RenderParams rp, const
     if (i < n) aov_body<STATS>(i, sc, rp, pixel_list, pl, &ts);
     if (i == 0) atomicAdd(&stats[STAT_AOV], (unsigned long long)n);
     if (STATS) {
-        warp_add_stat(&stats[STAT_NODES], ts.nodes);
-        warp_add_stat(&stats[STAT_PRIMS], ts.prims);
+        warp_add_stat(&stats[STAT_AOV_NODES], ts.nodes);
+        warp_add_stat(&stats[STAT_AOV_PRIMS], ts.prims);
     }
 }
 

@@ -1,0 +1,109 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/rtcuda.h declares (no compute
+calls without a GPU), ctypes mirrors match the compiled struct sizes, scene importers, host vocabulary."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_scene
+
+
+def declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "rtcuda.h")).read()
+    return sorted(set(re.findall(r"RTCUDA_API\s+[\w\s\*]+?\b(rtcuda_\w+)\s*\(", hdr)))
+
+
+def test_header_declares_the_binding_surface(rc):
+    assert declared_symbols() == sorted(rc._ffi.EXPORTED_SYMBOLS)
+
+
+def test_library_exports_every_declared_symbol(rc):
+    path = rc._ffi.LIB_PATH
+    assert os.path.exists(path), "libraytracing_cuda.so is not built: run __graft_entry__.build()"
+    lib = C.CDLL(path)
+    for sym in declared_symbols():
+        assert hasattr(lib, sym), sym
+
+
+def test_abi_struct_sizes_match_ctypes(rc):
+    lib = rc._ffi.load_library()   # raises on version / size mismatch
+    sizes = (C.c_uint32 * 32)()
+    n = lib.rtcuda_abi_struct_sizes(sizes, 32)
+    assert n == len(rc._ffi.ABI_STRUCTS)
+    assert lib.rtcuda_abi_version() == rc._ffi.ABI_VERSION
+
+
+def test_no_cpu_fallback_without_device(rc):
+    """Without a GPU the backend must fail loudly (NO_DEVICE), never render on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(rc._ffi.RtCudaError, match="NO_DEVICE"):
+        rc.render(rc.test_scenes.sphere_scene(), rc.RaytracerSettings(outputs=rc.AovFlags.NORMALS))
+
+
+def test_missing_library_fails_loudly(rc, tmp_path):
+    with pytest.raises(rc._ffi.RtCudaError, match="no CPU fallback"):
+        rc._ffi.load_library(str(tmp_path / "libraytracing_cuda.so"))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "opencl-raytracing_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".h", ".cu", ".cuh", ".cpp")):
+                src = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle_py" not in src and "liboracle" not in src and "hostsim" not in src.replace("tests/hostsim", ""), f
+
+
+def test_default_settings_match_reference(rc):
+    s = rc.RaytracerSettings()   # renderer/mod.rs:100-117
+    assert (s.max_ray_depth, s.accumulate_bounces, s.light_sample_count, s.samples_per_pixel, s.seed) == (8, True, 4, 32, None)
+    assert s.sampler.kind == "independent" and s.outputs == rc.AovFlags.BEAUTY
+    assert int(rc.AovFlags.FIRST_HIT_AOVS) == 2 | 4 | 8 | 16
+
+
+def test_gltf_fixture_facts():
+    cb = load_scene("cb")
+    assert (cb.camera.raster_width, cb.camera.raster_height) == (1066, 600)   # (600 * 1.7777778) as usize
+    assert cb.triangle_count() == 12 and len(cb.instances) == 6 and len(cb.lights) == 1
+    assert cb.lights[0].b == (1.0, 1.0, 1.0)   # emissive_factor only; emissive_strength ignored (scene.rs:411)
+    bun = load_scene("cbbunny_area_light_transforms", 1920, 1080)
+    assert bun.triangle_count() == 28588 and (bun.camera.raster_width, bun.camera.raster_height) == (1920, 1080)
+    tex = load_scene("cb_texture")
+    assert tex.triangle_count() == 972 and tex.images[0].shape == (461, 530, 3)
+    assert tex.textures[0].filter == 2 and tex.textures[0].wrap == 0   # trilinear / repeat
+
+
+def test_camera_matrices_are_consistent(rc):
+    cam = rc.test_scenes.sphere_scene().camera
+    ident = cam.raster_to_camera.forward.astype(np.float64) @ cam.raster_to_camera.inverse.astype(np.float64)
+    assert np.allclose(ident, np.eye(4), atol=1e-4)
+    # raster centre looks down -z towards the sphere
+    p = cam.raster_to_camera.apply_point([200.0, 200.0, 0.0])
+    assert abs(p[0]) < 1e-4 and abs(p[1]) < 1e-4
+
+
+def test_scene_desc_round_trip(rc):
+    sc = load_scene("cbbunny_area_light_transforms")
+    h = sc.to_desc()
+    d = h.desc
+    assert d.tri_count == 28588 and d.instance_count == 7 and d.light_count == 1
+    assert d.shapes[d.lights[0].shape].area_light == 0
+
+
+def test_tile_owner_map(rc):
+    m = rc.multi_gpu.tile_owner_map(200, 130, 3)
+    assert m.shape == (130, 200) and m[0, 0] == 0 and m[0, 64] == 1 and m[0, 128] == 2 and m[64, 0] == (4 % 3)
+
+
+def test_synthetic_mesh_generator(rc):
+    m = rc.test_scenes.procedural_sphere_mesh(64, 32)
+    assert m.vertices.shape == (65 * 33, 3) and m.tris.shape[0] == 2 * 64 * 32 - 2 * 64
+    r = np.linalg.norm(m.vertices, axis=1)
+    assert r.min() > 0.44 and r.max() < 0.56
+    assert np.allclose(np.linalg.norm(m.normals, axis=1), 1.0, atol=1e-4)
+    m2 = rc.test_scenes.procedural_sphere_mesh(64, 32)
+    assert np.array_equal(m.vertices, m2.vertices)

@@ -1,0 +1,145 @@
+"""CPU parity of the CUDA library's per-thread kernel bodies (compiled for the host, tests/hostsim) against
+the oracle. This is how the builder / traversal / shading logic is exercised in the GPU-less build container;
+the `-m gpu` tests repeat the same comparisons through libraytracing_cuda.so on a B200."""
+import numpy as np
+import pytest
+
+from conftest import load_scene, bunny_mesh
+from parity import assert_first_hit_parity, luminance, beauty_close
+
+A = None
+
+
+@pytest.fixture(autouse=True)
+def _flags(rc):
+    global A
+    A = rc.AovFlags
+
+
+def dbg():
+    return A.NORMALS | A.UV_COORDS | A.ALBEDO | A.MIP_LEVEL | A.DEBUG_IDS | A.DEBUG_DEPTH
+
+
+def test_sphere_c1(rc, oracle, hostsim):
+    sc = rc.test_scenes.sphere_scene()
+    st = rc.RaytracerSettings(outputs=dbg(), samples_per_pixel=4, max_ray_depth=5)
+    out, stats = hostsim.render(sc, st)
+    ref, _ = oracle.render(sc, st)
+    assert stats["aov_rays"] == 160000
+    assert_first_hit_parity(out, ref)
+
+
+@pytest.mark.parametrize("name", ["cube", "cube_orthographic"])
+def test_builtin_normals(rc, oracle, hostsim, name):
+    t = [t for t in rc.test_scenes.all_test_scenes() if t.name == name][0]
+    sc, st = t.scene_func(), t.settings_func()
+    st.outputs = dbg()
+    out, _ = hostsim.render(sc, st)
+    ref, _ = oracle.render(sc, st)
+    assert_first_hit_parity(out, ref)
+
+
+@pytest.mark.parametrize("name,w,h,spp,ls", [("cb", 96, 96, 8, 1), ("cbbunny_area_light_transforms", 96, 54, 4, 4),
+                                             ("cbbunny_area_light", 96, 54, 2, 2), ("cb_texture", 96, 54, 4, 4),
+                                             ("checker", 96, 54, 2, 1), ("cbbunny", 64, 36, 2, 1)])
+def test_gltf_scenes(rc, oracle, hostsim, name, w, h, spp, ls):
+    sc = load_scene(name, w, h)
+    st = rc.RaytracerSettings(outputs=dbg() | A.BEAUTY, samples_per_pixel=spp, light_sample_count=ls)
+    out, stats = hostsim.render(sc, st, capacity=4096)   # several batches: exercises pixel / sample chunking
+    ref, ostats = oracle.render(sc, st, num_threads=4)
+    assert stats["bvh_node_count"] != 0xdeadbeef
+    assert_first_hit_parity(out, ref)
+    assert stats["primary_rays"] == ostats["primary_rays"]
+    assert abs(stats["bounce_rays"] - ostats["bounce_rays"]) <= max(4, ostats["bounce_rays"] // 2000)
+    # same sampler streams => the two renders follow the same paths up to float rounding
+    la, lb = luminance(out.beauty), luminance(ref.beauty)
+    assert abs(la.mean() - lb.mean()) <= 2e-3 * lb.mean() + 1e-7
+    assert beauty_close(out.beauty, ref.beauty)
+
+
+@pytest.mark.parametrize("name", ["checkered_plane", "dielectric", "metal", "rough_metal", "rough_dielectric", "out_of_focus_sphere"])
+def test_builtin_materials_and_cameras(rc, oracle, hostsim, name):
+    t = [t for t in rc.test_scenes.all_test_scenes() if t.name == name][0]
+    sc, st = t.scene_func(), t.settings_func()
+    if name != "checkered_plane":
+        sc.camera = type(sc.camera).lookat_camera_thin_lens_perspective((0, 0, 0), (0, 0, -5), (0, 1, 0), False, 0.7853982, 64, 64, 0.1, 3.0) \
+            if name == "out_of_focus_sphere" else _small_cornell_camera(rc)
+    if st.sampler.kind != "stratified":
+        st.samples_per_pixel = min(st.samples_per_pixel, 4)
+    st.outputs = dbg() | A.BEAUTY
+    out, stats = hostsim.render(sc, st)
+    ref, ostats = oracle.render(sc, st, num_threads=4)
+    assert_first_hit_parity(out, ref)
+    la, lb = luminance(out.beauty), luminance(ref.beauty)
+    assert np.isnan(la).sum() == np.isnan(lb).sum()
+    assert abs(np.nanmean(la) - np.nanmean(lb)) <= 5e-3 * abs(np.nanmean(lb)) + 1e-7
+
+
+def _small_cornell_camera(rc):
+    import math
+    return rc.Camera.lookat_camera_perspective((0.0, 1.0 + 3.4, 0.4), (0, 0, 0.75), (0, 0, 1), False,
+                                               float(np.float32(37.8) * np.float32(math.pi / 180)), 64, 64)
+
+
+def test_coated_diffuse_bunny(rc, oracle, hostsim):
+    sc = rc.test_scenes.coated_diffuse_bunny_scene(bunny=bunny_mesh())
+    sc.camera = _small_cornell_camera(rc)
+    st = rc.RaytracerSettings(outputs=dbg() | A.BEAUTY, samples_per_pixel=1, max_ray_depth=3, light_sample_count=1)
+    out, _ = hostsim.render(sc, st)
+    ref, _ = oracle.render(sc, st, num_threads=8)
+    assert_first_hit_parity(out, ref)
+    la, lb = luminance(out.beauty), luminance(ref.beauty)
+    assert abs(np.nanmean(la) - np.nanmean(lb)) <= 2e-2 * abs(np.nanmean(lb))
+
+
+def test_environment_light(rc, oracle, hostsim):
+    sc = rc.test_scenes.environment_lighting_scene(rc.test_scenes.synthetic_environment_map())
+    # slightly off-axis: with the reference's axis-aligned view the cube face's diagonal runs exactly through
+    # pixel centres, and which of the two triangles owns an edge hit is a BVH-order tie
+    sc.camera = rc.Camera.lookat_camera_perspective((0.013, 0, 0.007), (0.1, 1, 0.05), (0, 0, 1), False, 0.66, 64, 64)
+    st = rc.RaytracerSettings(outputs=dbg() | A.BEAUTY, samples_per_pixel=4)
+    out, _ = hostsim.render(sc, st)
+    ref, _ = oracle.render(sc, st, num_threads=4)
+    assert_first_hit_parity(out, ref)
+    assert np.abs(out.beauty - ref.beauty).max() <= 1e-3
+
+
+def test_stratified_sampler(rc, oracle, hostsim):
+    sc = load_scene("cb", 64, 64)
+    st = rc.RaytracerSettings(outputs=A.BEAUTY, samples_per_pixel=9, light_sample_count=2, sampler=rc.Sampler.stratified(True, 3, 3))
+    out, _ = hostsim.render(sc, st)
+    ref, _ = oracle.render(sc, st, num_threads=4)
+    assert beauty_close(out.beauty, ref.beauty)
+    st2 = rc.RaytracerSettings(outputs=A.BEAUTY, samples_per_pixel=9, light_sample_count=2, sampler=rc.Sampler.stratified(False, 3, 3))
+    out2, _ = hostsim.render(sc, st2)
+    ref2, _ = oracle.render(sc, st2, num_threads=4)
+    assert beauty_close(out2.beauty, ref2.beauty)
+
+
+def test_settings_variants(rc, oracle, hostsim):
+    sc = load_scene("cb", 48, 48)
+    for kw in (dict(max_ray_depth=1), dict(max_ray_depth=3, accumulate_bounces=False), dict(seed=7), dict(antialias_primary_rays=False)):
+        st = rc.RaytracerSettings(outputs=A.BEAUTY, samples_per_pixel=4, light_sample_count=1, **kw)
+        out, _ = hostsim.render(sc, st)
+        ref, _ = oracle.render(sc, st, num_threads=4)
+        assert beauty_close(out.beauty, ref.beauty), kw
+        assert abs(out.beauty.mean() - ref.beauty.mean()) <= 2e-3 * ref.beauty.mean() + 1e-8, kw
+
+
+def test_tile_partition_sums_to_full_frame(rc, hostsim):
+    sc = load_scene("cb", 160, 130)
+    st = rc.RaytracerSettings(outputs=A.BEAUTY | A.NORMALS, samples_per_pixel=2, light_sample_count=1)
+    full, _ = hostsim.render(sc, st)
+    parts = [hostsim.render(sc, st, tile_rank=r, tile_world=3)[0] for r in range(3)]
+    owner = rc.multi_gpu.tile_owner_map(160, 130, 3)
+    for r, p in enumerate(parts):
+        assert (p.beauty[owner != r] == 0).all()
+    assert np.array_equal(sum(p.beauty for p in parts), full.beauty)
+    assert np.array_equal(sum(p.normals for p in parts), full.normals)
+
+
+def test_empty_scene(rc, hostsim):
+    b = rc.SceneBuilder()
+    b.add_camera(rc.Camera.lookat_camera_perspective((0, 0, 0), (0, 0, -1), (0, 1, 0), False, 0.7, 32, 32))
+    out, _ = hostsim.render(b.build(), rc.RaytracerSettings(outputs=A.BEAUTY | A.NORMALS, samples_per_pixel=2))
+    assert (out.beauty == 0).all() and (out.normals == 0).all()

@@ -7,15 +7,21 @@ HDRS := $(wildcard $(CSRC)/*.h) $(CSRC)/kernels.cuh include/rtcuda.h
 
 all: $(PKG)/libraytracing_cuda.so oracle/liboracle.so tests/hostsim/libhostsim.so
 
+# wavefront kernels: FMA contraction on, 2-ulp division / sqrt (the beauty plane is gated statistically; the
+# strict-tolerance AOV kernels live in kernels_aov.cu and keep IEEE division, sqrt and unfused multiply-add)
 build/kernels.o: $(CSRC)/kernels.cu $(HDRS)
 	@mkdir -p build
-	$(NVCC) $(NVCCFLAGS) -c $< -o $@
+	$(NVCC) $(NVCCFLAGS) -prec-div=false -prec-sqrt=false -c $< -o $@
+
+build/kernels_aov.o: $(CSRC)/kernels_aov.cu $(HDRS)
+	@mkdir -p build
+	$(NVCC) $(NVCCFLAGS) -fmad=false -c $< -o $@
 
 build/api.o: $(CSRC)/api.cu $(HDRS)
 	@mkdir -p build
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@
 
-$(PKG)/libraytracing_cuda.so: build/kernels.o build/api.o
+$(PKG)/libraytracing_cuda.so: build/kernels.o build/kernels_aov.o build/api.o
 	$(NVCC) -shared -o $@ $^ -lcudart_static -lrt -lpthread -ldl
 
 oracle/liboracle.so: oracle/oracle.cpp include/rtcuda.h

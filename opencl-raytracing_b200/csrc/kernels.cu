@@ -117,37 +117,6 @@ __global__ void __launch_bounds__(BLOCK) k_finalize(const uint32_t* pixel_list, 
     beauty[3 * idx + 2] = a.z * inv_spp;
 }
 
-template <bool STATS>
-__global__ void __launch_bounds__(BLOCK) k_aov(SceneD sc, RenderParams rp, const uint32_t* pixel_list, uint32_t n, AovPlanes pl,
-                                                unsigned long long* stats) {
-    const uint32_t i = blockIdx.x * BLOCK + threadIdx.x;
-    TraverseStats ts;
-    ts.nodes = ts.prims = 0;
-    if (i < n) aov_body<STATS>(i, sc, rp, pixel_list, pl, &ts);
-    if (i == 0) atomicAdd(&stats[STAT_AOV], (unsigned long long)n);
-    if (STATS) {
-        warp_add_stat(&stats[STAT_AOV_NODES], ts.nodes);
-        warp_add_stat(&stats[STAT_AOV_PRIMS], ts.prims);
-    }
-}
-
-__global__ void k_pixel_aov(SceneD sc, RenderParams rp, uint32_t x, uint32_t y, uint32_t lo, uint32_t n, PixelOut* out) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    TraverseStats ts;
-    FirstHit fh = first_hit<false>(sc, rp, x, y, lo + i, &ts);
-    PixelOut& o = out[i];
-    o.sample_index = lo + i;
-    o.hit = fh.hit ? 1u : 0u;
-    o.uv[0] = fh.uv.x; o.uv[1] = fh.uv.y;
-    o.normal[0] = fh.normal.x; o.normal[1] = fh.normal.y; o.normal[2] = fh.normal.z;
-}
-__global__ void k_pixel_radiance(const float4* radiance, uint32_t n, PixelOut* out) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    out[i].radiance[0] = radiance[i].x; out[i].radiance[1] = radiance[i].y; out[i].radiance[2] = radiance[i].z;
-}
-
 void launch_raygen(cudaStream_t st, const SceneD& sc, const RenderParams& rp, const Wave& w, uint32_t n, LaunchCounter& lc) {
     k_raygen<<<grid_for(n), BLOCK, 0, st>>>(sc, rp, w, n);
     lc.launches++;
@@ -173,21 +142,6 @@ void launch_resolve(cudaStream_t st, const Wave& w, float4* accum, LaunchCounter
 void launch_finalize(cudaStream_t st, const uint32_t* pixel_list, uint32_t n_pixels, uint32_t width, const float4* accum, float inv_spp,
                      float* beauty, LaunchCounter& lc) {
     k_finalize<<<grid_for(n_pixels), BLOCK, 0, st>>>(pixel_list, n_pixels, width, accum, inv_spp, beauty);
-    lc.launches++;
-}
-void launch_aov(cudaStream_t st, const SceneD& sc, const RenderParams& rp, const uint32_t* pixel_list, uint32_t n_pixels,
-                const AovPlanes& planes, unsigned long long* stats, bool collect, LaunchCounter& lc) {
-    if (collect) k_aov<true><<<grid_for(n_pixels), BLOCK, 0, st>>>(sc, rp, pixel_list, n_pixels, planes, stats);
-    else k_aov<false><<<grid_for(n_pixels), BLOCK, 0, st>>>(sc, rp, pixel_list, n_pixels, planes, stats);
-    lc.launches++;
-}
-void launch_pixel_aov(cudaStream_t st, const SceneD& sc, const RenderParams& rp, uint32_t x, uint32_t y, uint32_t sample_lo, uint32_t n,
-                      PixelOut* out, LaunchCounter& lc) {
-    k_pixel_aov<<<grid_for(n, 64), 64, 0, st>>>(sc, rp, x, y, sample_lo, n, out);
-    lc.launches++;
-}
-void launch_pixel_radiance(cudaStream_t st, const float4* radiance, uint32_t n, PixelOut* out, LaunchCounter& lc) {
-    k_pixel_radiance<<<grid_for(n, 64), 64, 0, st>>>(radiance, n, out);
     lc.launches++;
 }
 

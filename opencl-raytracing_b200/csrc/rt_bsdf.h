@@ -454,8 +454,18 @@ struct Surface {
     Layered l;
 };
 RT_HD bool surface_is_delta(const Surface& s) { return !s.layered && bsdf_is_delta(s.b); }
-RT_HD V3 surface_eval(const Surface& s, V3 wo, V3 wi) { return s.layered ? layered_eval(s.l, wo, wi) : bsdf_eval(s.b, wo, wi); }
+// Diffuse (the only material the glTF importer produces, scene.rs:406-407) is evaluated inline; everything
+// else goes through the out-of-line general BSDF code.
+RT_HD V3 surface_eval(const Surface& s, V3 wo, V3 wi) {
+    if (!s.layered && s.b.kind == B_DIFFUSE) return wo.z * wi.z < 0.0f ? mk3(0.0f) : s.b.albedo / PI;
+    return s.layered ? layered_eval(s.l, wo, wi) : bsdf_eval(s.b, wo, wi);
+}
 RT_HD int surface_sample(const Surface& s, V3 wo, Sampler& smp, BsdfSample& out) {
+    if (!s.layered && s.b.kind == B_DIFFUSE) {
+        V3 wi = sample_cosine_hemisphere(smp.uniform2());
+        out.wi = wi; out.f = s.b.albedo / PI; out.pdf = wi.z / PI; out.component = NONSPEC_REFL;
+        return validate_sample(out);
+    }
     return s.layered ? layered_sample(s.l, wo, smp, out) : bsdf_sample(s.b, wo, ALL_COMPONENTS, smp, out);
 }
 
@@ -466,7 +476,7 @@ RT_HD void zero_bsdf(Bsdf& b) {
 }
 
 // CpuMaterial::get_bsdf, materials.rs:823-955
-RT_HD_CALL void get_surface(const SceneD& sc, const MaterialD& m, const MatCtx& c, Surface& out) {
+RT_HD void get_surface(const SceneD& sc, const MaterialD& m, const MatCtx& c, Surface& out) {
     out.layered = false;
     Bsdf& b = out.b;
     zero_bsdf(b);

@@ -115,7 +115,7 @@ struct HitInfo {  // accel.rs:13-25 (+ ids for the debug planes)
 
 // intersect_shape + ray_mesh_intersect / ray_sphere_intersect + the identity local_to_root step of
 // traverse_bvh (accel.rs:144-164), from the (t, prim, u, v) record the traversal kernel wrote.
-RT_HD_CALL void reconstruct_hit(const SceneD& sc, V3 o, V3 d, const Hit& h, bool need_derivs, HitInfo& out) {
+RT_HD void reconstruct_hit(const SceneD& sc, V3 o, V3 d, const Hit& h, bool need_derivs, HitInfo& out) {
     const Prim* pr = sc.prims + h.prim;
     const uint32_t geom = f2u(ldg(&pr->a).w), prim_id = f2u(ldg(&pr->b).w), kind = f2u(ldg(&pr->c).w);
     const Instance& inst = sc.instances[geom];
@@ -182,7 +182,7 @@ RT_HD_CALL void reconstruct_hit(const SceneD& sc, V3 o, V3 d, const Hit& h, bool
 }
 
 // materials.rs:715-796
-RT_HD_CALL MatCtx matctx_from_differentials(const HitInfo& hit, const Ray& ray, const RayDiff& rd) {
+RT_HD MatCtx matctx_from_differentials(const HitInfo& hit, const Ray& ray, const RayDiff& rd) {
     V3 n = hit.normal, p = hit.point;
     V3 rx_o = ray.o + rd.x_origin, rx_d = ray.d + rd.x_direction;
     V3 ry_o = ray.o + rd.y_origin, ry_d = ray.d + rd.y_direction;
@@ -212,7 +212,7 @@ RT_HD_CALL MatCtx matctx_from_differentials(const HitInfo& hit, const Ray& ray, 
 struct LightSample { V3 radiance; V3 origin; V3 dir; float distance, pdf; };
 
 // lights.rs:14-122 (quirks kept: object-space triangle area and normal, un-normalised dir_world in the cosine)
-RT_HD_CALL LightSample sample_light(const SceneD& sc, const LightD& l, V3 point, Sampler& s) {
+RT_HD LightSample sample_light(const SceneD& sc, const LightD& l, V3 point, Sampler& s) {
     LightSample ls;
     V3 a = mk3(l.a[0], l.a[1], l.a[2]), b = mk3(l.b[0], l.b[1], l.b[2]);
     if (l.kind == 0) {

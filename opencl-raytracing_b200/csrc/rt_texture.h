@@ -132,7 +132,12 @@ RT_HD V4 sample_texture(const SceneD& sc, uint32_t tex_id, const MatCtx& c) {
     }
 }
 constexpr int TEXTURE_NEST = 3;
-RT_HD_CALL V4 tex(const SceneD& sc, uint32_t tex_id, const MatCtx& c) { return sample_texture<TEXTURE_NEST>(sc, tex_id, c); }
+RT_HD_CALL V4 tex_general(const SceneD& sc, uint32_t tex_id, const MatCtx& c) { return sample_texture<TEXTURE_NEST>(sc, tex_id, c); }
+RT_HD V4 tex(const SceneD& sc, uint32_t tex_id, const MatCtx& c) {
+    const TextureD& tx = sc.textures[tex_id];
+    if (tx.kind == 1) return mk4(ldg(&tx.value[0]), ldg(&tx.value[1]), ldg(&tx.value[2]), ldg(&tx.value[3]));  // ConstantTexture inline
+    return tex_general(sc, tex_id, c);
+}
 
 RT_HD bool texture_mip_level(const SceneD& sc, uint32_t tex_id, const MatCtx& c, float& level) {  // texture.rs:461-480
     const TextureD& tx = sc.textures[tex_id];

@@ -552,7 +552,7 @@ void ensure_wave(rtcuda_scene* s, uint32_t capacity, uint32_t shadow_k, uint32_t
     s->shadow_point.ensure(capacity);
     s->shadow_origin.ensure((size_t)capacity * std::max(1u, shadow_k));
     s->shadow_contrib.ensure((size_t)capacity * std::max(1u, shadow_k));
-    s->counters.ensure(2 * ((size_t)max_depth + 3));
+    s->counters.ensure(4 * ((size_t)max_depth + 3));
     s->stats_dev.ensure(STAT_TOTAL);
 }
 
@@ -585,7 +585,9 @@ void run_batch(rtcuda_scene* s, const RenderParams& rp, Wave w, uint32_t n_paths
     const uint32_t max_depth = rp.max_ray_depth;
     uint32_t* rays = s->counters.p;                       // rays[d]: queue length at depth d
     uint32_t* shadows = s->counters.p + (max_depth + 3);  // shadows[d]
-    CK(cudaMemsetAsync(s->counters.p, 0, 2 * ((size_t)max_depth + 3) * 4, st));
+    uint32_t* fetch_ext = s->counters.p + 2 * (max_depth + 3);  // work-fetch cursors of the persistent kernels
+    uint32_t* fetch_sh = s->counters.p + 3 * (max_depth + 3);
+    CK(cudaMemsetAsync(s->counters.p, 0, 4 * ((size_t)max_depth + 3) * 4, st));
     w.depth = 0;
     w.ray_o_out = s->ray_o[0].p;
     w.ray_d_out = s->ray_d[0].p;
@@ -597,9 +599,9 @@ void run_batch(rtcuda_scene* s, const RenderParams& rp, Wave w, uint32_t n_paths
         w.ray_o_in = s->ray_o[in].p; w.ray_d_in = s->ray_d[in].p;
         w.ray_o_out = s->ray_o[out].p; w.ray_d_out = s->ray_d[out].p;
         w.n_in = rays + depth; w.n_out = rays + depth + 1; w.n_shadow = shadows + depth;
-        { SpanGuard g(s, CLS_EXTEND, timing); launch_extend(st, s->sc, w, n_paths, depth == 0 ? s->sc.camera.near_clip : 0.0001f, collect, s->lc); }
+        { SpanGuard g(s, CLS_EXTEND, timing); launch_extend(st, s->sc, w, n_paths, depth == 0 ? s->sc.camera.near_clip : 0.0001f, fetch_ext + depth, collect, s->lc); }
         { SpanGuard g(s, CLS_SHADE, timing); launch_shade(st, s->sc, rp, w, n_paths, s->lc); }
-        if (depth < max_depth && w.shadow_k) { SpanGuard g(s, CLS_SHADOW, timing); launch_shadow(st, s->sc, w, n_paths, collect, s->lc); }
+        if (depth < max_depth && w.shadow_k) { SpanGuard g(s, CLS_SHADOW, timing); launch_shadow(st, s->sc, w, n_paths, fetch_sh + depth, collect, s->lc); }
     }
 }
 

@@ -5,6 +5,8 @@
 // warp-ballot + block-aggregated queue compaction, and warp-reduced statistics.
 #include <cub/device/device_radix_sort.cuh>
 
+#include <algorithm>
+
 #include "kernels.cuh"
 
 namespace rt {
@@ -42,20 +44,51 @@ __global__ void __launch_bounds__(BLOCK) k_raygen(SceneD sc, RenderParams rp, Wa
     if (i < n) raygen_body(i, sc, rp, w);
 }
 
+// Persistent traversal kernels. A warp keeps pulling work from the launch's queue: whenever at least
+// REFILL_MIN lanes have finished their ray the idle lanes fetch new ones (one global atomic per refill), so
+// every step of the walk (one wide node + its leaf primitives) runs with nearly full warps even though the
+// rays of a bounce have wildly different traversal lengths (profiles/r1_notes.md: 7.3 of 32 lanes active
+// before this change). Every lane stays in the loop until the whole warp is out of work, which keeps the
+// full-mask ballots / shuffles legal.
+constexpr int REFILL_MIN = 8;
+
 template <bool STATS>
-__global__ void __launch_bounds__(BLOCK) k_extend(SceneD sc, Wave w, float t_min) {
+__global__ void __launch_bounds__(BLOCK) k_extend(SceneD sc, Wave w, float t_min, uint32_t* fetch_counter) {
     const uint32_t n = *w.n_in;
-    const uint32_t q = blockIdx.x * BLOCK + threadIdx.x;
-    if (blockIdx.x * BLOCK >= n) return;
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&w.stats[w.depth == 0 ? STAT_PRIMARY : STAT_BOUNCE], (unsigned long long)n);
+    uint2 stack_mem[TRAVERSE_STACK];
+    Traversal<false, STATS> tr;
+    tr.stack = stack_mem;
     TraverseStats ts;
     ts.nodes = ts.prims = 0;
-    if (q < n) {
-        const float4 o4 = w.ray_o_in[q], d4 = w.ray_d_in[q];
-        Hit h;
-        traverse<false, STATS>(sc, xyz(o4), xyz(d4), t_min, o4.w, h, &ts);
-        w.hits[q] = make_float4(h.t, u2f(h.prim), h.u, h.v);
+    bool have = false, exhausted = n == 0;
+    uint32_t q = 0;
+    for (;;) {
+        const unsigned need = __ballot_sync(FULL, !have);
+        if (need == FULL && exhausted) break;
+        if (!exhausted && __popc(need) >= REFILL_MIN) {
+            const int cnt = __popc(need), leader = __ffs(need) - 1;
+            uint32_t base = 0;
+            if ((int)lane == leader) base = atomicAdd(fetch_counter, (uint32_t)cnt);
+            base = __shfl_sync(FULL, base, leader);
+            if (!have) {
+                const uint32_t mine = base + (uint32_t)__popc(need & lt);
+                if (mine < n) {
+                    q = mine;
+                    const float4 o4 = w.ray_o_in[q], d4 = w.ray_d_in[q];
+                    have = tr.init(sc, xyz(o4), xyz(d4), t_min, o4.w);
+                    if (!have) w.hits[q] = make_float4(o4.w, u2f(NONE), 0.0f, 0.0f);
+                }
+            }
+            if (base + (uint32_t)cnt >= n) exhausted = true;
+        }
+        if (have && !tr.step(sc, &ts)) {
+            w.hits[q] = make_float4(tr.hit.t, u2f(tr.hit.prim), tr.hit.u, tr.hit.v);
+            have = false;
+        }
     }
-    if (q == 0) atomicAdd(&w.stats[w.depth == 0 ? STAT_PRIMARY : STAT_BOUNCE], (unsigned long long)n);
     if (STATS) {
         warp_add_stat(&w.stats[STAT_EXT_NODES], ts.nodes);
         warp_add_stat(&w.stats[STAT_EXT_PRIMS], ts.prims);
@@ -84,15 +117,70 @@ __global__ void __launch_bounds__(BLOCK) k_shade(SceneD sc, RenderParams rp, Wav
     if (o.n_shadow != 0) w.shadow_queue[spos] = o.slot;
 }
 
+// `occluded` (lights.rs:159-168) for every pending light sample of a path vertex. The work item is the vertex
+// (its <= K rays are walked one after the other by the same lane and their contributions added once, in order:
+// deterministic, no float atomics); lanes refill with new vertices like k_extend.
 template <bool STATS>
-__global__ void __launch_bounds__(BLOCK) k_shadow(SceneD sc, Wave w) {
+__global__ void __launch_bounds__(BLOCK) k_shadow(SceneD sc, Wave w, uint32_t* fetch_counter) {
     const uint32_t n = *w.n_shadow;
-    if (blockIdx.x * BLOCK >= n) return;
-    const uint32_t i = blockIdx.x * BLOCK + threadIdx.x;
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
+    uint2 stack_mem[TRAVERSE_STACK];
+    Traversal<true, STATS> tr;
+    tr.stack = stack_mem;
     TraverseStats ts;
     ts.nodes = ts.prims = 0;
-    uint32_t n_rays = 0;
-    if (i < n) shadow_body<STATS>(i, sc, w, &ts, &n_rays);
+    bool have = false, exhausted = n == 0;
+    uint32_t slot = 0, k = 0, j = 0, n_rays = 0;
+    V3 point = mk3(0.0f), sum = mk3(0.0f), contrib = mk3(0.0f);
+    // start the next ray of this vertex that needs an occlusion test; returns false when the vertex is finished
+    auto next_ray = [&]() -> bool {
+        while (j < k) {
+            const size_t e = (size_t)j * w.capacity + slot;
+            const float4 o4 = w.shadow_origin[e], c4 = w.shadow_contrib[e];
+            contrib = xyz(c4);
+            if (!(f2u(o4.w) & 1u)) {
+                const V3 origin = xyz(o4);
+                const V3 dir_world = point - origin;
+                const float d = length(dir_world);
+                n_rays++;
+                if (tr.init(sc, origin, dir_world / d, 0.001f, c4.w - 0.001f)) return true;
+            }
+            sum += contrib;  // never occluded (non-finite origin quirk, or an empty scene)
+            j++;
+        }
+        const float4 r = w.radiance[slot];
+        w.radiance[slot] = make_float4(r.x + sum.x, r.y + sum.y, r.z + sum.z, 0.0f);
+        return false;
+    };
+    for (;;) {
+        const unsigned need = __ballot_sync(FULL, !have);
+        if (need == FULL && exhausted) break;
+        if (!exhausted && __popc(need) >= REFILL_MIN) {
+            const int cnt = __popc(need), leader = __ffs(need) - 1;
+            uint32_t base = 0;
+            if ((int)lane == leader) base = atomicAdd(fetch_counter, (uint32_t)cnt);
+            base = __shfl_sync(FULL, base, leader);
+            if (!have) {
+                const uint32_t mine = base + (uint32_t)__popc(need & lt);
+                if (mine < n) {
+                    slot = w.shadow_queue[mine];
+                    const float4 p4 = w.shadow_point[slot];
+                    point = xyz(p4);
+                    k = f2u(p4.w);
+                    j = 0;
+                    sum = mk3(0.0f);
+                    have = next_ray();
+                }
+            }
+            if (base + (uint32_t)cnt >= n) exhausted = true;
+        }
+        if (have && !tr.step(sc, &ts)) {
+            if (!tr.found) sum += contrib;
+            j++;
+            have = next_ray();
+        }
+    }
     warp_add_stat(&w.stats[STAT_SHADOW], n_rays);
     if (STATS) {
         warp_add_stat(&w.stats[STAT_SH_NODES], ts.nodes);
@@ -121,18 +209,31 @@ void launch_raygen(cudaStream_t st, const SceneD& sc, const RenderParams& rp, co
     k_raygen<<<grid_for(n), BLOCK, 0, st>>>(sc, rp, w, n);
     lc.launches++;
 }
-void launch_extend(cudaStream_t st, const SceneD& sc, const Wave& w, uint32_t n_max, float t_min, bool stats, LaunchCounter& lc) {
-    if (stats) k_extend<true><<<grid_for(n_max), BLOCK, 0, st>>>(sc, w, t_min);
-    else k_extend<false><<<grid_for(n_max), BLOCK, 0, st>>>(sc, w, t_min);
+static uint32_t persistent_grid(const void* kernel, uint32_t n_max) {
+    static int sm_count = 0;
+    if (!sm_count) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    }
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, BLOCK, 0);
+    const uint32_t resident = (uint32_t)sm_count * (uint32_t)(per_sm > 0 ? per_sm : 1);
+    return std::max(1u, std::min(resident, grid_for(n_max)));
+}
+void launch_extend(cudaStream_t st, const SceneD& sc, const Wave& w, uint32_t n_max, float t_min, uint32_t* fetch_counter, bool stats,
+                   LaunchCounter& lc) {
+    if (stats) k_extend<true><<<persistent_grid((const void*)k_extend<true>, n_max), BLOCK, 0, st>>>(sc, w, t_min, fetch_counter);
+    else k_extend<false><<<persistent_grid((const void*)k_extend<false>, n_max), BLOCK, 0, st>>>(sc, w, t_min, fetch_counter);
     lc.launches++;
 }
 void launch_shade(cudaStream_t st, const SceneD& sc, const RenderParams& rp, const Wave& w, uint32_t n_max, LaunchCounter& lc) {
     k_shade<<<grid_for(n_max), BLOCK, 0, st>>>(sc, rp, w);
     lc.launches++;
 }
-void launch_shadow(cudaStream_t st, const SceneD& sc, const Wave& w, uint32_t n_max, bool stats, LaunchCounter& lc) {
-    if (stats) k_shadow<true><<<grid_for(n_max), BLOCK, 0, st>>>(sc, w);
-    else k_shadow<false><<<grid_for(n_max), BLOCK, 0, st>>>(sc, w);
+void launch_shadow(cudaStream_t st, const SceneD& sc, const Wave& w, uint32_t n_max, uint32_t* fetch_counter, bool stats, LaunchCounter& lc) {
+    if (stats) k_shadow<true><<<persistent_grid((const void*)k_shadow<true>, n_max), BLOCK, 0, st>>>(sc, w, fetch_counter);
+    else k_shadow<false><<<persistent_grid((const void*)k_shadow<false>, n_max), BLOCK, 0, st>>>(sc, w, fetch_counter);
     lc.launches++;
 }
 void launch_resolve(cudaStream_t st, const Wave& w, float4* accum, LaunchCounter& lc) {

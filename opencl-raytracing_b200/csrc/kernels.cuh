@@ -9,9 +9,10 @@ struct LaunchCounter { unsigned long long launches = 0; };
 
 // wavefront
 void launch_raygen(cudaStream_t st, const SceneD& sc, const RenderParams& rp, const Wave& w, uint32_t n, LaunchCounter& lc);
-void launch_extend(cudaStream_t st, const SceneD& sc, const Wave& w, uint32_t n_max, float t_min, bool stats, LaunchCounter& lc);
+void launch_extend(cudaStream_t st, const SceneD& sc, const Wave& w, uint32_t n_max, float t_min, uint32_t* fetch_counter, bool stats,
+                   LaunchCounter& lc);
 void launch_shade(cudaStream_t st, const SceneD& sc, const RenderParams& rp, const Wave& w, uint32_t n_max, LaunchCounter& lc);
-void launch_shadow(cudaStream_t st, const SceneD& sc, const Wave& w, uint32_t n_max, bool stats, LaunchCounter& lc);
+void launch_shadow(cudaStream_t st, const SceneD& sc, const Wave& w, uint32_t n_max, uint32_t* fetch_counter, bool stats, LaunchCounter& lc);
 void launch_resolve(cudaStream_t st, const Wave& w, float4* accum, LaunchCounter& lc);
 void launch_finalize(cudaStream_t st, const uint32_t* pixel_list, uint32_t n_pixels, uint32_t width, const float4* accum,
                      float inv_spp, float* beauty, LaunchCounter& lc);

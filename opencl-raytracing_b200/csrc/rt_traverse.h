@@ -65,25 +65,65 @@ RT_HD float safe_rcp_dir(float d) {
     return 1.0f / a;
 }
 
+// quantised plane byte k of word w as a float. On the device this is one PRMT building 2^23 + q in the
+// mantissa plus one FADD (exact); `(float)((w >> 8k) & 0xff)` compiles to I2F.U8, which issues on the
+// quarter-rate XU pipe and made the 48 conversions per node the limiter of both traversal kernels
+// (profiles/r1_notes.md: XU pipe 60-105 % busy).
+template <int K>
+RT_HD float qbyte(uint32_t w) {
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(__byte_perm(w, 0x4b000000u, 0x7440u + K)) - 8388608.0f;
+#else
+    return (float)((w >> (8 * K)) & 0xffu);
+#endif
+}
+
+// Traversal as a resumable per-ray state machine: `init` once, then `step` until it returns false. One step
+// visits ONE wide node (8 quantised slab tests) and intersects the primitives of the leaf children it hit.
+// The one-ray-per-thread kernels just loop (`traverse` below); the persistent kernels interleave steps with
+// warp-level ray refill so lanes whose ray ended do not idle while their neighbours walk a deep subtree.
 template <bool ANY_HIT, bool STATS>
-RT_HD bool traverse(const SceneD& sc, V3 o, V3 d, float t_min, float t_max, Hit& hit, TraverseStats* stats) {
-    hit.prim = NONE;
-    hit.t = t_max;
-    hit.u = hit.v = 0.0f;
-    if (sc.prim_count == 0) return false;
+struct Traversal {
+    V3 o, d, idir;
+    float t_min, closest;
+    uint32_t oct, octinv;
+    uint2 ngroup;
+    uint2* stack;  // TRAVERSE_STACK entries of thread-local memory owned by the caller (keeps the scalar state in registers)
+    int sp;
+    Hit hit;
+    bool found;
 
-    const V3 idir = mk3(safe_rcp_dir(d.x), safe_rcp_dir(d.y), safe_rcp_dir(d.z));
-    const uint32_t oct = (d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u);
-    const uint32_t octinv = 7u - oct;
+    RT_HD bool init(const SceneD& sc, V3 o_, V3 d_, float t_min_, float t_max_) {
+        o = o_; d = d_; t_min = t_min_; closest = t_max_;
+        hit.prim = NONE; hit.t = t_max_; hit.u = hit.v = 0.0f;
+        found = false;
+        sp = 0;
+        idir = mk3(safe_rcp_dir(d.x), safe_rcp_dir(d.y), safe_rcp_dir(d.z));
+        oct = (d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u);
+        octinv = 7u - oct;
+        ngroup = make_uint2(0u, 0x80000000u);  // root: "child 7^octinv of a group with base 0, imask 0"
+        return sc.prim_count != 0;
+    }
 
-    uint2 stack[TRAVERSE_STACK];
-    int sp = 0;
-    uint2 ngroup = make_uint2(0u, 0x80000000u);  // root: "child 7^octinv of a group with base 0, imask 0"
-    float closest = t_max;
-    bool found = false;
+    template <int I>
+    RT_HD void child(uint32_t meta_w, uint32_t nx_w, uint32_t fx_w, uint32_t ny_w, uint32_t fy_w, uint32_t nz_w, uint32_t fz_w,
+                     float ax, float ay, float az, float bx, float by, float bz, uint32_t& hitmask) const {
+        const uint32_t meta = (meta_w >> (8 * I)) & 0xffu;
+        if (meta == 0u) return;
+        const float tnx = qbyte<I>(nx_w) * ax + bx, tfx = qbyte<I>(fx_w) * ax + bx;
+        const float tny = qbyte<I>(ny_w) * ay + by, tfy = qbyte<I>(fy_w) * ay + by;
+        const float tnz = qbyte<I>(nz_w) * az + bz, tfz = qbyte<I>(fz_w) * az + bz;
+        const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, t_min));
+        const float tf = fminf(fminf(tfx, tfy), fminf(tfz, closest)) * 1.0000004f;
+        if (tn <= tf) {
+            const bool inner = (meta & 0x18u) == 0x18u;
+            hitmask |= (meta >> 5) << ((meta ^ (inner ? octinv : 0u)) & 0x1fu);
+        }
+    }
 
-    for (;;) {
-        uint2 tgroup = make_uint2(0u, 0u);
+    // precondition: ngroup has node hits. Returns true while more nodes remain.
+    RT_HD bool step(const SceneD& sc, TraverseStats* stats) {
+        uint2 tgroup;
         {
             const uint32_t hits = ngroup.y;
             const int bit = bfind32(hits);
@@ -111,26 +151,14 @@ RT_HD bool traverse(const SceneD& sc, V3 o, V3 d, float t_min, float t_max, Hit&
             const uint32_t nearz0 = nz ? hiz0 : loz0, nearz1 = nz ? hiz1 : loz1, farz0 = nz ? loz0 : hiz0, farz1 = nz ? loz1 : hiz1;
 
             uint32_t hitmask = 0;
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const int sh = (i & 3) * 8;
-                const uint32_t meta = ((i < 4 ? meta_lo : meta_hi) >> sh) & 0xffu;
-                if (meta == 0u) continue;
-                const float qnx = (float)(((i < 4 ? nearx0 : nearx1) >> sh) & 0xffu), qfx = (float)(((i < 4 ? farx0 : farx1) >> sh) & 0xffu);
-                const float qny = (float)(((i < 4 ? neary0 : neary1) >> sh) & 0xffu), qfy = (float)(((i < 4 ? fary0 : fary1) >> sh) & 0xffu);
-                const float qnz = (float)(((i < 4 ? nearz0 : nearz1) >> sh) & 0xffu), qfz = (float)(((i < 4 ? farz0 : farz1) >> sh) & 0xffu);
-                const float tnx = qnx * ax + bx, tfx = qfx * ax + bx;
-                const float tny = qny * ay + by, tfy = qfy * ay + by;
-                const float tnz = qnz * az + bz, tfz = qfz * az + bz;
-                const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, t_min));
-                const float tf = fminf(fminf(tfx, tfy), fminf(tfz, closest)) * 1.0000004f;
-                if (tn <= tf) {
-                    const bool inner = (meta & 0x18u) == 0x18u;
-                    const uint32_t bits = meta >> 5;
-                    const uint32_t index = (meta ^ (inner ? octinv : 0u)) & 0x1fu;
-                    hitmask |= bits << index;
-                }
-            }
+            child<0>(meta_lo, nearx0, farx0, neary0, fary0, nearz0, farz0, ax, ay, az, bx, by, bz, hitmask);
+            child<1>(meta_lo, nearx0, farx0, neary0, fary0, nearz0, farz0, ax, ay, az, bx, by, bz, hitmask);
+            child<2>(meta_lo, nearx0, farx0, neary0, fary0, nearz0, farz0, ax, ay, az, bx, by, bz, hitmask);
+            child<3>(meta_lo, nearx0, farx0, neary0, fary0, nearz0, farz0, ax, ay, az, bx, by, bz, hitmask);
+            child<0>(meta_hi, nearx1, farx1, neary1, fary1, nearz1, farz1, ax, ay, az, bx, by, bz, hitmask);
+            child<1>(meta_hi, nearx1, farx1, neary1, fary1, nearz1, farz1, ax, ay, az, bx, by, bz, hitmask);
+            child<2>(meta_hi, nearx1, farx1, neary1, fary1, nearz1, farz1, ax, ay, az, bx, by, bz, hitmask);
+            child<3>(meta_hi, nearx1, farx1, neary1, fary1, nearz1, farz1, ax, ay, az, bx, by, bz, hitmask);
             ngroup.x = f2u(n1.x);
             ngroup.y = (hitmask & 0xff000000u) | imask;
             tgroup.x = f2u(n1.y);
@@ -160,16 +188,27 @@ RT_HD bool traverse(const SceneD& sc, V3 o, V3 d, float t_min, float t_max, Hit&
                 hit.u = u;
                 hit.v = v;
                 found = true;
-                if (ANY_HIT) return true;
+                if (ANY_HIT) return false;
             }
         }
 
         if (!(ngroup.y & 0xff000000u)) {
-            if (sp == 0) break;
+            if (sp == 0) return false;
             ngroup = stack[--sp];
         }
+        return true;
     }
-    return found;
+};
+
+template <bool ANY_HIT, bool STATS>
+RT_HD bool traverse(const SceneD& sc, V3 o, V3 d, float t_min, float t_max, Hit& hit, TraverseStats* stats) {
+    uint2 stack_mem[TRAVERSE_STACK];
+    Traversal<ANY_HIT, STATS> tr;
+    tr.stack = stack_mem;
+    if (tr.init(sc, o, d, t_min, t_max))
+        while (tr.step(sc, stats)) {}
+    hit = tr.hit;
+    return tr.found;
 }
 
 }  // namespace rt

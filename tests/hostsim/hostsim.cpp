@@ -5,6 +5,8 @@
 // libraytracing_cuda.so through the C ABI. Mirrors the launch sequence of api.cu.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <vector>
@@ -268,12 +270,14 @@ int hostsim_render(const rtcuda_scene_desc* d, const rtcuda_settings* st, rtcuda
                     w.depth = depth;
                     w.ray_o_in = ro[in].data(); w.ray_d_in = rd[in].data(); w.ray_o_out = ro[ot].data(); w.ray_d_out = rd[ot].data();
                     const float t_min = depth == 0 ? sc.camera.near_clip : 0.0001f;
+                    const TraverseStats ts_before = ts;
                     for (uint32_t q = 0; q < n_rays; q++) {
                         Hit h;
                         traverse<false, true>(sc, xyz(w.ray_o_in[q]), xyz(w.ray_d_in[q]), t_min, w.ray_o_in[q].w, h, &ts);
                         hits[q] = make_float4(h.t, u2f(h.prim), h.u, h.v);
                     }
                     stats[depth == 0 ? 0 : 1] += n_rays;
+                    const TraverseStats ts_mid = ts;
                     uint32_t n_out = 0, n_shadow = 0;
                     for (uint32_t q = 0; q < n_rays; q++) {
                         ShadeOut so;
@@ -288,6 +292,10 @@ int hostsim_render(const rtcuda_scene_desc* d, const rtcuda_settings* st, rtcuda
                     uint32_t shadow_rays = 0;
                     for (uint32_t i = 0; i < n_shadow; i++) shadow_body<true>(i, sc, w, &ts, &shadow_rays);
                     stats[2] += shadow_rays;
+                    if (std::getenv("HOSTSIM_TRACE"))  // per-depth work profile (DESIGN.md "Measurement": ray-class table)
+                        std::fprintf(stderr, "depth %u: extend rays %u nodes %u prims %u | vertices %u shadow rays %u nodes %u prims %u | next %u\n", depth,
+                                     n_rays, ts_mid.nodes - ts_before.nodes, ts_mid.prims - ts_before.prims, n_shadow, shadow_rays,
+                                     ts.nodes - ts_mid.nodes, ts.prims - ts_mid.prims, n_out);
                     n_rays = n_out;
                 }
                 for (uint32_t i = 0; i < np; i++) resolve_body(i, w, accum.data());

@@ -110,7 +110,7 @@ def main():
     config = {"workload": f"{args.workload}: {fixture}.glb {W}x{H}, {spp} spp, depth {depth}, light samples {ls}, "
                           f"independent sampler, seed 42",
               "triangles": None, "partition": f"64x64 tiles round-robin over {world} GPU(s), scene replicated, 1 NCCL sum-reduce per frame",
-              "l2": "every step re-streams ~1 GB of wavefront state per batch through L2 (>> 126 MB) and a 512 MiB buffer is "
+              "l2": "every step re-streams ~17 GB of wavefront state per batch through L2 (>> 126 MB) and a 512 MiB buffer is "
                     "written between timed steps; the 3 MB BVH is L2-resident by design"}
 
     if args.impl == "reference":
@@ -198,6 +198,11 @@ def main():
     e2e_steps = max(1, min(args.steps, 2))
     holder = sc.to_desc()
     h2d = int(holder.vertices.nbytes + holder.tris.nbytes + holder.normals.nbytes + holder.uvs.nbytes + holder.image_bytes.nbytes)
+    def e2e_call():
+        with rc.CudaRenderer(sc, rc.multi_gpu.backend_settings_for_rank(rank, world, local_rank)) as r:
+            return r.render(st)
+    if args.warmup:
+        e2e_call()   # one untimed call: the first allocation of a second set of path-state buffers pays the driver's page mapping
     sync_all()
     e0 = time.time()
     for _ in range(e2e_steps):

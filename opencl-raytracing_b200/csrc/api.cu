@@ -6,6 +6,7 @@
 // Error handling: status codes + rtcuda_last_error() instead of the exit() of the OptiX precedent
 // (crates/raytracing-optix/csrc/host/util.hpp:7-27).
 #include <algorithm>
+#include <cstdlib>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -117,6 +118,10 @@ struct rtcuda_scene {
     DevBuf<float4> weight, radiance, ray_o[2], ray_d[2], hits, shadow_point, shadow_origin, shadow_contrib;
     DevBuf<uint32_t> shadow_queue, counters;
     DevBuf<unsigned long long> stats_dev;
+    size_t wave_bytes() const {  // path state currently allocated (reused by the next render)
+        return rng_state.n * 8 + (weight.n + radiance.n + ray_o[0].n + ray_o[1].n + ray_d[0].n + ray_d[1].n + hits.n + shadow_point.n +
+                                  shadow_origin.n + shadow_contrib.n) * 16 + shadow_queue.n * 4;
+    }
     DevBuf<PixelOut> pixel_out;
     // host-API staging planes
     DevBuf<float> d_beauty, d_normals, d_albedo, d_uv, d_mip, d_depth;
@@ -650,9 +655,22 @@ void render_device(rtcuda_scene* s, const rtcuda_settings* settings, const rtcud
     if ((o & RTCUDA_AOV_BEAUTY) && out->beauty) {
         if (partial) CK(cudaMemsetAsync(out->beauty, 0, npix_img * 12, st));
         if (np_all) {
-            uint32_t capacity = s->ctx->bs.max_paths_in_flight ? s->ctx->bs.max_paths_in_flight : (1u << 22);
-            capacity = std::max(capacity, 1024u);
             const uint32_t shadow_k = shadow_entries_per_vertex(s, rp);
+            // Wavefront size. Deep bounces keep only a fraction of a batch alive (C3: 26 % at depth 1, 8 % at depth 8)
+            // and every launch of a persistent kernel ends with a drain tail, so batches are sized for the 180 GB of
+            // HBM3e, not for L2: 64 Mi paths by default (~17 GB of path state with 4 light samples per vertex), capped
+            // to 40 % of the free device memory.
+            uint32_t capacity = s->ctx->bs.max_paths_in_flight;
+            if (!capacity)
+                if (const char* env = std::getenv("RTCUDA_MAX_PATHS")) capacity = (uint32_t)std::strtoul(env, nullptr, 0);  // tuning aid
+            if (!capacity) {
+                const size_t bytes_per_slot = 8 + 16 + 16 + 4 * 16 + 16 + 4 + 16 + 32 * (size_t)std::max(1u, shadow_k);
+                size_t free_b = 0, total_b = 0;
+                CK(cudaMemGetInfo(&free_b, &total_b));
+                size_t have_b = free_b + s->wave_bytes();
+                capacity = (uint32_t)std::min<size_t>(1u << 26, (size_t)(0.4 * (double)have_b) / bytes_per_slot);
+            }
+            capacity = std::max(capacity, 1024u);
             const uint32_t np_batch = std::min(np_all, capacity);
             const uint32_t ns_batch = std::max(1u, std::min(settings->samples_per_pixel, capacity / np_batch));
             ensure_wave(s, np_batch * ns_batch, shadow_k, rp.max_ray_depth);

@@ -38,22 +38,40 @@ __device__ __forceinline__ void warp_add_stat(unsigned long long* dst, uint32_t 
 // ---------------------------------------------------------------------------------------------------
 // wavefront kernels
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(BLOCK) k_raygen(SceneD sc, RenderParams rp, Wave w, uint32_t n) {
+__global__ void __launch_bounds__(BLOCK) k_raygen(const __grid_constant__ SceneD sc, const __grid_constant__ RenderParams rp,
+                                                   const __grid_constant__ Wave w, uint32_t n) {
     const uint32_t i = blockIdx.x * BLOCK + threadIdx.x;
     if (i == 0) *w.n_out = n;
     if (i < n) raygen_body(i, sc, rp, w);
 }
 
 // Persistent traversal kernels. A warp keeps pulling work from the launch's queue: whenever at least
-// REFILL_MIN lanes have finished their ray the idle lanes fetch new ones (one global atomic per refill), so
-// every step of the walk (one wide node + its leaf primitives) runs with nearly full warps even though the
-// rays of a bounce have wildly different traversal lengths (profiles/r1_notes.md: 7.3 of 32 lanes active
-// before this change). Every lane stays in the loop until the whole warp is out of work, which keeps the
-// full-mask ballots / shuffles legal.
-constexpr int REFILL_MIN = 8;
+// REFILL_MIN lanes are out of work they fetch new rays together (one global atomic per refill), so the walk
+// runs with nearly full warps although the rays of a bounce have wildly different traversal lengths
+// (profiles/r1_notes.md: 7.3 of 32 lanes active with one ray per thread). Within the loop the warp votes, every
+// iteration, between a NODE phase (each lane with a pending wide node tests its 8 child boxes; lanes that still
+// hold untested leaf primitives stash them on their stack) and a PRIMITIVE phase (each lane with pending leaf
+// primitives intersects one): in a given step only a few lanes have leaf hits, and looping over them right after
+// the box test ran the Moller-Trumbore code at ~8 of 32 lanes. The policy and its constants were tuned with the
+// warp simulator in tests/hostsim (HOSTSIM_WARPSIM). Every lane stays in the loop until the whole warp is out
+// of work, which keeps the full-mask ballots / shuffles legal.
+constexpr int REFILL_MIN = 6;
+constexpr int TRI_MIN = 12;
+
+template <bool ANY_HIT, bool STATS>
+__device__ __forceinline__ void warp_phase(Traversal<ANY_HIT, STATS>& tr, bool have, const SceneD& sc, TraverseStats* ts) {
+    const unsigned FULL = 0xffffffffu;
+    const bool wt = have && tr.has_tris();
+    const bool wn = have && tr.has_nodes() && (!wt || tr.can_stash());
+    const unsigned mt = __ballot_sync(FULL, wt), mn = __ballot_sync(FULL, wn);
+    if (mt != 0u && (mn == 0u || __popc(mt) >= TRI_MIN)) {
+        if (wt) tr.tri_step(sc, ts);
+    } else if (wn) tr.node_step(sc, ts);
+}
 
 template <bool STATS>
-__global__ void __launch_bounds__(BLOCK) k_extend(SceneD sc, Wave w, float t_min, uint32_t* fetch_counter) {
+__global__ void __launch_bounds__(BLOCK) k_extend(const __grid_constant__ SceneD sc, const __grid_constant__ Wave w, float t_min,
+                                                   uint32_t* fetch_counter) {
     const uint32_t n = *w.n_in;
     const unsigned FULL = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
@@ -84,7 +102,8 @@ __global__ void __launch_bounds__(BLOCK) k_extend(SceneD sc, Wave w, float t_min
             }
             if (base + (uint32_t)cnt >= n) exhausted = true;
         }
-        if (have && !tr.step(sc, &ts)) {
+        warp_phase(tr, have, sc, &ts);
+        if (have && !tr.next()) {
             w.hits[q] = make_float4(tr.hit.t, u2f(tr.hit.prim), tr.hit.u, tr.hit.v);
             have = false;
         }
@@ -95,33 +114,39 @@ __global__ void __launch_bounds__(BLOCK) k_extend(SceneD sc, Wave w, float t_min
     }
 }
 
-__global__ void __launch_bounds__(BLOCK) k_shade(SceneD sc, RenderParams rp, Wave w) {
+// Shading: persistent blocks walk the ray queue in block-sized chunks (the live queue length is only known on the
+// device; a grid sized for the whole batch spent a third of its warp time in blocks that found nothing to do,
+// profiles/r1_notes.md). Survivors and NEE vertices are pushed with one global atomic per block per queue.
+__global__ void __launch_bounds__(BLOCK) k_shade(const __grid_constant__ SceneD sc, const __grid_constant__ RenderParams rp,
+                                                  const __grid_constant__ Wave w) {
     __shared__ uint32_t s_count[2], s_base[2];
     const uint32_t n = *w.n_in;
-    if (blockIdx.x * BLOCK >= n) return;
-    if (threadIdx.x < 2) s_count[threadIdx.x] = 0;
-    __syncthreads();
-    const uint32_t q = blockIdx.x * BLOCK + threadIdx.x;
-    ShadeOut o;
-    o.continue_path = false;
-    o.n_shadow = 0;
-    o.slot = 0;
-    if (q < n) shade_body(q, sc, rp, w, o);
-    if (q == 0) atomicAdd(&w.stats[STAT_SHADED], (unsigned long long)n);
-    const uint32_t rpos = block_push(o.continue_path, w.n_out, &s_count[0], &s_base[0]);
-    if (o.continue_path) {
-        w.ray_o_out[rpos] = make_float4(o.next.o.x, o.next.o.y, o.next.o.z, RT_INF);
-        w.ray_d_out[rpos] = make_float4(o.next.d.x, o.next.d.y, o.next.d.z, u2f(o.slot));
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&w.stats[STAT_SHADED], (unsigned long long)n);
+    for (uint32_t base = blockIdx.x * BLOCK; base < n; base += gridDim.x * BLOCK) {
+        if (threadIdx.x < 2) s_count[threadIdx.x] = 0;
+        __syncthreads();
+        const uint32_t q = base + threadIdx.x;
+        ShadeOut o;
+        o.continue_path = false;
+        o.n_shadow = 0;
+        o.slot = 0;
+        if (q < n) shade_body(q, sc, rp, w, o);
+        const uint32_t rpos = block_push(o.continue_path, w.n_out, &s_count[0], &s_base[0]);
+        if (o.continue_path) {
+            w.ray_o_out[rpos] = make_float4(o.next.o.x, o.next.o.y, o.next.o.z, RT_INF);
+            w.ray_d_out[rpos] = make_float4(o.next.d.x, o.next.d.y, o.next.d.z, u2f(o.slot));
+        }
+        const uint32_t spos = block_push(o.n_shadow != 0, w.n_shadow, &s_count[1], &s_base[1]);
+        if (o.n_shadow != 0) w.shadow_queue[spos] = o.slot;
     }
-    const uint32_t spos = block_push(o.n_shadow != 0, w.n_shadow, &s_count[1], &s_base[1]);
-    if (o.n_shadow != 0) w.shadow_queue[spos] = o.slot;
 }
 
-// `occluded` (lights.rs:159-168) for every pending light sample of a path vertex. The work item is the vertex
-// (its <= K rays are walked one after the other by the same lane and their contributions added once, in order:
-// deterministic, no float atomics); lanes refill with new vertices like k_extend.
+// `occluded` (lights.rs:159-168) for every pending light sample of a path vertex. The work item is the vertex:
+// its <= K rays are walked one after the other by the same lane and their unoccluded contributions added once,
+// in order (deterministic, no float atomics). Lanes that need a ray — the next one of their vertex, or a new
+// vertex from the queue — set it up together at the top of the loop, like k_extend's refill.
 template <bool STATS>
-__global__ void __launch_bounds__(BLOCK) k_shadow(SceneD sc, Wave w, uint32_t* fetch_counter) {
+__global__ void __launch_bounds__(BLOCK) k_shadow(const __grid_constant__ SceneD sc, const __grid_constant__ Wave w, uint32_t* fetch_counter) {
     const uint32_t n = *w.n_shadow;
     const unsigned FULL = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
@@ -130,55 +155,62 @@ __global__ void __launch_bounds__(BLOCK) k_shadow(SceneD sc, Wave w, uint32_t* f
     tr.stack = stack_mem;
     TraverseStats ts;
     ts.nodes = ts.prims = 0;
-    bool have = false, exhausted = n == 0;
-    uint32_t slot = 0, k = 0, j = 0, n_rays = 0;
+    bool have_ray = false, exhausted = n == 0;
+    uint32_t slot = 0, k = 0, j = 0, n_rays = 0;   // j == k: no vertex
     V3 point = mk3(0.0f), sum = mk3(0.0f), contrib = mk3(0.0f);
-    // start the next ray of this vertex that needs an occlusion test; returns false when the vertex is finished
-    auto next_ray = [&]() -> bool {
-        while (j < k) {
-            const size_t e = (size_t)j * w.capacity + slot;
-            const float4 o4 = w.shadow_origin[e], c4 = w.shadow_contrib[e];
-            contrib = xyz(c4);
-            if (!(f2u(o4.w) & 1u)) {
-                const V3 origin = xyz(o4);
-                const V3 dir_world = point - origin;
-                const float d = length(dir_world);
-                n_rays++;
-                if (tr.init(sc, origin, dir_world / d, 0.001f, c4.w - 0.001f)) return true;
-            }
-            sum += contrib;  // never occluded (non-finite origin quirk, or an empty scene)
-            j++;
-        }
-        const float4 r = w.radiance[slot];
-        w.radiance[slot] = make_float4(r.x + sum.x, r.y + sum.y, r.z + sum.z, 0.0f);
-        return false;
-    };
     for (;;) {
-        const unsigned need = __ballot_sync(FULL, !have);
-        if (need == FULL && exhausted) break;
-        if (!exhausted && __popc(need) >= REFILL_MIN) {
-            const int cnt = __popc(need), leader = __ffs(need) - 1;
-            uint32_t base = 0;
-            if ((int)lane == leader) base = atomicAdd(fetch_counter, (uint32_t)cnt);
-            base = __shfl_sync(FULL, base, leader);
-            if (!have) {
-                const uint32_t mine = base + (uint32_t)__popc(need & lt);
-                if (mine < n) {
-                    slot = w.shadow_queue[mine];
-                    const float4 p4 = w.shadow_point[slot];
-                    point = xyz(p4);
-                    k = f2u(p4.w);
-                    j = 0;
-                    sum = mk3(0.0f);
-                    have = next_ray();
+        const bool want_vertex = !have_ray && j == k;
+        const unsigned need_vertex = exhausted ? 0u : __ballot_sync(FULL, want_vertex);
+        const unsigned need_ray = __ballot_sync(FULL, !have_ray && (j < k || !exhausted));
+        if (__ballot_sync(FULL, have_ray || j < k) == 0u && exhausted) break;
+        if (__popc(need_ray) >= REFILL_MIN || __ballot_sync(FULL, have_ray) == 0u) {
+            if (need_vertex) {
+                const int cnt = __popc(need_vertex), leader = __ffs(need_vertex) - 1;
+                uint32_t base = 0;
+                if ((int)lane == leader) base = atomicAdd(fetch_counter, (uint32_t)cnt);
+                base = __shfl_sync(FULL, base, leader);
+                if (want_vertex) {
+                    const uint32_t mine = base + (uint32_t)__popc(need_vertex & lt);
+                    if (mine < n) {
+                        slot = w.shadow_queue[mine];
+                        const float4 p4 = w.shadow_point[slot];
+                        point = xyz(p4);
+                        k = f2u(p4.w);
+                        j = 0;
+                        sum = mk3(0.0f);
+                    }
+                }
+                if (base + (uint32_t)cnt >= n) exhausted = true;
+            }
+            if (!have_ray && j < k) {
+                // next entry of this vertex that needs an occlusion test
+                do {
+                    const size_t e = (size_t)j * w.capacity + slot;
+                    const float4 o4 = w.shadow_origin[e], c4 = w.shadow_contrib[e];
+                    contrib = xyz(c4);
+                    if (!(f2u(o4.w) & 1u)) {
+                        const V3 origin = xyz(o4);
+                        const V3 dir_world = point - origin;
+                        const float d = length(dir_world);
+                        n_rays++;
+                        have_ray = tr.init(sc, origin, dir_world / d, 0.001f, c4.w - 0.001f);
+                    }
+                    if (!have_ray) { sum += contrib; j++; }  // never occluded (non-finite origin quirk, or an empty scene)
+                } while (!have_ray && j < k);
+                if (!have_ray) {  // vertex finished without a traversal
+                    const float4 r = w.radiance[slot];
+                    w.radiance[slot] = make_float4(r.x + sum.x, r.y + sum.y, r.z + sum.z, 0.0f);
                 }
             }
-            if (base + (uint32_t)cnt >= n) exhausted = true;
         }
-        if (have && !tr.step(sc, &ts)) {
+        warp_phase(tr, have_ray, sc, &ts);
+        if (have_ray && !tr.next()) {
             if (!tr.found) sum += contrib;
-            j++;
-            have = next_ray();
+            have_ray = false;
+            if (++j == k) {
+                const float4 r = w.radiance[slot];
+                w.radiance[slot] = make_float4(r.x + sum.x, r.y + sum.y, r.z + sum.z, 0.0f);
+            }
         }
     }
     warp_add_stat(&w.stats[STAT_SHADOW], n_rays);
@@ -188,7 +220,7 @@ __global__ void __launch_bounds__(BLOCK) k_shadow(SceneD sc, Wave w, uint32_t* f
     }
 }
 
-__global__ void __launch_bounds__(BLOCK) k_resolve(Wave w, float4* accum) {
+__global__ void __launch_bounds__(BLOCK) k_resolve(const __grid_constant__ Wave w, float4* accum) {
     const uint32_t i = blockIdx.x * BLOCK + threadIdx.x;
     if (i < w.n_pixels) resolve_body(i, w, accum);
 }
@@ -228,7 +260,7 @@ void launch_extend(cudaStream_t st, const SceneD& sc, const Wave& w, uint32_t n_
     lc.launches++;
 }
 void launch_shade(cudaStream_t st, const SceneD& sc, const RenderParams& rp, const Wave& w, uint32_t n_max, LaunchCounter& lc) {
-    k_shade<<<grid_for(n_max), BLOCK, 0, st>>>(sc, rp, w);
+    k_shade<<<persistent_grid((const void*)k_shade, n_max), BLOCK, 0, st>>>(sc, rp, w);
     lc.launches++;
 }
 void launch_shadow(cudaStream_t st, const SceneD& sc, const Wave& w, uint32_t n_max, uint32_t* fetch_counter, bool stats, LaunchCounter& lc) {

@@ -16,7 +16,7 @@ __device__ __forceinline__ void warp_add_stat(unsigned long long* dst, uint32_t 
 }
 
 template <bool STATS>
-__global__ void __launch_bounds__(BLOCK) k_aov(SceneD sc, RenderParams rp, const uint32_t* pixel_list, uint32_t n, AovPlanes pl,
+__global__ void __launch_bounds__(BLOCK) k_aov(const __grid_constant__ SceneD sc, const __grid_constant__ RenderParams rp, const uint32_t* pixel_list, uint32_t n, AovPlanes pl,
                                                 unsigned long long* stats) {
     const uint32_t i = blockIdx.x * BLOCK + threadIdx.x;
     TraverseStats ts;
@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(BLOCK) k_aov(SceneD sc, RenderParams rp, const
     }
 }
 
-__global__ void k_pixel_aov(SceneD sc, RenderParams rp, uint32_t x, uint32_t y, uint32_t lo, uint32_t n, PixelOut* out) {
+__global__ void k_pixel_aov(const __grid_constant__ SceneD sc, const __grid_constant__ RenderParams rp, uint32_t x, uint32_t y, uint32_t lo, uint32_t n, PixelOut* out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     TraverseStats ts;

@@ -272,8 +272,8 @@ RT_HD void collapse_body(uint32_t item_idx, const BuildCtx& b) {
             frexpf(ext[a] / 255.0f, &ex);  // ext/255 = m * 2^ex, m in [0.5, 1)
             e = ex + 127;
             if (e < 1) e = 1;
-            if (e > 254) e = 254;
-            while (e < 254 && lov[a] + 255.0f * u2f((uint32_t)e << 23) < hiv[a]) e++;
+            if (e > 238) e = 238;  // rt_traverse.h folds 2^15 into the scale: e + 15 must stay a finite exponent
+            while (e < 238 && lov[a] + 255.0f * u2f((uint32_t)e << 23) < hiv[a]) e++;
         }
         ebits[a] = (uint32_t)e;
         scale[a] = u2f((uint32_t)e << 23);

@@ -65,29 +65,42 @@ RT_HD float safe_rcp_dir(float d) {
     return 1.0f / a;
 }
 
-// quantised plane byte k of word w as a float. On the device this is one PRMT building 2^23 + q in the
-// mantissa plus one FADD (exact); `(float)((w >> 8k) & 0xff)` compiles to I2F.U8, which issues on the
-// quarter-rate XU pipe and made the 48 conversions per node the limiter of both traversal kernels
-// (profiles/r1_notes.md: XU pipe 60-105 % busy).
+// Quantised plane byte K of word w as the float 1 + q * 2^-15 (q in mantissa bits 8..15): one PRMT on the
+// device, no int->float conversion (I2F issues on the quarter-rate XU pipe and was the limiter of the first
+// version, profiles/r1_notes.md) and no bias subtraction: the node constants absorb the "1 +" (see node_step).
 template <int K>
-RT_HD float qbyte(uint32_t w) {
+RT_HD float qfloat(uint32_t w) {
 #if defined(__CUDA_ARCH__)
-    return __uint_as_float(__byte_perm(w, 0x4b000000u, 0x7440u + K)) - 8388608.0f;
+    return __uint_as_float(__byte_perm(w, 0x3f800000u, 0x7604u + (K << 4)));
 #else
-    return (float)((w >> (8 * K)) & 0xffu);
+    return u2f(0x3f800000u | (((w >> (8 * K)) & 0xffu) << 8));
+#endif
+}
+template <int K>
+RT_HD uint32_t byte_of(uint32_t w) {
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(w, 0u, 0x4440u + K);
+#else
+    return (w >> (8 * K)) & 0xffu;
 #endif
 }
 
-// Traversal as a resumable per-ray state machine: `init` once, then `step` until it returns false. One step
-// visits ONE wide node (8 quantised slab tests) and intersects the primitives of the leaf children it hit.
-// The one-ray-per-thread kernels just loop (`traverse` below); the persistent kernels interleave steps with
-// warp-level ray refill so lanes whose ray ended do not idle while their neighbours walk a deep subtree.
+// Traversal as a resumable per-ray state machine with two kinds of work unit, so that a warp can run all its
+// lanes through the same kind at once (kernels.cu: the persistent kernels vote per iteration):
+//   node_step — pop ONE wide node of the current node group, test its 8 quantised child boxes;
+//   tri_step  — intersect ONE primitive of the current primitive group;
+//   next      — refill the current groups from the stack; false when the walk is complete.
+// Pending primitive groups can be postponed: node_step stashes a non-empty one on the stack (entries with no
+// bits in the top byte are primitive groups). The closest hit is independent of the order in which primitives
+// are tested: equal-t ties go to the larger primitive index (the reference resolves them by its own BVH2 leaf
+// order, "later hit overwrites", geometry.rs:335 / accel.rs:159-171, which no other tree can reproduce), so
+// frames stay bit-reproducible although lanes pick up rays dynamically.
 template <bool ANY_HIT, bool STATS>
 struct Traversal {
     V3 o, d, idir;
     float t_min, closest;
-    uint32_t oct, octinv;
-    uint2 ngroup;
+    uint32_t octinv;
+    uint2 ngroup, tgroup;
     uint2* stack;  // TRAVERSE_STACK entries of thread-local memory owned by the caller (keeps the scalar state in registers)
     int sp;
     Hit hit;
@@ -99,114 +112,140 @@ struct Traversal {
         found = false;
         sp = 0;
         idir = mk3(safe_rcp_dir(d.x), safe_rcp_dir(d.y), safe_rcp_dir(d.z));
-        oct = (d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u);
-        octinv = 7u - oct;
+        octinv = 7u - ((d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u));
         ngroup = make_uint2(0u, 0x80000000u);  // root: "child 7^octinv of a group with base 0, imask 0"
+        tgroup = make_uint2(0u, 0u);
         return sc.prim_count != 0;
     }
 
+    RT_HD bool has_tris() const { return tgroup.y != 0u; }
+    RT_HD bool has_nodes() const { return (ngroup.y & 0xff000000u) != 0u; }
+    RT_HD bool can_stash() const { return sp < TRAVERSE_STACK - 2; }
+
+    // child I of a 4-child half: slab test against the near / far plane words of the three axes
     template <int I>
-    RT_HD void child(uint32_t meta_w, uint32_t nx_w, uint32_t fx_w, uint32_t ny_w, uint32_t fy_w, uint32_t nz_w, uint32_t fz_w,
-                     float ax, float ay, float az, float bx, float by, float bz, uint32_t& hitmask) const {
-        const uint32_t meta = (meta_w >> (8 * I)) & 0xffu;
-        if (meta == 0u) return;
-        const float tnx = qbyte<I>(nx_w) * ax + bx, tfx = qbyte<I>(fx_w) * ax + bx;
-        const float tny = qbyte<I>(ny_w) * ay + by, tfy = qbyte<I>(fy_w) * ay + by;
-        const float tnz = qbyte<I>(nz_w) * az + bz, tfz = qbyte<I>(fz_w) * az + bz;
-        const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, t_min));
-        const float tf = fminf(fminf(tfx, tfy), fminf(tfz, closest)) * 1.0000004f;
-        if (tn <= tf) {
-            const bool inner = (meta & 0x18u) == 0x18u;
-            hitmask |= (meta >> 5) << ((meta ^ (inner ? octinv : 0u)) & 0x1fu);
+    RT_HD void child(uint32_t bits4, uint32_t index4, uint32_t nx_w, uint32_t fx_w, uint32_t ny_w, uint32_t fy_w, uint32_t nz_w, uint32_t fz_w,
+                     V3 an, V3 cn, V3 af, V3 cf, float tf_cap, uint32_t& hitmask) const {
+        const float tn = fmaxf(fmaxf(qfloat<I>(nx_w) * an.x + cn.x, qfloat<I>(ny_w) * an.y + cn.y), fmaxf(qfloat<I>(nz_w) * an.z + cn.z, t_min));
+        const float tf = fminf(fminf(qfloat<I>(fx_w) * af.x + cf.x, qfloat<I>(fy_w) * af.y + cf.y), fminf(qfloat<I>(fz_w) * af.z + cf.z, tf_cap));
+        if (tn <= tf) hitmask |= byte_of<I>(bits4) << byte_of<I>(index4);
+    }
+
+    // precondition: has_nodes()
+    RT_HD void node_step(const SceneD& sc, TraverseStats* stats) {
+        if (tgroup.y) stack[sp++] = tgroup;  // postponed primitives
+        const uint32_t hits = ngroup.y;
+        const int bit = bfind32(hits);
+        ngroup.y &= ~(1u << bit);
+        if (ngroup.y & 0xff000000u) stack[sp++] = ngroup;
+        const uint32_t slot = ((uint32_t)bit - 24u) ^ octinv;
+        const uint32_t rel = (uint32_t)popc32(hits & ~(0xffffffffu << slot) & 0xffu);
+        const Node8* node = sc.nodes + (ngroup.x + rel);
+        const float4 n0 = ldg(&node->n0), n1 = ldg(&node->n1), n2 = ldg(&node->n2), n3 = ldg(&node->n3), n4 = ldg(&node->n4);
+        if (STATS) stats->nodes++;
+
+        // plane coordinate = origin + q * 2^e; along the ray t = q * a + b with a = 2^e / d, b = (origin - o) / d.
+        // With qfloat = 1 + q * 2^-15: t = qfloat * A + C, A = 2^15 * a, C = b - A — one FFMA per plane. The rounding
+        // of C costs at most 2^-9 quantisation steps; both slab sides are pushed outwards by 2^-7 steps (per axis, so an
+        // axis-parallel ray keeps its exact in/out classification on the other axes) and the far side keeps the
+        // 4e-7 relative slack of the box test, so culling stays conservative.
+        const uint32_t e = f2u(n0.w);
+        const V3 a15 = mk3(u2f((byte_of<0>(e) + 15u) << 23) * idir.x, u2f((byte_of<1>(e) + 15u) << 23) * idir.y,
+                           u2f((byte_of<2>(e) + 15u) << 23) * idir.z);
+        const uint32_t imask = e >> 24;
+        const V3 c = mk3((n0.x - o.x) * idir.x - a15.x, (n0.y - o.y) * idir.y - a15.y, (n0.z - o.z) * idir.z - a15.z);
+        const V3 pad = mk3(fabsf(a15.x), fabsf(a15.y), fabsf(a15.z)) * 2.3841858e-7f;  // 2^-22 * |A| = 2^-7 steps
+        const float k_far = 1.0000004f;
+        const V3 cn = c - pad, af = a15 * k_far, cf = (c + pad) * k_far;
+        const float tf_cap = closest * k_far;
+        const uint32_t meta_lo = f2u(n1.z), meta_hi = f2u(n1.w);
+        // near / far plane words per axis, selected by the ray octant
+        const uint32_t lox0 = f2u(n2.x), lox1 = f2u(n2.y), loy0 = f2u(n2.z), loy1 = f2u(n2.w);
+        const uint32_t loz0 = f2u(n3.x), loz1 = f2u(n3.y), hix0 = f2u(n3.z), hix1 = f2u(n3.w);
+        const uint32_t hiy0 = f2u(n4.x), hiy1 = f2u(n4.y), hiz0 = f2u(n4.z), hiz1 = f2u(n4.w);
+        const bool nx = (octinv & 1u) == 0u, ny = (octinv & 2u) == 0u, nz = (octinv & 4u) == 0u;  // direction negative on the axis
+        const uint32_t nearx0 = nx ? hix0 : lox0, nearx1 = nx ? hix1 : lox1, farx0 = nx ? lox0 : hix0, farx1 = nx ? lox1 : hix1;
+        const uint32_t neary0 = ny ? hiy0 : loy0, neary1 = ny ? hiy1 : loy1, fary0 = ny ? loy0 : hiy0, fary1 = ny ? loy1 : hiy1;
+        const uint32_t nearz0 = nz ? hiz0 : loz0, nearz1 = nz ? hiz1 : loz1, farz0 = nz ? loz0 : hiz0, farz1 = nz ? loz1 : hiz1;
+        // four children at a time: hit-mask bit position (24 + slot ^ octinv for inner children, the primitive offset for
+        // leaves) and the bits to set there (1 for inner, unary primitive count for leaves; 0 for an empty child)
+        const uint32_t octinv4 = octinv * 0x01010101u;
+        uint32_t hitmask = 0;
+        {
+            const uint32_t inner4 = (meta_lo & (meta_lo << 1)) & 0x10101010u;   // bit 4 set <=> (meta & 0x18) == 0x18
+            const uint32_t index4 = (meta_lo ^ (octinv4 & ((inner4 >> 4) * 0x07u))) & 0x1f1f1f1fu;
+            const uint32_t bits4 = (meta_lo >> 5) & 0x07070707u;
+            child<0>(bits4, index4, nearx0, farx0, neary0, fary0, nearz0, farz0, a15, cn, af, cf, tf_cap, hitmask);
+            child<1>(bits4, index4, nearx0, farx0, neary0, fary0, nearz0, farz0, a15, cn, af, cf, tf_cap, hitmask);
+            child<2>(bits4, index4, nearx0, farx0, neary0, fary0, nearz0, farz0, a15, cn, af, cf, tf_cap, hitmask);
+            child<3>(bits4, index4, nearx0, farx0, neary0, fary0, nearz0, farz0, a15, cn, af, cf, tf_cap, hitmask);
+        }
+        {
+            const uint32_t inner4 = (meta_hi & (meta_hi << 1)) & 0x10101010u;
+            const uint32_t index4 = (meta_hi ^ (octinv4 & ((inner4 >> 4) * 0x07u))) & 0x1f1f1f1fu;
+            const uint32_t bits4 = (meta_hi >> 5) & 0x07070707u;
+            child<0>(bits4, index4, nearx1, farx1, neary1, fary1, nearz1, farz1, a15, cn, af, cf, tf_cap, hitmask);
+            child<1>(bits4, index4, nearx1, farx1, neary1, fary1, nearz1, farz1, a15, cn, af, cf, tf_cap, hitmask);
+            child<2>(bits4, index4, nearx1, farx1, neary1, fary1, nearz1, farz1, a15, cn, af, cf, tf_cap, hitmask);
+            child<3>(bits4, index4, nearx1, farx1, neary1, fary1, nearz1, farz1, a15, cn, af, cf, tf_cap, hitmask);
+        }
+        ngroup.x = f2u(n1.x);
+        ngroup.y = (hitmask & 0xff000000u) | imask;
+        tgroup.x = f2u(n1.y);
+        tgroup.y = hitmask & 0x00ffffffu;
+    }
+
+    // precondition: has_tris(). Intersects the lowest-numbered pending primitive of the current group.
+    RT_HD void tri_step(const SceneD& sc, TraverseStats* stats) {
+        const int b = 31 - clz32(tgroup.y & (0u - tgroup.y));  // lowest set bit
+        tgroup.y &= tgroup.y - 1u;
+        const uint32_t pi = tgroup.x + (uint32_t)b;
+        const Prim* pr = sc.prims + pi;
+        const float4 pa = ldg(&pr->a), pb = ldg(&pr->b), pc = ldg(&pr->c);
+        if (STATS) stats->prims++;
+        float t, u = 0.0f, v = 0.0f;
+        bool h;
+        if (f2u(pc.w) == 0u) {
+            h = triangle_t(xyz(pa), xyz(pb), xyz(pc), o, d, t_min, closest, t, u, v);
+        } else {
+            const Instance* inst = sc.instances + f2u(pa.w);
+            V3 oo = apply_point(inst->w2o, o), od = apply_vector(inst->w2o, d);
+            h = sphere_t(xyz(pa), pb.x, oo, od, t_min, closest, t);
+        }
+        if (h && (t < closest || hit.prim == NONE || pi > hit.prim)) {
+            closest = t;
+            hit.t = t;
+            hit.prim = pi;
+            hit.u = u;
+            hit.v = v;
+            found = true;
+            if (ANY_HIT) { ngroup.y = 0u; tgroup.y = 0u; sp = 0; }
         }
     }
 
-    // precondition: ngroup has node hits. Returns true while more nodes remain.
-    RT_HD bool step(const SceneD& sc, TraverseStats* stats) {
-        uint2 tgroup;
-        {
-            const uint32_t hits = ngroup.y;
-            const int bit = bfind32(hits);
-            ngroup.y &= ~(1u << bit);
-            if (ngroup.y & 0xff000000u) stack[sp++] = ngroup;
-            const uint32_t slot = ((uint32_t)bit - 24u) ^ octinv;
-            const uint32_t rel = (uint32_t)popc32(hits & ~(0xffffffffu << slot) & 0xffu);
-            const Node8* node = sc.nodes + (ngroup.x + rel);
-            const float4 n0 = ldg(&node->n0), n1 = ldg(&node->n1), n2 = ldg(&node->n2), n3 = ldg(&node->n3), n4 = ldg(&node->n4);
-            if (STATS) stats->nodes++;
-
-            const uint32_t e = f2u(n0.w);
-            const float sx = u2f((e & 0xffu) << 23), sy = u2f(((e >> 8) & 0xffu) << 23), sz = u2f(((e >> 16) & 0xffu) << 23);
-            const uint32_t imask = e >> 24;
-            const float ax = sx * idir.x, ay = sy * idir.y, az = sz * idir.z;
-            const float bx = (n0.x - o.x) * idir.x, by = (n0.y - o.y) * idir.y, bz = (n0.z - o.z) * idir.z;
-            const uint32_t meta_lo = f2u(n1.z), meta_hi = f2u(n1.w);
-            // near / far plane words per axis, selected by the ray octant
-            const uint32_t lox0 = f2u(n2.x), lox1 = f2u(n2.y), loy0 = f2u(n2.z), loy1 = f2u(n2.w);
-            const uint32_t loz0 = f2u(n3.x), loz1 = f2u(n3.y), hix0 = f2u(n3.z), hix1 = f2u(n3.w);
-            const uint32_t hiy0 = f2u(n4.x), hiy1 = f2u(n4.y), hiz0 = f2u(n4.z), hiz1 = f2u(n4.w);
-            const bool nx = (oct & 1u) != 0, ny = (oct & 2u) != 0, nz = (oct & 4u) != 0;
-            const uint32_t nearx0 = nx ? hix0 : lox0, nearx1 = nx ? hix1 : lox1, farx0 = nx ? lox0 : hix0, farx1 = nx ? lox1 : hix1;
-            const uint32_t neary0 = ny ? hiy0 : loy0, neary1 = ny ? hiy1 : loy1, fary0 = ny ? loy0 : hiy0, fary1 = ny ? loy1 : hiy1;
-            const uint32_t nearz0 = nz ? hiz0 : loz0, nearz1 = nz ? hiz1 : loz1, farz0 = nz ? loz0 : hiz0, farz1 = nz ? loz1 : hiz1;
-
-            uint32_t hitmask = 0;
-            child<0>(meta_lo, nearx0, farx0, neary0, fary0, nearz0, farz0, ax, ay, az, bx, by, bz, hitmask);
-            child<1>(meta_lo, nearx0, farx0, neary0, fary0, nearz0, farz0, ax, ay, az, bx, by, bz, hitmask);
-            child<2>(meta_lo, nearx0, farx0, neary0, fary0, nearz0, farz0, ax, ay, az, bx, by, bz, hitmask);
-            child<3>(meta_lo, nearx0, farx0, neary0, fary0, nearz0, farz0, ax, ay, az, bx, by, bz, hitmask);
-            child<0>(meta_hi, nearx1, farx1, neary1, fary1, nearz1, farz1, ax, ay, az, bx, by, bz, hitmask);
-            child<1>(meta_hi, nearx1, farx1, neary1, fary1, nearz1, farz1, ax, ay, az, bx, by, bz, hitmask);
-            child<2>(meta_hi, nearx1, farx1, neary1, fary1, nearz1, farz1, ax, ay, az, bx, by, bz, hitmask);
-            child<3>(meta_hi, nearx1, farx1, neary1, fary1, nearz1, farz1, ax, ay, az, bx, by, bz, hitmask);
-            ngroup.x = f2u(n1.x);
-            ngroup.y = (hitmask & 0xff000000u) | imask;
-            tgroup.x = f2u(n1.y);
-            tgroup.y = hitmask & 0x00ffffffu;
-        }
-
-        while (tgroup.y) {
-            const int b = 31 - clz32(tgroup.y & (0u - tgroup.y));  // lowest set bit
-            tgroup.y &= tgroup.y - 1u;
-            const uint32_t pi = tgroup.x + (uint32_t)b;
-            const Prim* pr = sc.prims + pi;
-            const float4 pa = ldg(&pr->a), pb = ldg(&pr->b), pc = ldg(&pr->c);
-            if (STATS) stats->prims++;
-            float t, u = 0.0f, v = 0.0f;
-            bool h;
-            if (f2u(pc.w) == 0u) {
-                h = triangle_t(xyz(pa), xyz(pb), xyz(pc), o, d, t_min, closest, t, u, v);
-            } else {
-                const Instance* inst = sc.instances + f2u(pa.w);
-                V3 oo = apply_point(inst->w2o, o), od = apply_vector(inst->w2o, d);
-                h = sphere_t(xyz(pa), pb.x, oo, od, t_min, closest, t);
-            }
-            if (h) {
-                closest = t;
-                hit.t = t;
-                hit.prim = pi;
-                hit.u = u;
-                hit.v = v;
-                found = true;
-                if (ANY_HIT) return false;
-            }
-        }
-
-        if (!(ngroup.y & 0xff000000u)) {
-            if (sp == 0) return false;
-            ngroup = stack[--sp];
-        }
+    // make the current groups non-empty from the stack; false when nothing is left
+    RT_HD bool next() {
+        if (tgroup.y | (ngroup.y & 0xff000000u)) return true;
+        if (sp == 0) return false;
+        const uint2 g = stack[--sp];
+        if (g.y & 0xff000000u) ngroup = g;
+        else tgroup = g;
         return true;
     }
 };
 
+// One ray start to finish: each node's primitives right after its box test.
 template <bool ANY_HIT, bool STATS>
 RT_HD bool traverse(const SceneD& sc, V3 o, V3 d, float t_min, float t_max, Hit& hit, TraverseStats* stats) {
     uint2 stack_mem[TRAVERSE_STACK];
     Traversal<ANY_HIT, STATS> tr;
     tr.stack = stack_mem;
-    if (tr.init(sc, o, d, t_min, t_max))
-        while (tr.step(sc, stats)) {}
+    if (tr.init(sc, o, d, t_min, t_max)) {
+        do {
+            if (tr.has_tris()) tr.tri_step(sc, stats);
+            else tr.node_step(sc, stats);
+        } while (tr.next());
+    }
     hit = tr.hit;
     return tr.found;
 }

@@ -195,6 +195,93 @@ RenderParams make_params(const rtcuda_settings* st) {
 
 }  // namespace
 
+
+// ---- warp-phase simulator (tuning aid for the persistent traversal kernels, kernels.cu) ---------------------
+// Runs the rays of one queue through 32-lane "warps" with the same refill / vote loop as k_extend / k_shadow and
+// charges each iteration the instruction cost of the phase it executed, so policies can be compared without a GPU.
+// HOSTSIM_WARPSIM="policy,tri_min,refill_min": policy 0 = node + all its primitives per iteration (the r1b kernels),
+// 1 = vote, lanes with pending primitives idle during node phases, 2 = vote, pending primitives are stashed.
+struct SimRay { V3 o, d; float t_min, t_max; };
+template <bool ANY_HIT>
+static void warp_sim(const SceneD& sc, const std::vector<SimRay>& rays, const char* label) {
+    const char* cfg = std::getenv("HOSTSIM_WARPSIM");
+    if (!cfg || rays.empty()) return;
+    int policy = 2, tri_min = 12, refill_min = 8, rays_per_warp = 0;  // rays_per_warp 0: one warp drains the whole queue (no tail)
+    std::sscanf(cfg, "%d,%d,%d,%d", &policy, &tri_min, &refill_min, &rays_per_warp);
+    const double C_NODE = 230, C_TRI = 85, C_INIT = 45, C_LOOP = 14, C_FIN = 8;
+    struct Lane { Traversal<ANY_HIT, true> tr; uint2 stack[TRAVERSE_STACK]; bool have = false; };
+    struct Warp { std::vector<Lane> lanes; bool done = false; };
+    const size_t n_warps = rays_per_warp > 0 ? std::max<size_t>(1, rays.size() / rays_per_warp) : 1;
+    std::vector<Warp> warps(n_warps);
+    for (auto& w : warps) { w.lanes.resize(32); for (auto& l : w.lanes) l.tr.stack = l.stack; }
+    TraverseStats ts{0, 0};
+    size_t cursor = 0, live = n_warps;
+    double cost = 0, useful = 0;
+    uint64_t iters = 0, node_phases = 0, tri_phases = 0, node_lanes = 0, tri_lanes = 0, idle_lanes = 0;
+    while (live) {
+        for (auto& wp : warps) {   // round robin: one loop iteration per live warp
+            if (wp.done) continue;
+            auto& lanes = wp.lanes;
+            int need = 0;
+            for (auto& l : lanes) need += !l.have;
+            const bool exhausted = cursor >= rays.size();
+            if (need == 32 && exhausted) { wp.done = true; live--; continue; }
+            cost += C_LOOP; iters++; idle_lanes += need;
+            if (!exhausted && need >= refill_min) {
+                cost += C_INIT;
+                for (auto& l : lanes)
+                    if (!l.have && cursor < rays.size()) {
+                        const SimRay& r = rays[cursor++];
+                        l.have = l.tr.init(sc, r.o, r.d, r.t_min, r.t_max);
+                        useful += C_INIT / 32;
+                    }
+            }
+            if (policy == 0) {
+                int max_tris = 0, n_act = 0, tri_work = 0;
+                for (auto& l : lanes) {
+                    if (!l.have) continue;
+                    n_act++;
+                    l.tr.node_step(sc, &ts);
+                    int k = 0;
+                    while (l.tr.has_tris()) { l.tr.tri_step(sc, &ts); k++; }
+                    tri_work += k;
+                    max_tris = std::max(max_tris, k);
+                }
+                cost += C_NODE + max_tris * C_TRI;
+                useful += (n_act * C_NODE + tri_work * C_TRI) / 32;
+                node_phases++; node_lanes += n_act;
+            } else {
+                int nt = 0, nn = 0;
+                for (auto& l : lanes) {
+                    if (!l.have) continue;
+                    const bool wt = l.tr.has_tris(), wn = l.tr.has_nodes() && (policy == 2 ? (!wt || l.tr.can_stash()) : !wt);
+                    nt += wt; nn += wn;
+                }
+                const bool tri_phase = nt > 0 && (nn == 0 || nt >= tri_min || (policy == 1 && nt >= nn) || (policy == 3 && nt * 2 >= nn));
+                if (tri_phase) {
+                    for (auto& l : lanes) if (l.have && l.tr.has_tris()) l.tr.tri_step(sc, &ts);
+                    cost += C_TRI; useful += nt * C_TRI / 32; tri_phases++; tri_lanes += nt;
+                } else {
+                    for (auto& l : lanes) {
+                        if (!l.have) continue;
+                        const bool wt = l.tr.has_tris();
+                        if (l.tr.has_nodes() && (policy == 2 ? (!wt || l.tr.can_stash()) : !wt)) l.tr.node_step(sc, &ts);
+                    }
+                    cost += C_NODE; useful += nn * C_NODE / 32; node_phases++; node_lanes += nn;
+                }
+            }
+            int fin = 0;
+            for (auto& l : lanes) if (l.have && !l.tr.next()) { l.have = false; fin++; }
+            if (fin) { cost += C_FIN; useful += fin * C_FIN / 32; }
+        }
+    }
+    std::fprintf(stderr, "  warpsim %-9s policy %d tri_min %d refill %d warps %zu: rays %zu cost/ray %.1f util %.3f nodes/ray %.2f prims/ray %.2f "
+                 "node-phases %llu (%.1f lanes) tri-phases %llu (%.1f lanes) idle %.1f\n", label, policy, tri_min, refill_min, n_warps, rays.size(),
+                 cost / rays.size(), useful / cost, (double)ts.nodes / rays.size(), (double)ts.prims / rays.size(),
+                 (unsigned long long)node_phases, (double)node_lanes / std::max<uint64_t>(1, node_phases), (unsigned long long)tri_phases,
+                 (double)tri_lanes / std::max<uint64_t>(1, tri_phases), (double)idle_lanes / iters);
+}
+
 extern "C" {
 
 // stats_out[8]: primary, bounce, shadow, aov rays, nodes fetched, prims fetched, wide node count, collapse levels
@@ -271,6 +358,13 @@ int hostsim_render(const rtcuda_scene_desc* d, const rtcuda_settings* st, rtcuda
                     w.ray_o_in = ro[in].data(); w.ray_d_in = rd[in].data(); w.ray_o_out = ro[ot].data(); w.ray_d_out = rd[ot].data();
                     const float t_min = depth == 0 ? sc.camera.near_clip : 0.0001f;
                     const TraverseStats ts_before = ts;
+                    if (std::getenv("HOSTSIM_WARPSIM")) {
+                        std::vector<SimRay> sim(n_rays);
+                        for (uint32_t q = 0; q < n_rays; q++) sim[q] = SimRay{xyz(w.ray_o_in[q]), xyz(w.ray_d_in[q]), t_min, w.ray_o_in[q].w};
+                        char label[32];
+                        std::snprintf(label, sizeof label, "ext d%u", depth);
+                        warp_sim<false>(sc, sim, label);
+                    }
                     for (uint32_t q = 0; q < n_rays; q++) {
                         Hit h;
                         traverse<false, true>(sc, xyz(w.ray_o_in[q]), xyz(w.ray_d_in[q]), t_min, w.ray_o_in[q].w, h, &ts);
@@ -290,6 +384,22 @@ int hostsim_render(const rtcuda_scene_desc* d, const rtcuda_settings* st, rtcuda
                         if (so.n_shadow) squeue[n_shadow++] = so.slot;
                     }
                     uint32_t shadow_rays = 0;
+                    if (std::getenv("HOSTSIM_WARPSIM")) {
+                        std::vector<SimRay> sim;
+                        for (uint32_t i = 0; i < n_shadow; i++) {
+                            const uint32_t slot = squeue[i];
+                            const V3 point = xyz(spoint[slot]);
+                            for (uint32_t j = 0; j < f2u(spoint[slot].w); j++) {
+                                const size_t e = (size_t)j * w.capacity + slot;
+                                if (f2u(sorigin[e].w) & 1u) continue;
+                                const V3 origin = xyz(sorigin[e]), dw = point - origin;
+                                sim.push_back(SimRay{origin, dw / length(dw), 0.001f, scontrib[e].w - 0.001f});
+                            }
+                        }
+                        char label[32];
+                        std::snprintf(label, sizeof label, "shadow d%u", depth);
+                        warp_sim<true>(sc, sim, label);
+                    }
                     for (uint32_t i = 0; i < n_shadow; i++) shadow_body<true>(i, sc, w, &ts, &shadow_rays);
                     stats[2] += shadow_rays;
                     if (std::getenv("HOSTSIM_TRACE"))  // per-depth work profile (DESIGN.md "Measurement": ray-class table)

@@ -205,9 +205,14 @@ def main():
         e2e_call()   # one untimed call: the first allocation of a second set of path-state buffers pays the driver's page mapping
     sync_all()
     e0 = time.time()
+    e2e_each = []
     for _ in range(e2e_steps):
+        t_call = time.time()
         with rc.CudaRenderer(sc, rc.multi_gpu.backend_settings_for_rank(rank, world, local_rank)) as r:
+            t_up = time.time()
             out = r.render(st)
+            t_rn = time.time()
+            e2e_each.append({"upload_build_ms": 1e3 * (t_up - t_call), "render_d2h_ms": 1e3 * (t_rn - t_up), "device_render_ms": r.stats()["render_ms"], "bvh_build_device_ms": r.stats()["bvh_build_ms"], "setup_ms": r.setup_ms})
             if world > 1:   # host frames are tile-disjoint: rank 0 receives the others' tiles
                 tt = torch.from_numpy(out.beauty).to(f"cuda:{local_rank}")
                 dist.reduce(tt, dst=0)
@@ -262,7 +267,7 @@ def main():
             "data": "scene fixture (reference asset), no synthetic data needed", "config": config,
             "wall_s_timed_region": wall, "clocks": clocks.summary(),
             "e2e": {"value": (W * H * spp * e2e_steps) / e2e_s / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "d2h_bytes_per_step": d2h, "steps": e2e_steps, "breakdown": e2e_each,
                     "what": "raytracing_cuda.render(scene, settings): rtcuda_init + scene_upload (H2D, device BVH build) + render + D2H frame"},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
     print(json.dumps(line))

@@ -312,6 +312,11 @@ RTCUDA_API void rtcuda_shutdown(rtcuda_ctx* ctx);
 RTCUDA_API rtcuda_status rtcuda_scene_upload(rtcuda_ctx* ctx, const rtcuda_scene_desc* desc, rtcuda_scene** out_scene);
 RTCUDA_API void rtcuda_scene_release(rtcuda_scene* scene);
 
+/* The path-state arena of a released scene (multi-GB: batches are sized for HBM) is parked per process and reused by
+ * the next scene on the same device, so back-to-back one-shot renders do not pay for mapping device memory again.
+ * This call returns the parked memory to the driver. No reference counterpart (the CPU backend allocates per tile). */
+RTCUDA_API void rtcuda_release_cached_memory(void);
+
 /* Replaces raytracing_cpu::render (lib.rs:645-858). */
 RTCUDA_API rtcuda_status rtcuda_render(rtcuda_scene* scene, const rtcuda_settings* settings, rtcuda_outputs* outputs);
 

@@ -135,7 +135,7 @@ ABI_STRUCTS = [Camera, Shape, Instance, Light, Material, Texture, Image, SceneDe
                Outputs, PixelOutput, Stats]
 
 # every symbol include/rtcuda.h declares
-EXPORTED_SYMBOLS = ["rtcuda_init", "rtcuda_shutdown", "rtcuda_scene_upload", "rtcuda_scene_release", "rtcuda_render",
+EXPORTED_SYMBOLS = ["rtcuda_init", "rtcuda_shutdown", "rtcuda_scene_upload", "rtcuda_scene_release", "rtcuda_release_cached_memory", "rtcuda_render",
                     "rtcuda_render_device", "rtcuda_render_pixel", "rtcuda_get_stats", "rtcuda_last_error",
                     "rtcuda_abi_version", "rtcuda_abi_struct_sizes"]
 
@@ -168,6 +168,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.rtcuda_scene_upload.restype = C.c_int
     lib.rtcuda_scene_release.argtypes = [C.c_void_p]
     lib.rtcuda_scene_release.restype = None
+    lib.rtcuda_release_cached_memory.argtypes = []
+    lib.rtcuda_release_cached_memory.restype = None
     lib.rtcuda_render.argtypes = [C.c_void_p, C.POINTER(Settings), C.POINTER(Outputs)]
     lib.rtcuda_render.restype = C.c_int
     lib.rtcuda_render_device.argtypes = [C.c_void_p, C.POINTER(Settings), C.POINTER(Outputs)]

@@ -7,6 +7,7 @@ library is missing `_ffi.load_library()` raises.
 from __future__ import annotations
 
 import ctypes as C
+import time
 from dataclasses import dataclass
 from typing import List, Optional
 
@@ -44,14 +45,19 @@ class CudaRenderer:
         self._ctx = C.c_void_p()
         self._scene = C.c_void_p()
         bs = self.backend_settings.to_c()
+        t0 = time.perf_counter()
         _ffi.check(self.lib, self.lib.rtcuda_init(C.byref(bs), C.byref(self._ctx)), "rtcuda_init")
+        t1 = time.perf_counter()
         holder = scene.to_desc()
+        t2 = time.perf_counter()
         try:
             _ffi.check(self.lib, self.lib.rtcuda_scene_upload(self._ctx, C.byref(holder.desc), C.byref(self._scene)),
                        "rtcuda_scene_upload")
         except Exception:
             self.close()
             raise
+        # host wall-clock of the three setup phases (reported by bench.py's end-to-end breakdown)
+        self.setup_ms = {"init": 1e3 * (t1 - t0), "scene_to_desc": 1e3 * (t2 - t1), "upload_and_build": 1e3 * (time.perf_counter() - t2)}
         self.width, self.height = scene.camera.raster_width, scene.camera.raster_height
 
     def close(self) -> None:

@@ -11,8 +11,10 @@
 #include <cstdio>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/rtcuda.h"
@@ -43,6 +45,12 @@ struct RtError {
         if (!(cond)) throw RtError{RTCUDA_ERR_INVALID_ARGUMENT, msg}; \
     } while (0)
 
+// Device buffers come from the device's stream-ordered memory pool (cudaMallocAsync on the calling context's stream;
+// the pool keeps freed blocks, rtcuda_init raises its release threshold): a one-shot render creates ~40 buffers for the
+// scene and the BVH build and frees them again, and cudaMalloc / cudaFree serialise on the driver and get slow once tens
+// of GB are mapped in the process.
+static thread_local cudaStream_t tls_stream = nullptr;
+
 template <typename T>
 struct DevBuf {
     T* p = nullptr;
@@ -52,14 +60,14 @@ struct DevBuf {
     DevBuf& operator=(const DevBuf&) = delete;
     ~DevBuf() { release(); }
     void release() {
-        if (p) cudaFree(p);
+        if (p) cudaFreeAsync(p, tls_stream);
         p = nullptr;
         n = 0;
     }
     void alloc(size_t count) {
         release();
         n = count;
-        CK(cudaMalloc((void**)&p, std::max<size_t>(count, 1) * sizeof(T)));
+        CK(cudaMallocAsync((void**)&p, std::max<size_t>(count, 1) * sizeof(T), tls_stream));
     }
     void ensure(size_t count) {
         if (count > n || !p) alloc(count);
@@ -85,6 +93,80 @@ bool is_pow2(uint32_t v) { return v && !(v & (v - 1)); }
 uint32_t bytes_per_sample(uint32_t fmt) { return fmt == RTCUDA_IMAGE_U8 ? 1 : (fmt == RTCUDA_IMAGE_U16 ? 2 : 4); }
 
 }  // namespace
+
+// Path-state arena: one allocation holding every wavefront buffer of a scene. Arenas are multi-GB (the batch is
+// sized for HBM, render_device) and mapping that much fresh device memory costs far more than a 1080p frame's worth
+// of kernels, so a released arena is parked in a per-process cache and handed to the next scene on the same device
+// (a one-shot `render(scene, settings)` call creates and destroys its context every time). rtcuda_release_cached_memory
+// returns the parked memory to the driver.
+struct ArenaCache {
+    struct Slot { int device; void* p; size_t bytes; };
+    std::mutex mu;
+    std::vector<Slot> parked;
+    void* take(int device, size_t need, size_t& got) {  // best fit, or null; smaller parked slots of this device are freed
+        std::lock_guard<std::mutex> g(mu);
+        int best = -1;
+        for (int i = 0; i < (int)parked.size(); i++)
+            if (parked[i].device == device && parked[i].bytes >= need && (best < 0 || parked[i].bytes < parked[best].bytes)) best = i;
+        if (best >= 0) {
+            Slot sl = parked[best];
+            parked.erase(parked.begin() + best);
+            got = sl.bytes;
+            return sl.p;
+        }
+        for (int i = (int)parked.size() - 1; i >= 0; i--)
+            if (parked[i].device == device) { cudaFree(parked[i].p); parked.erase(parked.begin() + i); }
+        return nullptr;
+    }
+    void park(int device, void* p, size_t bytes) {
+        std::lock_guard<std::mutex> g(mu);
+        parked.push_back({device, p, bytes});
+    }
+    size_t parked_bytes(int device) {
+        std::lock_guard<std::mutex> g(mu);
+        size_t b = 0;
+        for (const Slot& sl : parked) if (sl.device == device) b += sl.bytes;
+        return b;
+    }
+    void release_all() {
+        std::lock_guard<std::mutex> g(mu);
+        int cur = 0;
+        cudaGetDevice(&cur);
+        for (const Slot& sl : parked) { cudaSetDevice(sl.device); cudaFree(sl.p); }
+        cudaSetDevice(cur);
+        parked.clear();
+    }
+};
+static ArenaCache g_arena_cache;
+
+struct WaveArena {
+    int device = 0;
+    uint8_t* base = nullptr;
+    size_t bytes = 0, used = 0;
+    WaveArena() = default;
+    WaveArena(const WaveArena&) = delete;
+    WaveArena& operator=(const WaveArena&) = delete;
+    ~WaveArena() { if (base) g_arena_cache.park(device, base, bytes); }
+    void reserve(int dev, size_t need) {
+        used = 0;
+        if (base && bytes >= need) return;
+        if (base) { cudaFree(base); base = nullptr; bytes = 0; }
+        device = dev;
+        size_t got = 0;
+        if (void* p = g_arena_cache.take(dev, need, got)) { base = (uint8_t*)p; bytes = got; return; }
+        CK(cudaMalloc((void**)&base, need));
+        bytes = need;
+    }
+    template <typename T>
+    T* carve(size_t count) {
+        const size_t off = (used + 255) & ~(size_t)255;
+        used = off + count * sizeof(T);
+        if (used > bytes) throw RtError{RTCUDA_ERR_CUDA, "path-state arena overflow"};
+        return (T*)(base + off);
+    }
+};
+template <typename T>
+struct View { T* p = nullptr; size_t n = 0; };
 
 struct rtcuda_ctx {
     int device = 0;
@@ -114,14 +196,13 @@ struct rtcuda_scene {
     DevBuf<uint32_t> pixel_list;
     uint32_t n_my_pixels = 0;
     DevBuf<float4> accum;
-    DevBuf<uint64_t> rng_state;
-    DevBuf<float4> weight, radiance, ray_o[2], ray_d[2], hits, shadow_point, shadow_origin, shadow_contrib;
-    DevBuf<uint32_t> shadow_queue, counters;
+    WaveArena arena;
+    size_t arena_capacity = 0, arena_shadow_k = 0, arena_depth = 0;
+    View<uint64_t> rng_state;
+    View<float4> weight, radiance, ray_o[2], ray_d[2], hits, shadow_point, shadow_origin, shadow_contrib;
+    View<uint32_t> shadow_queue, counters;
     DevBuf<unsigned long long> stats_dev;
-    size_t wave_bytes() const {  // path state currently allocated (reused by the next render)
-        return rng_state.n * 8 + (weight.n + radiance.n + ray_o[0].n + ray_o[1].n + ray_d[0].n + ray_d[1].n + hits.n + shadow_point.n +
-                                  shadow_origin.n + shadow_contrib.n) * 16 + shadow_queue.n * 4;
-    }
+    size_t wave_bytes() const { return arena.bytes + g_arena_cache.parked_bytes(ctx->device); }  // reusable by the next render
     DevBuf<PixelOut> pixel_out;
     // host-API staging planes
     DevBuf<float> d_beauty, d_normals, d_albedo, d_uv, d_mip, d_depth;
@@ -301,14 +382,14 @@ void build_bvh(rtcuda_scene* s, const std::vector<Instance>& instances, uint32_t
     const uint32_t n = n_prims;
     DevBuf<Prim> prims_unsorted;
     DevBuf<float4> aabb_lo, aabb_hi, node_lo, node_hi;
-    DevBuf<uint32_t> bounds_keys, vals, vals_sorted, left, right, parent, range_lo, range_hi, visit, counters;
-    DevBuf<uint64_t> keys, keys_sorted;
+    DevBuf<uint32_t> bounds_keys, vals, vals_sorted, left, right, parent, count, visit, counters, cl_a, cl_b, nn, ploc_out;
+    DevBuf<uint64_t> keys, keys_sorted, scan;
     DevBuf<WorkItem> queue_a, queue_b;
-    DevBuf<uint8_t> sort_temp;
+    DevBuf<uint8_t> sort_temp, scan_temp;
     prims_unsorted.alloc(n); aabb_lo.alloc(n); aabb_hi.alloc(n);
     node_lo.alloc(2 * (size_t)n); node_hi.alloc(2 * (size_t)n);
     bounds_keys.alloc(6); vals.alloc(n); vals_sorted.alloc(n); keys.alloc(n); keys_sorted.alloc(n);
-    left.alloc(n); right.alloc(n); parent.alloc(2 * (size_t)n); range_lo.alloc(n); range_hi.alloc(n); visit.alloc(n);
+    left.alloc(n); right.alloc(n); parent.alloc(2 * (size_t)n); count.alloc(2 * (size_t)n); visit.alloc(n);
     counters.alloc(4);
     queue_a.alloc(n); queue_b.alloc(n);
     s->nodes.alloc(n);   // every wide node consumes at least one binary internal node
@@ -325,15 +406,39 @@ void build_bvh(rtcuda_scene* s, const std::vector<Instance>& instances, uint32_t
     b.vertices = s->vertices.p; b.tris = s->tris.p; b.n = n;
     b.prims_unsorted = prims_unsorted.p; b.aabb_lo = aabb_lo.p; b.aabb_hi = aabb_hi.p; b.bounds_keys = bounds_keys.p;
     b.keys = keys.p; b.vals = vals.p; b.keys_sorted = keys_sorted.p; b.vals_sorted = vals_sorted.p;
-    b.left = left.p; b.right = right.p; b.parent = parent.p; b.range_lo = range_lo.p; b.range_hi = range_hi.p;
+    b.left = left.p; b.right = right.p; b.parent = parent.p; b.count = count.p;
     b.node_lo = node_lo.p; b.node_hi = node_hi.p; b.visit = visit.p;
     b.nodes = s->nodes.p; b.prims = s->prims.p; b.counters = counters.p;
 
     launch_prim_setup(st, b, s->lc);
     launch_morton(st, b, s->lc);
     launch_sort(st, sort_temp.p, temp_bytes, keys.p, keys_sorted.p, vals.p, vals_sorted.p, n, s->lc);
-    launch_karras(st, b, s->lc);
-    launch_refit(st, b, s->lc);
+    const char* builder = std::getenv("RTCUDA_BUILDER");   // A/B aid: "lbvh" selects the Karras tree + refit
+    if (builder && std::strcmp(builder, "lbvh") == 0) {
+        launch_karras(st, b, s->lc);
+        launch_refit(st, b, s->lc);
+    } else {
+        // PLOC: one round = nearest neighbours, flags, scan, merge + compaction; the host reads back the new cluster count
+        cl_a.alloc(n); cl_b.alloc(n); nn.alloc(n); scan.alloc(n); ploc_out.alloc(2);
+        const size_t scan_bytes = ploc_scan_temp_bytes(n);
+        scan_temp.alloc(scan_bytes);
+        b.nn = nn.p; b.scan = scan.p; b.ploc_out = ploc_out.p;
+        b.cl_out = cl_a.p;
+        launch_ploc_init(st, b, s->lc);
+        uint32_t* cin = cl_a.p;
+        uint32_t* cout = cl_b.p;
+        b.m = n; b.next_node = n - 1;
+        while (b.m > 1) {
+            b.cl_in = cin; b.cl_out = cout;
+            launch_ploc_round(st, b, scan_temp.p, scan_bytes, s->lc);
+            uint32_t h_out[2];
+            CK(cudaMemcpyAsync(h_out, ploc_out.p, sizeof h_out, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (h_out[1] == 0 || h_out[0] >= b.m) throw RtError{RTCUDA_ERR_CUDA, "PLOC round made no progress"};
+            b.m = h_out[0]; b.next_node -= h_out[1];
+            std::swap(cin, cout);
+        }
+    }
 
     // collapse, one launch per wide level
     WorkItem root{0u, 0u};
@@ -548,17 +653,24 @@ uint32_t shadow_entries_per_vertex(const rtcuda_scene* s, const RenderParams& rp
 
 // Allocate the wavefront state for `capacity` path slots.
 void ensure_wave(rtcuda_scene* s, uint32_t capacity, uint32_t shadow_k, uint32_t max_depth) {
-    s->rng_state.ensure(capacity);
-    s->weight.ensure(capacity);
-    s->radiance.ensure(capacity);
-    for (int i = 0; i < 2; i++) { s->ray_o[i].ensure(capacity); s->ray_d[i].ensure(capacity); }
-    s->hits.ensure(capacity);
-    s->shadow_queue.ensure(capacity);
-    s->shadow_point.ensure(capacity);
-    s->shadow_origin.ensure((size_t)capacity * std::max(1u, shadow_k));
-    s->shadow_contrib.ensure((size_t)capacity * std::max(1u, shadow_k));
-    s->counters.ensure(4 * ((size_t)max_depth + 3));
     s->stats_dev.ensure(STAT_TOTAL);
+    const size_t k = std::max(1u, shadow_k), n_counters = 4 * ((size_t)max_depth + 3);
+    if (s->arena.base && capacity <= s->arena_capacity && k <= s->arena_shadow_k && max_depth <= s->arena_depth) return;
+    const size_t cap = capacity;
+    const size_t need = cap * (8 + 16 * 8 + 4) + cap * k * 32 + n_counters * 4 + 16 * 256;
+    s->arena.reserve(s->ctx->device, need);
+    auto view = [&](auto& v, size_t count) { v.p = s->arena.carve<std::remove_pointer_t<decltype(v.p)>>(count); v.n = count; };
+    view(s->rng_state, cap);
+    view(s->weight, cap);
+    view(s->radiance, cap);
+    for (int i = 0; i < 2; i++) { view(s->ray_o[i], cap); view(s->ray_d[i], cap); }
+    view(s->hits, cap);
+    view(s->shadow_queue, cap);
+    view(s->shadow_point, cap);
+    view(s->shadow_origin, cap * k);
+    view(s->shadow_contrib, cap * k);
+    view(s->counters, n_counters);
+    s->arena_capacity = capacity; s->arena_shadow_k = k; s->arena_depth = max_depth;
 }
 
 enum { CLS_EXTEND = 0, CLS_SHADE = 1, CLS_SHADOW = 2, CLS_OTHER = 3, CLS_COUNT = 4 };
@@ -667,7 +779,7 @@ void render_device(rtcuda_scene* s, const rtcuda_settings* settings, const rtcud
                 const size_t bytes_per_slot = 8 + 16 + 16 + 4 * 16 + 16 + 4 + 16 + 32 * (size_t)std::max(1u, shadow_k);
                 size_t free_b = 0, total_b = 0;
                 CK(cudaMemGetInfo(&free_b, &total_b));
-                size_t have_b = free_b + s->wave_bytes();
+                const size_t have_b = free_b + s->wave_bytes();
                 capacity = (uint32_t)std::min<size_t>(1u << 26, (size_t)(0.4 * (double)have_b) / bytes_per_slot);
             }
             capacity = std::max(capacity, 1024u);
@@ -831,6 +943,10 @@ RTCUDA_API rtcuda_status rtcuda_init(const rtcuda_backend_settings* settings, rt
         ctx->bs = *settings;
         CK(cudaSetDevice(ctx->device));
         CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        cudaMemPool_t pool;
+        CK(cudaDeviceGetDefaultMemPool(&pool, ctx->device));
+        uint64_t keep = UINT64_MAX;   // freed blocks stay in the pool until rtcuda_release_cached_memory
+        CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
         *out_ctx = ctx.release();
     });
 }
@@ -847,6 +963,7 @@ RTCUDA_API rtcuda_status rtcuda_scene_upload(rtcuda_ctx* ctx, const rtcuda_scene
         REQUIRE(ctx && desc && out_scene, "null argument");
         *out_scene = nullptr;
         CK(cudaSetDevice(ctx->device));
+        tls_stream = ctx->stream;
         auto s = std::make_unique<rtcuda_scene>();
         s->ctx = ctx;
         upload_scene(s.get(), desc);
@@ -854,17 +971,30 @@ RTCUDA_API rtcuda_status rtcuda_scene_upload(rtcuda_ctx* ctx, const rtcuda_scene
     });
 }
 
+RTCUDA_API void rtcuda_release_cached_memory(void) {
+    g_arena_cache.release_all();
+    int dev = 0;
+    cudaMemPool_t pool;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        cudaDeviceSynchronize();
+        cudaMemPoolTrimTo(pool, 0);
+    }
+}
+
 RTCUDA_API void rtcuda_scene_release(rtcuda_scene* scene) {
     if (!scene) return;
     cudaSetDevice(scene->ctx->device);
-    cudaStreamSynchronize(scene->ctx->stream);
+    tls_stream = scene->ctx->stream;
+    cudaStreamSynchronize(tls_stream);
     delete scene;
+    cudaStreamSynchronize(tls_stream);
 }
 
 RTCUDA_API rtcuda_status rtcuda_render(rtcuda_scene* scene, const rtcuda_settings* settings, rtcuda_outputs* outputs) {
     return guarded([&] {
         REQUIRE(scene && settings && outputs, "null argument");
         CK(cudaSetDevice(scene->ctx->device));
+        tls_stream = scene->ctx->stream;
         render_host(scene, settings, outputs);
     });
 }
@@ -873,6 +1003,7 @@ RTCUDA_API rtcuda_status rtcuda_render_device(rtcuda_scene* scene, const rtcuda_
     return guarded([&] {
         REQUIRE(scene && settings && device_outputs, "null argument");
         CK(cudaSetDevice(scene->ctx->device));
+        tls_stream = scene->ctx->stream;
         render_device(scene, settings, device_outputs);
     });
 }
@@ -882,6 +1013,7 @@ RTCUDA_API rtcuda_status rtcuda_render_pixel(rtcuda_scene* scene, const rtcuda_s
     return guarded([&] {
         REQUIRE(scene && settings && (out || sample_hi == sample_lo), "null argument");
         CK(cudaSetDevice(scene->ctx->device));
+        tls_stream = scene->ctx->stream;
         render_pixel(scene, settings, x, y, sample_lo, sample_hi, out);
     });
 }

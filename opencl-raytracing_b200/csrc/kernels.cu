@@ -4,6 +4,7 @@
 // data-parallel plumbing: grid-stride-free one-thread-per-item launches sized from device counters,
 // warp-ballot + block-aggregated queue compaction, and warp-reduced statistics.
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include <algorithm>
 
@@ -297,6 +298,22 @@ __global__ void __launch_bounds__(BLOCK) k_refit(BuildCtx b) {
     const uint32_t i = blockIdx.x * BLOCK + threadIdx.x;
     if (i < b.n) refit_body(i, b);
 }
+__global__ void __launch_bounds__(BLOCK) k_ploc_init(BuildCtx b) {
+    const uint32_t i = blockIdx.x * BLOCK + threadIdx.x;
+    if (i < b.n) ploc_init_body(i, b);
+}
+__global__ void __launch_bounds__(BLOCK) k_ploc_nn(BuildCtx b) {
+    const uint32_t i = blockIdx.x * BLOCK + threadIdx.x;
+    if (i < b.m) ploc_nn_body(i, b);
+}
+__global__ void __launch_bounds__(BLOCK) k_ploc_flag(BuildCtx b) {
+    const uint32_t i = blockIdx.x * BLOCK + threadIdx.x;
+    if (i < b.m) ploc_flag_body(i, b);
+}
+__global__ void __launch_bounds__(BLOCK) k_ploc_merge(BuildCtx b) {
+    const uint32_t i = blockIdx.x * BLOCK + threadIdx.x;
+    if (i < b.m) ploc_merge_body(i, b);
+}
 __global__ void __launch_bounds__(128) k_collapse(BuildCtx b, uint32_t n_items) {
     const uint32_t i = blockIdx.x * 128 + threadIdx.x;
     if (i < n_items) collapse_body(i, b);
@@ -309,6 +326,20 @@ void launch_refit(cudaStream_t st, const BuildCtx& b, LaunchCounter& lc) { k_ref
 void launch_collapse(cudaStream_t st, const BuildCtx& b, uint32_t n_items, LaunchCounter& lc) {
     k_collapse<<<grid_for(n_items, 128), 128, 0, st>>>(b, n_items);
     lc.launches++;
+}
+
+void launch_ploc_init(cudaStream_t st, const BuildCtx& b, LaunchCounter& lc) { k_ploc_init<<<grid_for(b.n), BLOCK, 0, st>>>(b); lc.launches++; }
+size_t ploc_scan_temp_bytes(uint32_t n) {
+    size_t bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, bytes, (uint64_t*)nullptr, (uint64_t*)nullptr, (int)n);
+    return bytes;
+}
+void launch_ploc_round(cudaStream_t st, const BuildCtx& b, void* scan_temp, size_t scan_temp_bytes, LaunchCounter& lc) {
+    k_ploc_nn<<<grid_for(b.m), BLOCK, 0, st>>>(b);
+    k_ploc_flag<<<grid_for(b.m), BLOCK, 0, st>>>(b);
+    cub::DeviceScan::ExclusiveSum(scan_temp, scan_temp_bytes, b.scan, b.scan, (int)b.m, st);  // library prefix sum, like the sort
+    k_ploc_merge<<<grid_for(b.m), BLOCK, 0, st>>>(b);
+    lc.launches += 5;
 }
 
 // The Morton keys are sorted with the toolkit's radix sort (a library call, like cuBLAS for a GEMM);

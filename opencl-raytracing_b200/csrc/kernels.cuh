@@ -33,6 +33,10 @@ void launch_sort(cudaStream_t st, void* temp, size_t temp_bytes, const uint64_t*
 void launch_karras(cudaStream_t st, const BuildCtx& b, LaunchCounter& lc);
 void launch_refit(cudaStream_t st, const BuildCtx& b, LaunchCounter& lc);
 void launch_collapse(cudaStream_t st, const BuildCtx& b, uint32_t n_items, LaunchCounter& lc);
+void launch_ploc_init(cudaStream_t st, const BuildCtx& b, LaunchCounter& lc);
+size_t ploc_scan_temp_bytes(uint32_t n);
+// one PLOC round: nearest neighbours, merge flags, exclusive scan (CUB), merged nodes + compacted cluster list
+void launch_ploc_round(cudaStream_t st, const BuildCtx& b, void* scan_temp, size_t scan_temp_bytes, LaunchCounter& lc);
 
 // mip pyramids
 void launch_to_f32(cudaStream_t st, const uint8_t* src, uint32_t format, float* dst, uint32_t n, LaunchCounter& lc);

@@ -5,11 +5,21 @@
 // rtcBuildBVH (crates/embree4/src/bvh.rs:204-254). Same primitive conventions — one build primitive per
 // triangle of every root-aggregate child with (geomID = child index, primID = triangle index), world-space
 // AABB of the transformed vertices; a sphere is one primitive whose box is the transformed object box
-// (bvh2.rs:208-236) — but a different structure: Morton-code LBVH (Karras 2012) -> SAH-area-guided collapse
-// into 8-wide nodes with quantised child boxes (Ylitie et al. 2017 layout, 80 B).
+// (bvh2.rs:208-236) — but a different structure: a binary tree built on the device from the Morton order of
+// the primitive centroids, then an SAH-area-guided collapse into 8-wide nodes with quantised child boxes
+// (Ylitie et al. 2017 layout, 80 B).
 //
-// Pipeline (one kernel each, see kernels.cu): prim_setup -> morton -> radix sort -> karras -> refit ->
-// collapse (one launch per wide level).
+// Binary tree, two builders over the same sorted Morton keys:
+//   * PLOC (default; Meister & Bittner 2018, parallel locally-ordered clustering): clusters within
+//     PLOC_RADIUS positions of each other in Morton order are merged bottom-up, always the mutually nearest
+//     pairs by surface area of the union. A plain LBVH groups a wall-sized triangle with whatever small
+//     triangles share its Morton neighbourhood and every ray then enters that fat subtree; clustering by
+//     area keeps large primitives near the root. (This takes the place of the "LBVH + SAH treelet refit"
+//     of the plan: same goal, one pass.)
+//   * LBVH (Karras 2012) + bottom-up refit: kept for A/B comparison (RTCUDA_BUILDER=lbvh).
+//
+// Pipeline (one kernel each, see kernels.cu): prim_setup -> morton -> radix sort -> [ploc_init ->
+// (ploc_nn -> scan -> ploc_merge)* | karras -> refit] -> collapse (one launch per wide level).
 #pragma once
 #include "rt_scene.h"
 
@@ -39,9 +49,8 @@ struct BuildCtx {
     // binary tree: internal nodes [0, n-1), leaves [n-1, 2n-1)
     uint32_t* left;
     uint32_t* right;
-    uint32_t* parent;           // 2n-1
-    uint32_t* range_lo;         // internal
-    uint32_t* range_hi;
+    uint32_t* parent;           // 2n-1 (LBVH only)
+    uint32_t* count;            // 2n-1: primitives below each node
     float4* node_lo;            // 2n-1
     float4* node_hi;
     uint32_t* visit;            // n-1 atomic counters
@@ -51,7 +60,17 @@ struct BuildCtx {
     const WorkItem* queue_in;
     WorkItem* queue_out;
     uint32_t* counters;         // [0] next-level size, [1] wide node count, [2] packed prim count
+    // PLOC state
+    const uint32_t* cl_in;      // current clusters (binary node ids) in Morton order
+    uint32_t* cl_out;
+    uint32_t m;                 // number of current clusters
+    uint32_t* nn;               // nearest neighbour position of each cluster
+    uint64_t* scan;             // per cluster: lo 32 = survives into the next round, hi 32 = leads a merge; exclusive-summed in place
+    uint32_t next_node;         // internal node ids are handed out downwards from here, so the last merge creates node 0 (the root)
+    uint32_t* ploc_out;         // [0] clusters after this round, [1] merges of this round
 };
+
+constexpr int PLOC_RADIUS = 16;
 
 RT_HD uint32_t instance_of_prim(const BuildCtx& b, uint32_t i) {
     uint32_t lo = 0, hi = b.instance_count;  // last instance with prim_base <= i
@@ -164,8 +183,7 @@ RT_HD void karras_body(uint32_t idx, const BuildCtx& b) {
     b.right[i] = rc;
     b.parent[lc] = (uint32_t)i;
     b.parent[rc] = (uint32_t)i;
-    b.range_lo[i] = (uint32_t)lo;
-    b.range_hi[i] = (uint32_t)hi;
+    b.count[i] = (uint32_t)(hi - lo + 1);
     if (i == 0) b.parent[0] = NONE;
 }
 
@@ -175,6 +193,7 @@ RT_HD void refit_body(uint32_t k, const BuildCtx& b) {
     uint32_t pi = b.vals_sorted[k];
     b.node_lo[node] = b.aabb_lo[pi];
     b.node_hi[node] = b.aabb_hi[pi];
+    b.count[node] = 1u;
     if (n == 1) return;
     uint32_t cur = b.parent[node];
     while (cur != NONE) {
@@ -198,6 +217,65 @@ RT_HD float half_area(V3 lo, V3 hi) {
     return d.x * d.y + d.y * d.z + d.z * d.x;
 }
 
+// ---- PLOC ------------------------------------------------------------------------------------------------
+RT_HD void ploc_init_body(uint32_t k, const BuildCtx& b) {
+    const uint32_t node = b.n - 1 + k;
+    const uint32_t pi = b.vals_sorted[k];
+    b.node_lo[node] = b.aabb_lo[pi];
+    b.node_hi[node] = b.aabb_hi[pi];
+    b.count[node] = 1u;
+    b.cl_out[k] = node;
+}
+
+// nearest neighbour of cluster i among the clusters within PLOC_RADIUS positions: smallest union area, ties to the
+// lower position (with this order the globally best pair is always mutual, so every round merges something)
+RT_HD void ploc_nn_body(uint32_t i, const BuildCtx& b) {
+    const uint32_t ci = b.cl_in[i];
+    const V3 lo = xyz(b.node_lo[ci]), hi = xyz(b.node_hi[ci]);
+    const uint32_t j0 = i > (uint32_t)PLOC_RADIUS ? i - PLOC_RADIUS : 0u;
+    const uint32_t j1 = i + PLOC_RADIUS < b.m - 1 ? i + PLOC_RADIUS : b.m - 1;
+    float best = RT_INF;
+    uint32_t bj = NONE;
+    for (uint32_t j = j0; j <= j1; j++) {
+        if (j == i) continue;
+        const uint32_t cj = b.cl_in[j];
+        const float a = half_area(vmin(lo, xyz(b.node_lo[cj])), vmax(hi, xyz(b.node_hi[cj])));
+        if (a < best || bj == NONE) { best = a; bj = j; }
+    }
+    b.nn[i] = bj;
+}
+// flags for the scan: lo word = the cluster (or the merged node that replaces it) is in the next round, hi word = merge leader
+RT_HD void ploc_flag_body(uint32_t i, const BuildCtx& b) {
+    const uint32_t j = b.nn[i];
+    const bool mutual = j != NONE && b.nn[j] == i;
+    const bool leader = mutual && i < j, absorbed = mutual && i > j;
+    b.scan[i] = (absorbed ? 0ull : 1ull) | (leader ? (1ull << 32) : 0ull);
+}
+// after the exclusive sum of the flags: create the merged nodes and compact the cluster list, order preserved
+RT_HD void ploc_merge_body(uint32_t i, const BuildCtx& b) {
+    const uint32_t j = b.nn[i];
+    const bool mutual = j != NONE && b.nn[j] == i;
+    const uint64_t ex = b.scan[i];
+    const uint32_t pos = (uint32_t)ex, rank = (uint32_t)(ex >> 32);
+    if (mutual && i > j) {
+        if (i == b.m - 1) { b.ploc_out[0] = pos; b.ploc_out[1] = rank; }
+        return;
+    }
+    uint32_t id = b.cl_in[i];
+    if (mutual) {
+        const uint32_t l = id, r = b.cl_in[j];
+        id = b.next_node - 1u - rank;
+        b.left[id] = l;
+        b.right[id] = r;
+        const V3 lo = vmin(xyz(b.node_lo[l]), xyz(b.node_lo[r])), hi = vmax(xyz(b.node_hi[l]), xyz(b.node_hi[r]));
+        b.node_lo[id] = make_float4(lo.x, lo.y, lo.z, 0.0f);
+        b.node_hi[id] = make_float4(hi.x, hi.y, hi.z, 0.0f);
+        b.count[id] = b.count[l] + b.count[r];
+    }
+    b.cl_out[pos] = id;
+    if (i == b.m - 1) { b.ploc_out[0] = pos + 1u; b.ploc_out[1] = rank + (mutual ? 1u : 0u); }
+}
+
 // One wide node per work item: gather up to 8 children by repeatedly opening the binary child with
 // the largest surface area, order them into octant slots, quantise, emit child work items.
 RT_HD void collapse_body(uint32_t item_idx, const BuildCtx& b) {
@@ -216,7 +294,7 @@ RT_HD void collapse_body(uint32_t item_idx, const BuildCtx& b) {
             for (int c = 0; c < nc; c++) {
                 uint32_t nd = ch[c];
                 if (nd >= first_leaf) continue;
-                uint32_t cnt = b.range_hi[nd] - b.range_lo[nd] + 1;
+                uint32_t cnt = b.count[nd];
                 if (stage == 0 && cnt <= LEAF_MAX) continue;
                 float a = half_area(xyz(b.node_lo[nd]), xyz(b.node_hi[nd]));
                 if (a > best_area) { best_area = a; best = c; }
@@ -284,7 +362,7 @@ RT_HD void collapse_body(uint32_t item_idx, const BuildCtx& b) {
         int c = child_in[s];
         if (c < 0) continue;
         uint32_t nd = ch[c];
-        uint32_t cnt = nd >= first_leaf ? 1u : (b.range_hi[nd] - b.range_lo[nd] + 1);
+        uint32_t cnt = b.count[nd];
         if (cnt <= LEAF_MAX) n_leaf_prims += cnt; else n_internal++;
     }
     const uint32_t child_base = n_internal ? atomic_add_u32(&b.counters[1], n_internal) : 0u;
@@ -299,8 +377,7 @@ RT_HD void collapse_body(uint32_t item_idx, const BuildCtx& b) {
         int c = child_in[s];
         if (c < 0) continue;
         uint32_t nd = ch[c];
-        bool is_leaf_node = nd >= first_leaf;
-        uint32_t cnt = is_leaf_node ? 1u : (b.range_hi[nd] - b.range_lo[nd] + 1);
+        uint32_t cnt = b.count[nd];
         const float cl[3] = {clo[c].x, clo[c].y, clo[c].z}, chh[3] = {chi[c].x, chi[c].y, chi[c].z};
         for (int a = 0; a < 3; a++) {
             float ql = floorf((cl[a] - lov[a]) / scale[a]);
@@ -315,9 +392,14 @@ RT_HD void collapse_body(uint32_t item_idx, const BuildCtx& b) {
         }
         if (cnt <= LEAF_MAX) {
             meta[s] = (((1u << cnt) - 1u) << 5) | k_prim;
-            uint32_t first = is_leaf_node ? (nd - first_leaf) : b.range_lo[nd];
-            for (uint32_t k = 0; k < cnt; k++) b.prims[prim_base + k_prim + k] = b.prims_unsorted[b.vals_sorted[first + k]];
-            k_prim += cnt;
+            uint32_t walk[4];  // the <= LEAF_MAX leaves of this subtree, left to right
+            int wsp = 0;
+            walk[wsp++] = nd;
+            while (wsp) {
+                const uint32_t x = walk[--wsp];
+                if (x >= first_leaf) b.prims[prim_base + k_prim++] = b.prims_unsorted[b.vals_sorted[x - first_leaf]];
+                else { walk[wsp++] = b.right[x]; walk[wsp++] = b.left[x]; }
+            }
         } else {
             meta[s] = (1u << 5) | (24u + (uint32_t)s);
             imask |= 1u << s;

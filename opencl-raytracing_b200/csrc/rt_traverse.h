@@ -92,9 +92,9 @@ RT_HD uint32_t byte_of(uint32_t w) {
 //   next      — refill the current groups from the stack; false when the walk is complete.
 // Pending primitive groups can be postponed: node_step stashes a non-empty one on the stack (entries with no
 // bits in the top byte are primitive groups). The closest hit is independent of the order in which primitives
-// are tested: equal-t ties go to the larger primitive index (the reference resolves them by its own BVH2 leaf
+// are tested: equal-t ties go to the larger (geom_id, prim_id) (the reference resolves them by its own BVH2 leaf
 // order, "later hit overwrites", geometry.rs:335 / accel.rs:159-171, which no other tree can reproduce), so
-// frames stay bit-reproducible although lanes pick up rays dynamically.
+// frames stay bit-reproducible although lanes pick up rays dynamically and the builder packs primitives with atomics.
 template <bool ANY_HIT, bool STATS>
 struct Traversal {
     V3 o, d, idir;
@@ -104,12 +104,14 @@ struct Traversal {
     uint2* stack;  // TRAVERSE_STACK entries of thread-local memory owned by the caller (keeps the scalar state in registers)
     int sp;
     Hit hit;
+    uint32_t hit_geom, hit_pid;  // ids of the current closest hit (tie-break)
     bool found;
 
     RT_HD bool init(const SceneD& sc, V3 o_, V3 d_, float t_min_, float t_max_) {
         o = o_; d = d_; t_min = t_min_; closest = t_max_;
         hit.prim = NONE; hit.t = t_max_; hit.u = hit.v = 0.0f;
         found = false;
+        hit_geom = hit_pid = 0u;
         sp = 0;
         idir = mk3(safe_rcp_dir(d.x), safe_rcp_dir(d.y), safe_rcp_dir(d.z));
         octinv = 7u - ((d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u));
@@ -212,7 +214,10 @@ struct Traversal {
             V3 oo = apply_point(inst->w2o, o), od = apply_vector(inst->w2o, d);
             h = sphere_t(xyz(pa), pb.x, oo, od, t_min, closest, t);
         }
-        if (h && (t < closest || hit.prim == NONE || pi > hit.prim)) {
+        const uint32_t geom = f2u(pa.w), pid = f2u(pb.w);
+        if (h && (t < closest || hit.prim == NONE || geom > hit_geom || (geom == hit_geom && pid > hit_pid))) {
+            hit_geom = geom;
+            hit_pid = pid;
             closest = t;
             hit.t = t;
             hit.prim = pi;

@@ -142,7 +142,7 @@ void build(HostScene& hs, const rtcuda_scene_desc* d) {
     const uint32_t n = n_prims;
     std::vector<Prim> prims_unsorted(n);
     std::vector<float4> aabb_lo(n), aabb_hi(n), node_lo(2 * (size_t)n), node_hi(2 * (size_t)n);
-    std::vector<uint32_t> vals(n), vals_sorted(n), left(n), right(n), parent(2 * (size_t)n), range_lo(n), range_hi(n), visit(n, 0);
+    std::vector<uint32_t> vals(n), vals_sorted(n), left(n), right(n), parent(2 * (size_t)n), count(2 * (size_t)n), visit(n, 0);
     std::vector<uint64_t> keys(n), keys_sorted(n);
     std::vector<WorkItem> qa(n), qb(n);
     uint32_t bounds_keys[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0, 0, 0};
@@ -151,7 +151,7 @@ void build(HostScene& hs, const rtcuda_scene_desc* d) {
     b.instances = hs.instances.data(); b.instance_count = d->instance_count; b.vertices = d->vertices; b.tris = d->tris; b.n = n;
     b.prims_unsorted = prims_unsorted.data(); b.aabb_lo = aabb_lo.data(); b.aabb_hi = aabb_hi.data(); b.bounds_keys = bounds_keys;
     b.keys = keys.data(); b.vals = vals.data(); b.keys_sorted = keys_sorted.data(); b.vals_sorted = vals_sorted.data();
-    b.left = left.data(); b.right = right.data(); b.parent = parent.data(); b.range_lo = range_lo.data(); b.range_hi = range_hi.data();
+    b.left = left.data(); b.right = right.data(); b.parent = parent.data(); b.count = count.data();
     b.node_lo = node_lo.data(); b.node_hi = node_hi.data(); b.visit = visit.data();
     b.nodes = hs.nodes.data(); b.prims = hs.prims.data(); b.counters = counters;
     for (uint32_t i = 0; i < n; i++) prim_setup_body(i, b);
@@ -160,8 +160,31 @@ void build(HostScene& hs, const rtcuda_scene_desc* d) {
     std::iota(order.begin(), order.end(), 0u);
     std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return keys[x] < keys[y]; });
     for (uint32_t i = 0; i < n; i++) { keys_sorted[i] = keys[order[i]]; vals_sorted[i] = vals[order[i]]; }
-    for (uint32_t i = 0; i + 1 < n; i++) karras_body(i, b);
-    for (uint32_t i = 0; i < n; i++) refit_body(i, b);
+    const char* builder = std::getenv("RTCUDA_BUILDER");
+    if (builder && std::strcmp(builder, "lbvh") == 0) {
+        for (uint32_t i = 0; i + 1 < n; i++) karras_body(i, b);
+        for (uint32_t i = 0; i < n; i++) refit_body(i, b);
+    } else {  // PLOC (api.cu build_bvh): rounds of nearest-neighbour search, flag scan, merge + compaction
+        std::vector<uint32_t> cl_a(n), cl_b(n), nn(n);
+        std::vector<uint64_t> scan(n);
+        uint32_t ploc_out[2] = {0, 0};
+        b.nn = nn.data(); b.scan = scan.data(); b.ploc_out = ploc_out;
+        b.cl_out = cl_a.data();
+        for (uint32_t k = 0; k < n; k++) ploc_init_body(k, b);
+        uint32_t* cin = cl_a.data();
+        uint32_t* cout = cl_b.data();
+        b.m = n; b.next_node = n - 1;
+        while (b.m > 1) {
+            b.cl_in = cin; b.cl_out = cout;
+            for (uint32_t i = 0; i < b.m; i++) ploc_nn_body(i, b);
+            for (uint32_t i = 0; i < b.m; i++) ploc_flag_body(i, b);
+            uint64_t run = 0;
+            for (uint32_t i = 0; i < b.m; i++) { const uint64_t f = scan[i]; scan[i] = run; run += f; }
+            for (uint32_t i = 0; i < b.m; i++) ploc_merge_body(i, b);
+            b.m = ploc_out[0]; b.next_node -= ploc_out[1];
+            std::swap(cin, cout);
+        }
+    }
     qa[0] = WorkItem{0, 0};
     uint32_t n_items = 1;
     WorkItem* qin = qa.data();

@@ -185,6 +185,7 @@ struct rtcuda_scene {
     DevBuf<Instance> instances;
     DevBuf<ShapeD> shapes;
     DevBuf<LightD> lights;
+    DevBuf<LightTri> light_tris;
     DevBuf<MaterialD> materials;
     DevBuf<TextureD> textures;
     DevBuf<ImageD> images;
@@ -198,9 +199,11 @@ struct rtcuda_scene {
     DevBuf<float4> accum;
     WaveArena arena;
     size_t arena_capacity = 0, arena_shadow_k = 0, arena_depth = 0;
-    View<uint64_t> rng_state;
-    View<float4> weight, radiance, ray_o[2], ray_d[2], hits, shadow_point, shadow_origin, shadow_contrib;
-    View<uint32_t> shadow_queue, counters;
+    View<RngState> rng_state;
+    View<float4> weight, radiance, ray_o[2], ray_d[2], hits, sray_o, sray_d, scontrib;
+    View<uint4> svertex;
+    View<uint32_t> counters;
+    View<unsigned long long> counters64;
     DevBuf<unsigned long long> stats_dev;
     size_t wave_bytes() const { return arena.bytes + g_arena_cache.parked_bytes(ctx->device); }  // reusable by the next render
     DevBuf<PixelOut> pixel_out;
@@ -534,6 +537,7 @@ void upload_scene(rtcuda_scene* s, const rtcuda_scene_desc* d) {
     // instances without primitives (empty meshes) would break the prim -> instance search: give them an
     // empty range that the search skips (prim_base is non-decreasing; the LAST instance with base <= i wins)
     std::vector<LightD> lights(d->light_count);
+    uint64_t n_light_tris = 0;
     for (uint32_t i = 0; i < d->light_count; i++) {
         const rtcuda_light& a = d->lights[i];
         LightD& b = lights[i];
@@ -541,6 +545,11 @@ void upload_scene(rtcuda_scene* s, const rtcuda_scene_desc* d) {
         std::memcpy(b.a, a.position_or_direction, sizeof b.a);
         std::memcpy(b.b, a.intensity_or_radiance, sizeof b.b);
         b.light_to_world = to_m4(a.light_to_world);
+        b.tri_table = 0;
+        if (a.kind == RTCUDA_LIGHT_DIFFUSE_AREA) {
+            b.tri_table = (uint32_t)n_light_tris;
+            n_light_tris += d->shapes[a.shape].tri_count;
+        }
     }
     s->host_lights.assign(d->lights, d->lights + d->light_count);
     std::vector<MaterialD> materials(d->material_count);
@@ -571,11 +580,16 @@ void upload_scene(rtcuda_scene* s, const rtcuda_scene_desc* d) {
     s->textures.upload(textures.data(), textures.size(), st);
     s->images.upload(images.data(), images.size(), st);
     s->mips.upload(chains.data(), chains.size(), st);
+    s->light_tris.alloc(n_light_tris);
+    for (uint32_t i = 0; i < d->light_count; i++)
+        if (lights[i].kind == RTCUDA_LIGHT_DIFFUSE_AREA)
+            launch_light_tris(st, s->shapes.p, lights[i].shape, shapes[lights[i].shape].tri_count, s->vertices.p, s->tris.p,
+                              s->light_tris.p + lights[i].tri_table, s->lc);
     CK(cudaStreamSynchronize(st));  // host vectors die at scope end
     CK(cudaEventRecord(e1, st));
 
     SceneD& sc = s->sc;
-    sc.instances = s->instances.p; sc.shapes = s->shapes.p; sc.lights = s->lights.p; sc.materials = s->materials.p;
+    sc.instances = s->instances.p; sc.shapes = s->shapes.p; sc.lights = s->lights.p; sc.light_tris = s->light_tris.p; sc.materials = s->materials.p;
     sc.textures = s->textures.p; sc.images = s->images.p; sc.mips = s->mips.p; sc.image_bytes = s->image_bytes.p;
     sc.vertices = s->vertices.p; sc.tris = s->tris.p; sc.normals = s->normals.p; sc.uvs = s->uvs.p;
     sc.instance_count = d->instance_count; sc.light_count = d->light_count; sc.material_count = d->material_count;
@@ -657,7 +671,8 @@ void ensure_wave(rtcuda_scene* s, uint32_t capacity, uint32_t shadow_k, uint32_t
     const size_t k = std::max(1u, shadow_k), n_counters = 4 * ((size_t)max_depth + 3);
     if (s->arena.base && capacity <= s->arena_capacity && k <= s->arena_shadow_k && max_depth <= s->arena_depth) return;
     const size_t cap = capacity;
-    const size_t need = cap * (8 + 16 * 8 + 4) + cap * k * 32 + n_counters * 4 + 16 * 256;
+    REQUIRE((uint64_t)cap * k < (1ull << 32), "paths in flight x light samples per vertex must stay below 2^32");
+    const size_t need = cap * (16 + 16 * 7 + 16) + cap * k * 48 + n_counters * 4 + ((size_t)max_depth + 3) * 8 + 16 * 256;
     s->arena.reserve(s->ctx->device, need);
     auto view = [&](auto& v, size_t count) { v.p = s->arena.carve<std::remove_pointer_t<decltype(v.p)>>(count); v.n = count; };
     view(s->rng_state, cap);
@@ -665,11 +680,12 @@ void ensure_wave(rtcuda_scene* s, uint32_t capacity, uint32_t shadow_k, uint32_t
     view(s->radiance, cap);
     for (int i = 0; i < 2; i++) { view(s->ray_o[i], cap); view(s->ray_d[i], cap); }
     view(s->hits, cap);
-    view(s->shadow_queue, cap);
-    view(s->shadow_point, cap);
-    view(s->shadow_origin, cap * k);
-    view(s->shadow_contrib, cap * k);
+    view(s->svertex, cap);
+    view(s->sray_o, cap * k);
+    view(s->sray_d, cap * k);
+    view(s->scontrib, cap * k);
     view(s->counters, n_counters);
+    view(s->counters64, (size_t)max_depth + 3);
     s->arena_capacity = capacity; s->arena_shadow_k = k; s->arena_depth = max_depth;
 }
 
@@ -701,10 +717,11 @@ void run_batch(rtcuda_scene* s, const RenderParams& rp, Wave w, uint32_t n_paths
     const bool timing = (s->ctx->bs.collect_stats & RTCUDA_STATS_KERNEL_TIMES) != 0;
     const uint32_t max_depth = rp.max_ray_depth;
     uint32_t* rays = s->counters.p;                       // rays[d]: queue length at depth d
-    uint32_t* shadows = s->counters.p + (max_depth + 3);  // shadows[d]
-    uint32_t* fetch_ext = s->counters.p + 2 * (max_depth + 3);  // work-fetch cursors of the persistent kernels
-    uint32_t* fetch_sh = s->counters.p + 3 * (max_depth + 3);
+    uint32_t* fetch_ext = s->counters.p + (max_depth + 3);      // work-fetch cursors of the persistent kernels
+    uint32_t* fetch_sh = s->counters.p + 2 * (max_depth + 3);
+    unsigned long long* shadows = s->counters64.p;              // shadows[d]: NEE vertices | shadow rays << 32
     CK(cudaMemsetAsync(s->counters.p, 0, 4 * ((size_t)max_depth + 3) * 4, st));
+    CK(cudaMemsetAsync(s->counters64.p, 0, ((size_t)max_depth + 3) * 8, st));
     w.depth = 0;
     w.ray_o_out = s->ray_o[0].p;
     w.ray_d_out = s->ray_d[0].p;
@@ -718,7 +735,7 @@ void run_batch(rtcuda_scene* s, const RenderParams& rp, Wave w, uint32_t n_paths
         w.n_in = rays + depth; w.n_out = rays + depth + 1; w.n_shadow = shadows + depth;
         { SpanGuard g(s, CLS_EXTEND, timing); launch_extend(st, s->sc, w, n_paths, depth == 0 ? s->sc.camera.near_clip : 0.0001f, fetch_ext + depth, collect, s->lc); }
         { SpanGuard g(s, CLS_SHADE, timing); launch_shade(st, s->sc, rp, w, n_paths, s->lc); }
-        if (depth < max_depth && w.shadow_k) { SpanGuard g(s, CLS_SHADOW, timing); launch_shadow(st, s->sc, w, n_paths, fetch_sh + depth, collect, s->lc); }
+        if (depth < max_depth && w.shadow_k) { SpanGuard g(s, CLS_SHADOW, timing); launch_shadow(st, s->sc, w, (uint32_t)std::min<uint64_t>(0xffffffffull, (uint64_t)n_paths * std::max(1u, w.shadow_k)), fetch_sh + depth, collect, s->lc); }
     }
 }
 
@@ -776,7 +793,7 @@ void render_device(rtcuda_scene* s, const rtcuda_settings* settings, const rtcud
             if (!capacity)
                 if (const char* env = std::getenv("RTCUDA_MAX_PATHS")) capacity = (uint32_t)std::strtoul(env, nullptr, 0);  // tuning aid
             if (!capacity) {
-                const size_t bytes_per_slot = 8 + 16 + 16 + 4 * 16 + 16 + 4 + 16 + 32 * (size_t)std::max(1u, shadow_k);
+                const size_t bytes_per_slot = 16 + 16 * 7 + 16 + 48 * (size_t)std::max(1u, shadow_k);
                 size_t free_b = 0, total_b = 0;
                 CK(cudaMemGetInfo(&free_b, &total_b));
                 const size_t have_b = free_b + s->wave_bytes();
@@ -793,8 +810,8 @@ void render_device(rtcuda_scene* s, const rtcuda_settings* settings, const rtcud
             w.capacity = np_batch * ns_batch;
             w.rng_state = s->rng_state.p; w.weight = s->weight.p; w.radiance = s->radiance.p; w.hits = s->hits.p;
             w.stats = s->stats_dev.p;
-            w.shadow_k = shadow_k; w.shadow_queue = s->shadow_queue.p; w.shadow_point = s->shadow_point.p;
-            w.shadow_origin = s->shadow_origin.p; w.shadow_contrib = s->shadow_contrib.p;
+            w.shadow_k = shadow_k; w.svertex = s->svertex.p;
+            w.sray_o = s->sray_o.p; w.sray_d = s->sray_d.p; w.scontrib = s->scontrib.p;
             for (uint32_t p0 = 0; p0 < np_all; p0 += np_batch) {
                 const uint32_t np = std::min(np_batch, np_all - p0);
                 for (uint32_t s0 = 0; s0 < settings->samples_per_pixel; s0 += ns_batch) {
@@ -896,8 +913,8 @@ void render_pixel(rtcuda_scene* s, const rtcuda_settings* settings, uint32_t x, 
     w.pixel_base = 0; w.n_pixels = 1; w.sample_base = lo; w.n_samples = n; w.capacity = n;
     w.rng_state = s->rng_state.p; w.weight = s->weight.p; w.radiance = s->radiance.p; w.hits = s->hits.p;
     w.stats = s->stats_dev.p;
-    w.shadow_k = shadow_k; w.shadow_queue = s->shadow_queue.p; w.shadow_point = s->shadow_point.p;
-    w.shadow_origin = s->shadow_origin.p; w.shadow_contrib = s->shadow_contrib.p;
+    w.shadow_k = shadow_k; w.svertex = s->svertex.p;
+    w.sray_o = s->sray_o.p; w.sray_d = s->sray_d.p; w.scontrib = s->scontrib.p;
     s->spans.clear();
     s->ev_used = 0;
     run_batch(s, rp, w, n, false);

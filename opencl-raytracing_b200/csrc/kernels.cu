@@ -117,38 +117,57 @@ __global__ void __launch_bounds__(BLOCK) k_extend(const __grid_constant__ SceneD
 
 // Shading: persistent blocks walk the ray queue in block-sized chunks (the live queue length is only known on the
 // device; a grid sized for the whole batch spent a third of its warp time in blocks that found nothing to do,
-// profiles/r1_notes.md). Survivors and NEE vertices are pushed with one global atomic per block per queue.
+// profiles/r1_notes.md). Per chunk ONE block-wide scan hands out the positions of all three outputs — continuation
+// rays, NEE vertices, shadow rays (a variable number per thread, consecutive per vertex) — and two threads issue
+// the block's global atomics (one per queue counter).
 __global__ void __launch_bounds__(BLOCK) k_shade(const __grid_constant__ SceneD sc, const __grid_constant__ RenderParams rp,
                                                   const __grid_constant__ Wave w) {
-    __shared__ uint32_t s_count[2], s_base[2];
+    __shared__ unsigned long long s_warp[BLOCK / 32][2];   // per warp: [0] continuation rays, [1] vertices | shadow rays << 32
+    __shared__ unsigned long long s_base[2];
     const uint32_t n = *w.n_in;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&w.stats[STAT_SHADED], (unsigned long long)n);
     for (uint32_t base = blockIdx.x * BLOCK; base < n; base += gridDim.x * BLOCK) {
-        if (threadIdx.x < 2) s_count[threadIdx.x] = 0;
-        __syncthreads();
         const uint32_t q = base + threadIdx.x;
-        ShadeOut o;
-        o.continue_path = false;
-        o.n_shadow = 0;
-        o.slot = 0;
-        if (q < n) shade_body(q, sc, rp, w, o);
-        const uint32_t rpos = block_push(o.continue_path, w.n_out, &s_count[0], &s_base[0]);
-        if (o.continue_path) {
-            w.ray_o_out[rpos] = make_float4(o.next.o.x, o.next.o.y, o.next.o.z, RT_INF);
-            w.ray_d_out[rpos] = make_float4(o.next.d.x, o.next.d.y, o.next.d.z, u2f(o.slot));
-        }
-        const uint32_t spos = block_push(o.n_shadow != 0, w.n_shadow, &s_count[1], &s_base[1]);
-        if (o.n_shadow != 0) w.shadow_queue[spos] = o.slot;
+        shade_vertex(q < n, q, sc, rp, w, [&](bool cont, bool has_vertex, uint32_t k, uint32_t& rpos, uint32_t& vpos, uint32_t& first) {
+            const unsigned FULL = 0xffffffffu;
+            const unsigned mc = __ballot_sync(FULL, cont), mv = __ballot_sync(FULL, has_vertex);
+            uint32_t incl = k;   // inclusive warp scan of the shadow-ray counts
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t up = __shfl_up_sync(FULL, incl, o);
+                if ((int)lane >= o) incl += up;
+            }
+            if (lane == 31) {
+                s_warp[warp][0] = (unsigned long long)__popc(mc);
+                s_warp[warp][1] = (unsigned long long)__popc(mv) | ((unsigned long long)incl << 32);
+            }
+            __syncthreads();
+            unsigned long long before0 = 0, before1 = 0, total0 = 0, total1 = 0;
+#pragma unroll
+            for (int i = 0; i < BLOCK / 32; i++) {
+                const unsigned long long a = s_warp[i][0], b = s_warp[i][1];
+                if (i < (int)warp) { before0 += a; before1 += b; }
+                total0 += a; total1 += b;
+            }
+            if (threadIdx.x == 0) s_base[0] = total0 ? (unsigned long long)atomicAdd(w.n_out, (uint32_t)total0) : 0ull;
+            if (threadIdx.x == 32) s_base[1] = total1 ? atomicAdd(w.n_shadow, total1) : 0ull;
+            __syncthreads();
+            const unsigned lt = (1u << lane) - 1u;
+            const unsigned long long b1 = s_base[1] + before1;
+            rpos = (uint32_t)(s_base[0] + before0) + (uint32_t)__popc(mc & lt);
+            vpos = (uint32_t)b1 + (uint32_t)__popc(mv & lt);
+            first = (uint32_t)(b1 >> 32) + (incl - k);
+        });
     }
 }
 
-// `occluded` (lights.rs:159-168) for every pending light sample of a path vertex. The work item is the vertex:
-// its <= K rays are walked one after the other by the same lane and their unoccluded contributions added once,
-// in order (deterministic, no float atomics). Lanes that need a ray — the next one of their vertex, or a new
-// vertex from the queue — set it up together at the top of the loop, like k_extend's refill.
+// `occluded` (lights.rs:159-168): any-hit traversal of the compacted shadow-ray queue, same persistent refill / phase
+// vote loop as k_extend. A blocked ray zeroes its contribution entry; k_shadow_gather then adds each vertex's
+// entries to the path in light-sample order (deterministic: one thread per vertex, no float atomics).
 template <bool STATS>
 __global__ void __launch_bounds__(BLOCK) k_shadow(const __grid_constant__ SceneD sc, const __grid_constant__ Wave w, uint32_t* fetch_counter) {
-    const uint32_t n = *w.n_shadow;
+    const uint32_t n = (uint32_t)(*w.n_shadow >> 32);
     const unsigned FULL = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
     uint2 stack_mem[TRAVERSE_STACK];
@@ -156,62 +175,33 @@ __global__ void __launch_bounds__(BLOCK) k_shadow(const __grid_constant__ SceneD
     tr.stack = stack_mem;
     TraverseStats ts;
     ts.nodes = ts.prims = 0;
-    bool have_ray = false, exhausted = n == 0;
-    uint32_t slot = 0, k = 0, j = 0, n_rays = 0;   // j == k: no vertex
-    V3 point = mk3(0.0f), sum = mk3(0.0f), contrib = mk3(0.0f);
+    bool have = false, exhausted = n == 0;
+    uint32_t q = 0, n_rays = 0;
     for (;;) {
-        const bool want_vertex = !have_ray && j == k;
-        const unsigned need_vertex = exhausted ? 0u : __ballot_sync(FULL, want_vertex);
-        const unsigned need_ray = __ballot_sync(FULL, !have_ray && (j < k || !exhausted));
-        if (__ballot_sync(FULL, have_ray || j < k) == 0u && exhausted) break;
-        if (__popc(need_ray) >= REFILL_MIN || __ballot_sync(FULL, have_ray) == 0u) {
-            if (need_vertex) {
-                const int cnt = __popc(need_vertex), leader = __ffs(need_vertex) - 1;
-                uint32_t base = 0;
-                if ((int)lane == leader) base = atomicAdd(fetch_counter, (uint32_t)cnt);
-                base = __shfl_sync(FULL, base, leader);
-                if (want_vertex) {
-                    const uint32_t mine = base + (uint32_t)__popc(need_vertex & lt);
-                    if (mine < n) {
-                        slot = w.shadow_queue[mine];
-                        const float4 p4 = w.shadow_point[slot];
-                        point = xyz(p4);
-                        k = f2u(p4.w);
-                        j = 0;
-                        sum = mk3(0.0f);
-                    }
-                }
-                if (base + (uint32_t)cnt >= n) exhausted = true;
-            }
-            if (!have_ray && j < k) {
-                // next entry of this vertex that needs an occlusion test
-                do {
-                    const size_t e = (size_t)j * w.capacity + slot;
-                    const float4 o4 = w.shadow_origin[e], c4 = w.shadow_contrib[e];
-                    contrib = xyz(c4);
-                    if (!(f2u(o4.w) & 1u)) {
-                        const V3 origin = xyz(o4);
-                        const V3 dir_world = point - origin;
-                        const float d = length(dir_world);
+        const unsigned need = __ballot_sync(FULL, !have);
+        if (need == FULL && exhausted) break;
+        if (!exhausted && __popc(need) >= REFILL_MIN) {
+            const int cnt = __popc(need), leader = __ffs(need) - 1;
+            uint32_t base = 0;
+            if ((int)lane == leader) base = atomicAdd(fetch_counter, (uint32_t)cnt);
+            base = __shfl_sync(FULL, base, leader);
+            if (!have) {
+                const uint32_t mine = base + (uint32_t)__popc(need & lt);
+                if (mine < n) {
+                    q = mine;
+                    const float4 o4 = w.sray_o[q], d4 = w.sray_d[q];
+                    if (o4.w >= 0.0f) {   // negative: never occluded (non-finite origin quirk), not traced
                         n_rays++;
-                        have_ray = tr.init(sc, origin, dir_world / d, 0.001f, c4.w - 0.001f);
+                        have = tr.init(sc, xyz(o4), xyz(d4), 0.001f, o4.w);
                     }
-                    if (!have_ray) { sum += contrib; j++; }  // never occluded (non-finite origin quirk, or an empty scene)
-                } while (!have_ray && j < k);
-                if (!have_ray) {  // vertex finished without a traversal
-                    const float4 r = w.radiance[slot];
-                    w.radiance[slot] = make_float4(r.x + sum.x, r.y + sum.y, r.z + sum.z, 0.0f);
                 }
             }
+            if (base + (uint32_t)cnt >= n) exhausted = true;
         }
-        warp_phase(tr, have_ray, sc, &ts);
-        if (have_ray && !tr.next()) {
-            if (!tr.found) sum += contrib;
-            have_ray = false;
-            if (++j == k) {
-                const float4 r = w.radiance[slot];
-                w.radiance[slot] = make_float4(r.x + sum.x, r.y + sum.y, r.z + sum.z, 0.0f);
-            }
+        warp_phase(tr, have, sc, &ts);
+        if (have && !tr.next()) {
+            if (tr.found) w.scontrib[q] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            have = false;
         }
     }
     warp_add_stat(&w.stats[STAT_SHADOW], n_rays);
@@ -219,6 +209,11 @@ __global__ void __launch_bounds__(BLOCK) k_shadow(const __grid_constant__ SceneD
         warp_add_stat(&w.stats[STAT_SH_NODES], ts.nodes);
         warp_add_stat(&w.stats[STAT_SH_PRIMS], ts.prims);
     }
+}
+
+__global__ void __launch_bounds__(BLOCK) k_shadow_gather(const __grid_constant__ Wave w) {
+    const uint32_t n = (uint32_t)(*w.n_shadow & 0xffffffffull);
+    for (uint32_t v = blockIdx.x * BLOCK + threadIdx.x; v < n; v += gridDim.x * BLOCK) shadow_gather_body(v, w);
 }
 
 __global__ void __launch_bounds__(BLOCK) k_resolve(const __grid_constant__ Wave w, float4* accum) {
@@ -267,7 +262,8 @@ void launch_shade(cudaStream_t st, const SceneD& sc, const RenderParams& rp, con
 void launch_shadow(cudaStream_t st, const SceneD& sc, const Wave& w, uint32_t n_max, uint32_t* fetch_counter, bool stats, LaunchCounter& lc) {
     if (stats) k_shadow<true><<<persistent_grid((const void*)k_shadow<true>, n_max), BLOCK, 0, st>>>(sc, w, fetch_counter);
     else k_shadow<false><<<persistent_grid((const void*)k_shadow<false>, n_max), BLOCK, 0, st>>>(sc, w, fetch_counter);
-    lc.launches++;
+    k_shadow_gather<<<persistent_grid((const void*)k_shadow_gather, n_max), BLOCK, 0, st>>>(w);
+    lc.launches += 2;
 }
 void launch_resolve(cudaStream_t st, const Wave& w, float4* accum, LaunchCounter& lc) {
     k_resolve<<<grid_for(w.n_pixels), BLOCK, 0, st>>>(w, accum);
@@ -354,6 +350,18 @@ void launch_sort(cudaStream_t st, void* temp, size_t temp_bytes, const uint64_t*
                  uint32_t* vals_out, uint32_t n, LaunchCounter& lc) {
     cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, vals_in, vals_out, (int)n, 0, 63, st);
     lc.launches += 4;
+}
+
+__global__ void __launch_bounds__(BLOCK) k_light_tris(const ShapeD* shapes, uint32_t shape, uint32_t tri_count, const float* vertices,
+                                                       const uint32_t* tris, LightTri* out) {
+    const uint32_t i = blockIdx.x * BLOCK + threadIdx.x;
+    if (i < tri_count) light_tri_body(i, shapes[shape], vertices, tris, out);
+}
+void launch_light_tris(cudaStream_t st, const ShapeD* shapes, uint32_t shape, uint32_t tri_count, const float* vertices, const uint32_t* tris,
+                       LightTri* out, LaunchCounter& lc) {
+    if (!tri_count) return;
+    k_light_tris<<<grid_for(tri_count), BLOCK, 0, st>>>(shapes, shape, tri_count, vertices, tris, out);
+    lc.launches++;
 }
 
 // ---------------------------------------------------------------------------------------------------

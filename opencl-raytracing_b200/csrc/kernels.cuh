@@ -38,6 +38,10 @@ size_t ploc_scan_temp_bytes(uint32_t n);
 // one PLOC round: nearest neighbours, merge flags, exclusive scan (CUB), merged nodes + compacted cluster list
 void launch_ploc_round(cudaStream_t st, const BuildCtx& b, void* scan_temp, size_t scan_temp_bytes, LaunchCounter& lc);
 
+// emitter triangle table (rt_scene.h LightTri)
+void launch_light_tris(cudaStream_t st, const ShapeD* shapes, uint32_t shape, uint32_t tri_count, const float* vertices, const uint32_t* tris,
+                       LightTri* out, LaunchCounter& lc);
+
 // mip pyramids
 void launch_to_f32(cudaStream_t st, const uint8_t* src, uint32_t format, float* dst, uint32_t n, LaunchCounter& lc);
 void launch_resize(cudaStream_t st, const float* src, float* dst, uint32_t w, uint32_t h, uint32_t ch, uint32_t n_out, int axis, LaunchCounter& lc);

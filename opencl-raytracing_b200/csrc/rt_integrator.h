@@ -21,6 +21,8 @@ struct RenderParams {  // RaytracerSettings (renderer/mod.rs:84-98)
     SamplerParams sampler;
 };
 
+struct alignas(16) RngState { uint64_t state, inc; };
+
 // Wavefront state of one batch (all pointers device memory; DESIGN.md "Path state").
 struct Wave {
     // batch shape: slot = s_local * n_pixels + p_local
@@ -29,7 +31,7 @@ struct Wave {
     uint32_t capacity;           // slots allocated (>= n_pixels * n_samples)
     uint32_t depth;              // bounce index of the rays in the current queue
     // path state, by slot
-    uint64_t* rng_state;
+    RngState* rng_state;         // PCG32 state + inc (inc is a pure function of (x, y, sample); carried so that shade needs no pixel lookup)
     float4* weight;              // xyz path weight | w: bit0 specular_bounce, bits 8.. stratified dimension
     float4* radiance;            // xyz accumulated radiance of this sample
     // ray queue (compacted), by queue position
@@ -40,20 +42,22 @@ struct Wave {
     float4* hits;                // t | prim | u | v
     const uint32_t* n_in;        // rays in the current queue (device counter of this depth)
     uint32_t* n_out;             // rays pushed for the next bounce
-    uint32_t* n_shadow;          // paths pushed to the shadow queue at this depth
+    unsigned long long* n_shadow;  // this depth's NEE counter: low 32 bits = vertices with shadow rays, high 32 = shadow rays
     unsigned long long* stats;   // STAT_* counters (rays per class, BVH fetches)
-    // next-event estimation, by slot; K = sum over lights of their sample counts
-    uint32_t shadow_k;
-    uint32_t* shadow_queue;      // slots with at least one pending shadow ray
-    float4* shadow_point;        // shading point.xyz | number of entries
-    float4* shadow_origin;       // [k * capacity + slot]: light-side ray origin.xyz | flags (bit0: skip occlusion test)
-    float4* shadow_contrib;      // [k * capacity + slot]: weighted contribution.xyz
+    // next-event estimation: a compacted queue of shadow rays (one entry per light sample with a non-zero unoccluded
+    // contribution; the rays of a vertex are consecutive) and a queue of the vertices they belong to
+    uint32_t shadow_k;           // light samples per vertex = sum over lights of their sample counts
+    float4* sray_o;              // light-side origin.xyz | t_max (distance - 0.001; negative: never occluded, not traced)
+    float4* sray_d;              // unit direction light -> shading point
+    float4* scontrib;            // weighted contribution.xyz if unoccluded; zeroed by k_shadow when the ray is blocked
+    uint4* svertex;              // slot | first ray | ray count | -
 };
 
 enum { STAT_PRIMARY = 0, STAT_BOUNCE = 1, STAT_SHADOW = 2, STAT_AOV = 3, STAT_EXT_NODES = 4, STAT_EXT_PRIMS = 5, STAT_SH_NODES = 6,
        STAT_SH_PRIMS = 7, STAT_AOV_NODES = 8, STAT_AOV_PRIMS = 9, STAT_SHADED = 10, STAT_TOTAL = 12 };
 
 struct Ray { V3 o, d; };
+
 struct RayDiff { V3 x_origin, y_origin, x_direction, y_direction; };
 
 // lib.rs:145-195
@@ -234,19 +238,22 @@ RT_HD LightSample sample_light(const SceneD& sc, const LightD& l, V3 point, Samp
     V3 bary;
     if (smp.x < smp.y) { float b0 = smp.x / 2.0f, b1 = smp.y - smp.x / 2.0f; bary = mk3(b0, b1, 1.0f - b0 - b1); }
     else { float b0 = smp.x - smp.y / 2.0f, b1 = smp.y / 2.0f; bary = mk3(b0, b1, 1.0f - b0 - b1); }
-    const uint32_t* t = sc.tris + 3 * (size_t)(em.tri_offset + tri);
-    uint32_t i0 = ldg(t), i1 = ldg(t + 1), i2 = ldg(t + 2);
-    V3 p0 = load3(sc.vertices, em.vertex_offset + i0), p1 = load3(sc.vertices, em.vertex_offset + i1),
-       p2 = load3(sc.vertices, em.vertex_offset + i2);
-    pdf /= length(cross(p1 - p0, p2 - p0)) / 2.0f;  // Mesh::tri_area, mesh.rs:271-278
+    const LightTri* lt = sc.light_tris + (l.tri_table + tri);
+    const float4 r0 = ldg(&lt->p0_area), r1 = ldg(&lt->p1_nx), r2 = ldg(&lt->p2_ny);
+    const V3 p0 = xyz(r0), p1 = xyz(r1), p2 = xyz(r2);
+    pdf /= r0.w;  // Mesh::tri_area, mesh.rs:271-278
     V3 p_local = bary.x * p0 + bary.y * p1 + bary.z * p2;
     V3 p_world = apply_point(l.light_to_world, p_local);
     V3 dir_world = point - p_world;
     float d = length(dir_world);
-    V3 n = em.normal_offset == NONE
-               ? unit(cross(p2 - p0, p1 - p0))
-               : unit(bary.x * load3(sc.normals, em.normal_offset + i0) + bary.y * load3(sc.normals, em.normal_offset + i1) +
-                      bary.z * load3(sc.normals, em.normal_offset + i2));
+    V3 n;
+    if (em.normal_offset == NONE) n = mk3(r1.w, r2.w, ldg(&lt->nz).x);
+    else {
+        const uint32_t* t = sc.tris + 3 * (size_t)(em.tri_offset + tri);
+        const uint32_t i0 = ldg(t), i1 = ldg(t + 1), i2 = ldg(t + 2);
+        n = unit(bary.x * load3(sc.normals, em.normal_offset + i0) + bary.y * load3(sc.normals, em.normal_offset + i1) +
+                 bary.z * load3(sc.normals, em.normal_offset + i2));
+    }
     ls.radiance = dot(dir_world, n) < 0.0f ? mk3(0.0f) : b;
     pdf *= (d * d) / fabsf(dot(dir_world, n));
     ls.origin = p_world; ls.dir = dir_world / d; ls.distance = d; ls.pdf = pdf;
@@ -278,168 +285,205 @@ RT_HD void raygen_body(uint32_t slot, const SceneD& sc, const RenderParams& rp, 
     Ray ray;
     RayDiff rd;
     generate_ray<false>(sc.camera, px, py, s, rp.samples_per_pixel, true, ray, rd);
-    w.rng_state[slot] = s.rng.state;
+    RngState rs;
+    rs.state = s.rng.state; rs.inc = s.rng.inc;
+    w.rng_state[slot] = rs;
     w.weight[slot] = make_float4(1.0f, 1.0f, 1.0f, u2f(1u | (s.dimension << 8)));
     w.radiance[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     w.ray_o_out[slot] = make_float4(ray.o.x, ray.o.y, ray.o.z, sc.camera.far_clip);
     w.ray_d_out[slot] = make_float4(ray.d.x, ray.d.y, ray.d.z, u2f(slot));
 }
 
-// Result of shading one path vertex; the kernel wrapper turns `continue_path` / `n_shadow` into
-// compacted queue pushes (warp-aggregated on the device, sequential in the CPU harness).
-struct ShadeOut {
-    bool continue_path;
-    Ray next;
-    uint32_t n_shadow;   // entries written to shadow_origin / shadow_contrib for this slot
-    uint32_t slot;
+// ---- shade: one iteration of the ray_radiance loop after traverse_bvh (lib.rs:284-391) ------------------
+// A vertex can emit three kinds of output: a continuation ray, up to K shadow rays, and one NEE vertex record.
+// Their queue positions come from `alloc`, which every thread of the launch calls exactly once per queue chunk
+// (on the device it is a block-wide scan + one global atomic per queue per block, kernels.cu; the CPU harness
+// hands out running counters). To know the shadow-ray count before the positions, the light samples are
+// evaluated twice from the same sampler state: a counting pass, then a writing pass — shade is bound by the
+// latency of its dependent loads, not by issue slots, so the recomputation is cheaper than staging the entries.
+struct ShadeState {
+    uint32_t slot, flags, sidx;
+    Ray ray;
+    V3 radiance, path_weight;
+    Sampler s;
+    HitInfo hit;
+    Surface surf;
+    Frame fr;
+    V3 wo;
+    bool dirty;
 };
 
-// ---- shade: one iteration of the ray_radiance loop after traverse_bvh (lib.rs:284-391) ------------------
-RT_HD void shade_body(uint32_t q, const SceneD& sc, const RenderParams& rp, const Wave& w, ShadeOut& out) {
+// lib.rs:284-322: miss / emission / material setup. False when the path ends here (state already written back).
+RT_HD bool shade_begin(uint32_t q, const SceneD& sc, const RenderParams& rp, const Wave& w, ShadeState& S) {
     const float4 ro4 = w.ray_o_in[q], rd4 = w.ray_d_in[q], h4 = w.hits[q];
     const uint32_t slot = f2u(rd4.w);
-    Ray ray;
-    ray.o = xyz(ro4);
-    ray.d = xyz(rd4);
+    S.slot = slot;
+    S.ray.o = xyz(ro4);
+    S.ray.d = xyz(rd4);
     Hit h;
     h.t = h4.x; h.prim = f2u(h4.y); h.u = h4.z; h.v = h4.w;
-    out.continue_path = false;
-    out.n_shadow = 0;
-    out.slot = slot;
-
-    float4 rad4 = w.radiance[slot];
-    V3 radiance = xyz(rad4);
-    const float4 wt4 = w.weight[slot];
-    V3 path_weight = xyz(wt4);
-    const uint32_t flags = f2u(wt4.w);
-    const bool specular_bounce = (flags & 1u) != 0;
     const uint32_t depth = w.depth;
+    const bool has_hit = h.prim != NONE;
+    if (!has_hit && sc.env_texture == NONE) return false;
 
-    if (h.prim == NONE) {
-        if (sc.env_texture != NONE) {
-            radiance += path_weight * environment_radiance(sc, ray.d);
-            w.radiance[slot] = make_float4(radiance.x, radiance.y, radiance.z, 0.0f);
-        }
-        return;
+    const float4 rad4 = w.radiance[slot];
+    const float4 wt4 = w.weight[slot];
+    S.radiance = xyz(rad4);
+    S.path_weight = xyz(wt4);
+    S.flags = f2u(wt4.w);
+    S.dirty = false;
+    if (!has_hit) {
+        S.radiance += S.path_weight * environment_radiance(sc, S.ray.d);
+        w.radiance[slot] = make_float4(S.radiance.x, S.radiance.y, S.radiance.z, 0.0f);
+        return false;
     }
-
-    uint32_t px, py, sidx;
-    slot_to_sample(w, slot, px, py, sidx);
-    Sampler s;
-    s.init(rp.sampler);
-    s.resume(px, py, sidx, w.rng_state[slot], flags >> 8);
+    const bool specular_bounce = (S.flags & 1u) != 0;
+    const RngState rs = w.rng_state[slot];
+    S.sidx = w.sample_base + slot / w.n_pixels;
+    S.s.init(rp.sampler);
+    S.s.rng.state = rs.state;
+    S.s.rng.inc = rs.inc;
+    S.s.dimension = S.flags >> 8;
+    S.s.sample_index = S.sidx;
 
     const bool aa = depth == 0 && rp.antialias_primary_rays;
-    HitInfo hit;
-    reconstruct_hit(sc, ray.o, ray.d, h, aa, hit);
+    reconstruct_hit(sc, S.ray.o, S.ray.d, h, aa, S.hit);
 
-    bool dirty = false;
     const bool add_zero_bounce = rp.accumulate_bounces || rp.max_ray_depth == depth;
-    if (specular_bounce && add_zero_bounce && hit.light != NONE) {
-        const LightD& l = sc.lights[hit.light];
-        if (l.kind == 2) { radiance += path_weight * mk3(l.b[0], l.b[1], l.b[2]); dirty = true; }
+    if (specular_bounce && add_zero_bounce && S.hit.light != NONE) {
+        const LightD& l = sc.lights[S.hit.light];
+        if (l.kind == 2) { S.radiance += S.path_weight * mk3(l.b[0], l.b[1], l.b[2]); S.dirty = true; }
     }
 
     MatCtx mc;
     if (aa) {
         // the camera-ray differentials are a pure function of (pixel, sample): re-derive them from a fresh
         // stream instead of carrying 48 bytes per path (lib.rs:206-243)
+        uint32_t px, py, sidx;
+        slot_to_sample(w, slot, px, py, sidx);
         Sampler s0;
         s0.init(rp.sampler);
         s0.start_sample(px, py, sidx);
         Ray cam_ray;
         RayDiff rdiff;
         generate_ray<true>(sc.camera, px, py, s0, rp.samples_per_pixel, true, cam_ray, rdiff);
-        mc = matctx_from_differentials(hit, ray, rdiff);
-    } else mc = matctx_no_aa(hit.uv);
+        mc = matctx_from_differentials(S.hit, S.ray, rdiff);
+    } else mc = matctx_no_aa(S.hit.uv);
 
-    Surface surf;
-    get_surface(sc, sc.materials[hit.material], mc, surf);
-    Frame fr;
-    fr.n = hit.normal;
-    make_orthonormal_basis(hit.normal, fr.x, fr.y);
-    const V3 wo = fr.to_local(-ray.d);
+    get_surface(sc, sc.materials[S.hit.material], mc, S.surf);
+    S.fr.n = S.hit.normal;
+    make_orthonormal_basis(S.hit.normal, S.fr.x, S.fr.y);
+    S.wo = S.fr.to_local(-S.ray.d);
 
-    const uint32_t depth1 = depth + 1;
-    if (depth1 > rp.max_ray_depth) {
-        if (dirty) w.radiance[slot] = make_float4(radiance.x, radiance.y, radiance.z, 0.0f);
-        return;
+    if (depth + 1 > rp.max_ray_depth) {
+        if (S.dirty) w.radiance[slot] = make_float4(S.radiance.x, S.radiance.y, S.radiance.z, 0.0f);
+        return false;
     }
-
-    const bool add_direct = rp.accumulate_bounces || rp.max_ray_depth == depth1;
-    if (!surface_is_delta(surf) && add_direct) {
-        uint32_t k = 0;
-        for (uint32_t li = 0; li < sc.light_count; li++) {
-            const LightD& light = sc.lights[li];
-            const uint32_t n = light.kind == 2 ? rp.light_sample_count : 1u;
-            const float inv_n = 1.0f / (float)n;
-            for (uint32_t j = 0; j < n; j++) {
-                LightSample ls = sample_light(sc, light, hit.point, s);
-                V3 wi = fr.to_local(-ls.dir);
-                // contribution if unoccluded (lib.rs:337-343); zero contributions never need a shadow ray
-                V3 c = mk3(0.0f);
-                float cosv = fmaxf(0.0f, wi.z);
-                if (!(is_zero(ls.radiance) || cosv == 0.0f) || !(ls.pdf > 0.0f)) {
-                    V3 bv = surface_eval(surf, wo, wi);
-                    c = path_weight * ((bv * ls.radiance * cosv / ls.pdf) * inv_n);
-                }
-                if (!is_zero(c)) {
-                    // a non-finite origin (directional light with an infinite scene radius: single-primitive
-                    // scenes, bvh2.rs:448-452) can never be occluded in the reference: NaN slab test
-                    bool skip_test = !(finite_f(ls.origin.x) && finite_f(ls.origin.y) && finite_f(ls.origin.z));
-                    size_t e = (size_t)k * w.capacity + slot;
-                    w.shadow_origin[e] = make_float4(ls.origin.x, ls.origin.y, ls.origin.z, u2f(skip_test ? 1u : 0u));
-                    w.shadow_contrib[e] = make_float4(c.x, c.y, c.z, ls.distance);
-                    k++;
-                }
-            }
-        }
-        if (k) {
-            w.shadow_point[slot] = make_float4(hit.point.x, hit.point.y, hit.point.z, u2f(k));
-            out.n_shadow = k;
-        }
-    }
-
-    BsdfSample bs;
-    bool alive = surface_sample(surf, wo, s, bs) == S_VALID;
-    if (alive && (is_zero(bs.f) || bs.pdf == 0.0f)) alive = false;
-    if (dirty) w.radiance[slot] = make_float4(radiance.x, radiance.y, radiance.z, 0.0f);
-    if (!alive) return;
-    path_weight *= bs.f * fabsf(bs.wi.z) / bs.pdf;
-    const uint32_t spec = (bs.component & SPECULAR) ? 1u : 0u;
-    w.weight[slot] = make_float4(path_weight.x, path_weight.y, path_weight.z, u2f(spec | (s.dimension << 8)));
-    w.rng_state[slot] = s.rng.state;
-    out.continue_path = true;
-    out.next.o = hit.point;
-    out.next.d = fr.to_world(bs.wi);
+    return true;
 }
 
-// ---- shadow: `occluded` (lights.rs:159-168) for every pending light sample of one path vertex -----------
-template <bool STATS>
-RT_HD void shadow_body(uint32_t i, const SceneD& sc, const Wave& w, TraverseStats* stats, uint32_t* n_rays) {
-    const uint32_t slot = w.shadow_queue[i];
-    const float4 p4 = w.shadow_point[slot];
-    const V3 point = xyz(p4);
-    const uint32_t k = f2u(p4.w);
-    V3 sum = mk3(0.0f);
-    for (uint32_t j = 0; j < k; j++) {
-        const size_t e = (size_t)j * w.capacity + slot;
-        const float4 o4 = w.shadow_origin[e], c4 = w.shadow_contrib[e];
-        bool occ = false;
-        if (!(f2u(o4.w) & 1u)) {
-            const V3 origin = xyz(o4);
-            const V3 dir_world = point - origin;
-            const float d = length(dir_world);
-            const V3 dir = dir_world / d;
-            const float distance = c4.w;
-            Hit h;
-            (*n_rays)++;
-            occ = traverse<true, STATS>(sc, origin, dir, 0.001f, distance - 0.001f, h, stats);
+// lib.rs:324-356: every light, every sample; entries with a non-zero unoccluded contribution become shadow rays.
+// MODE 0 counts them, MODE 1 stages up to NEE_STAGE of them in thread-local memory (and counts), MODE 2 writes them
+// (at most `limit`) to the shadow-ray queue starting at `first`. All modes draw the same numbers from `s`.
+constexpr uint32_t NEE_STAGE = 8;
+struct NeeStage { float4 o[NEE_STAGE], d[NEE_STAGE], c[NEE_STAGE]; };
+
+template <int MODE>
+RT_HD uint32_t nee_pass(const SceneD& sc, const RenderParams& rp, const Wave& w, const ShadeState& S, Sampler& s, uint32_t first, uint32_t limit,
+                        NeeStage* stage) {
+    uint32_t k = 0;
+    for (uint32_t li = 0; li < sc.light_count; li++) {
+        const LightD& light = sc.lights[li];
+        const uint32_t n = light.kind == 2 ? rp.light_sample_count : 1u;
+        const float inv_n = 1.0f / (float)n;
+        for (uint32_t j = 0; j < n; j++) {
+            LightSample ls = sample_light(sc, light, S.hit.point, s);
+            V3 wi = S.fr.to_local(-ls.dir);
+            // contribution if unoccluded (lib.rs:337-343); zero contributions never need a shadow ray
+            V3 c = mk3(0.0f);
+            float cosv = fmaxf(0.0f, wi.z);
+            if (!(is_zero(ls.radiance) || cosv == 0.0f) || !(ls.pdf > 0.0f)) {
+                V3 bv = surface_eval(S.surf, S.wo, wi);
+                c = S.path_weight * ((bv * ls.radiance * cosv / ls.pdf) * inv_n);
+            }
+            if (!is_zero(c)) {
+                if (MODE != 0 && k < limit) {
+                    // a non-finite origin (directional light with an infinite scene radius: single-primitive
+                    // scenes, bvh2.rs:448-452) can never be occluded in the reference: NaN slab test
+                    const bool skip_test = !(finite_f(ls.origin.x) && finite_f(ls.origin.y) && finite_f(ls.origin.z));
+                    const float4 eo = make_float4(ls.origin.x, ls.origin.y, ls.origin.z, skip_test ? -1.0f : ls.distance - 0.001f);
+                    const float4 ed = make_float4(ls.dir.x, ls.dir.y, ls.dir.z, 0.0f), ec = make_float4(c.x, c.y, c.z, 0.0f);
+                    if (MODE == 1) { stage->o[k] = eo; stage->d[k] = ed; stage->c[k] = ec; }
+                    else { const size_t e = (size_t)first + k; w.sray_o[e] = eo; w.sray_d[e] = ed; w.scontrib[e] = ec; }
+                }
+                k++;
+            }
         }
-        if (!occ) sum += xyz(c4);
     }
-    float4 r = w.radiance[slot];
-    w.radiance[slot] = make_float4(r.x + sum.x, r.y + sum.y, r.z + sum.z, 0.0f);
+    if (MODE == 2)   // the passes are the same arithmetic; should a compiler ever make them disagree, stay in bounds
+        for (; k < limit; k++) {
+            const size_t e = (size_t)first + k;
+            w.sray_o[e] = make_float4(0.0f, 0.0f, 0.0f, -1.0f);
+            w.sray_d[e] = make_float4(0.0f, 0.0f, 1.0f, 0.0f);
+            w.scontrib[e] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        }
+    return k;
+}
+
+// alloc(continue_path, has_nee_vertex, n_shadow_rays, &ray_pos, &vertex_pos, &first_shadow_ray)
+template <typename Alloc>
+RT_HD void shade_vertex(bool active, uint32_t q, const SceneD& sc, const RenderParams& rp, const Wave& w, Alloc&& alloc) {
+    ShadeState S;
+    Sampler s2;
+    BsdfSample bs;
+    NeeStage stage;
+    uint32_t k = 0;
+    bool alive = false;
+    // few light samples per vertex (the usual case): one evaluation, entries staged in thread-local memory until their
+    // queue position is known; otherwise count first and evaluate again when writing
+    const bool staged = w.shadow_k <= NEE_STAGE;
+    if (active) active = shade_begin(q, sc, rp, w, S);
+    if (active) {
+        s2 = S.s;
+        const bool add_direct = rp.accumulate_bounces || rp.max_ray_depth == w.depth + 1;
+        const bool nee = !surface_is_delta(S.surf) && add_direct;
+        if (nee) k = staged ? nee_pass<1>(sc, rp, w, S, s2, 0u, NEE_STAGE, &stage) : nee_pass<0>(sc, rp, w, S, s2, 0u, 0u, nullptr);
+        alive = surface_sample(S.surf, S.wo, s2, bs) == S_VALID;
+        if (alive && (is_zero(bs.f) || bs.pdf == 0.0f)) alive = false;
+    }
+    uint32_t rpos = 0, vpos = 0, first = 0;
+    alloc(alive, k != 0u, k, rpos, vpos, first);
+    if (!active) return;
+    if (k) {
+        if (staged)
+            for (uint32_t j = 0; j < k; j++) {
+                const size_t e = (size_t)first + j;
+                w.sray_o[e] = stage.o[j]; w.sray_d[e] = stage.d[j]; w.scontrib[e] = stage.c[j];
+            }
+        else nee_pass<2>(sc, rp, w, S, S.s, first, k, nullptr);
+        w.svertex[vpos] = make_uint4(S.slot, first, k, 0u);
+    }
+    if (S.dirty) w.radiance[S.slot] = make_float4(S.radiance.x, S.radiance.y, S.radiance.z, 0.0f);
+    if (!alive) return;
+    const V3 pw = S.path_weight * (bs.f * fabsf(bs.wi.z) / bs.pdf);
+    const uint32_t spec = (bs.component & SPECULAR) ? 1u : 0u;
+    w.weight[S.slot] = make_float4(pw.x, pw.y, pw.z, u2f(spec | (s2.dimension << 8)));
+    RngState rs;
+    rs.state = s2.rng.state; rs.inc = s2.rng.inc;
+    w.rng_state[S.slot] = rs;
+    const V3 nd = S.fr.to_world(bs.wi);
+    w.ray_o_out[rpos] = make_float4(S.hit.point.x, S.hit.point.y, S.hit.point.z, RT_INF);
+    w.ray_d_out[rpos] = make_float4(nd.x, nd.y, nd.z, u2f(S.slot));
+}
+
+// ---- shadow gather: add the unoccluded contributions of one NEE vertex to its path, in light-sample order ----
+// (`occluded`, lights.rs:159-168, is the any-hit traversal in k_shadow, which zeroes the entries it finds blocked)
+RT_HD void shadow_gather_body(uint32_t v, const Wave& w) {
+    const uint4 rec = w.svertex[v];
+    V3 sum = mk3(0.0f);
+    for (uint32_t j = 0; j < rec.z; j++) sum += xyz(w.scontrib[(size_t)rec.y + j]);
+    const float4 r = w.radiance[rec.x];
+    w.radiance[rec.x] = make_float4(r.x + sum.x, r.y + sum.y, r.z + sum.z, 0.0f);
 }
 
 // ---- resolve: render_tile's per-pixel sample loop tail (lib.rs:538-548) — sum in sample order -----------

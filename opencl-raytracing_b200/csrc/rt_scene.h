@@ -42,7 +42,16 @@ struct LightD {
     float a[3];   // position / direction
     float b[3];   // intensity / radiance
     M4 light_to_world;
+    uint32_t tri_table;   // diffuse area light: first record of its emitter in SceneD::light_tris
+    uint32_t _pad[3];
 };
+
+// One emitter triangle as next-event estimation reads it (four 128-bit loads instead of three index loads and nine
+// scalar vertex loads, and no per-sample cross product / square root for the values that depend on the triangle only):
+// object-space vertices, Mesh::tri_area (mesh.rs:271-278) and, for meshes without vertex normals, the geometric normal
+// unit(cross(p2 - p0, p1 - p0)) of lights.rs:93-95. Computed once per scene by light_tri_body with the reference's
+// formulas, so sample_light returns what it would have computed from the mesh arrays.
+struct LightTri { float4 p0_area, p1_nx, p2_ny, nz; };
 
 struct MaterialD { uint32_t kind, remap_roughness, albedo, eta, kappa, roughness, thickness, coat_albedo; };
 
@@ -84,6 +93,7 @@ struct SceneD {
     const Instance* instances;
     const ShapeD* shapes;
     const LightD* lights;
+    const LightTri* light_tris;
     const MaterialD* materials;
     const TextureD* textures;
     const ImageD* images;
@@ -100,6 +110,19 @@ struct SceneD {
 };
 
 RT_HD V3 load3(const float* p, uint32_t i) { return mk3(ldg(p + 3 * (size_t)i), ldg(p + 3 * (size_t)i + 1), ldg(p + 3 * (size_t)i + 2)); }
+RT_HD void light_tri_body(uint32_t tri, const ShapeD& em, const float* vertices, const uint32_t* tris, LightTri* out) {
+    const uint32_t* t = tris + 3 * (size_t)(em.tri_offset + tri);
+    const V3 p0 = load3(vertices, em.vertex_offset + t[0]), p1 = load3(vertices, em.vertex_offset + t[1]), p2 = load3(vertices, em.vertex_offset + t[2]);
+    const float area = length(cross(p1 - p0, p2 - p0)) / 2.0f;
+    const V3 n = unit(cross(p2 - p0, p1 - p0));
+    LightTri r;
+    r.p0_area = make_float4(p0.x, p0.y, p0.z, area);
+    r.p1_nx = make_float4(p1.x, p1.y, p1.z, n.x);
+    r.p2_ny = make_float4(p2.x, p2.y, p2.z, n.y);
+    r.nz = make_float4(n.z, 0.0f, 0.0f, 0.0f);
+    out[tri] = r;
+}
+
 RT_HD V2 load2(const float* p, uint32_t i) { return mk2(ldg(p + 2 * (size_t)i), ldg(p + 2 * (size_t)i + 1)); }
 
 }  // namespace rt

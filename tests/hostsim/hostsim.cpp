@@ -29,6 +29,7 @@ struct HostScene {
     std::vector<Instance> instances;
     std::vector<ShapeD> shapes;
     std::vector<LightD> lights;
+    std::vector<LightTri> light_tris;
     std::vector<MaterialD> materials;
     std::vector<TextureD> textures;
     std::vector<ImageD> images;
@@ -75,6 +76,13 @@ void build(HostScene& hs, const rtcuda_scene_desc* d) {
         b.kind = a.kind; b.shape = a.shape;
         std::memcpy(b.a, a.position_or_direction, sizeof b.a); std::memcpy(b.b, a.intensity_or_radiance, sizeof b.b);
         b.light_to_world = to_m4(a.light_to_world);
+        b.tri_table = 0;
+        if (a.kind == 2) {
+            b.tri_table = (uint32_t)hs.light_tris.size();
+            hs.light_tris.resize(hs.light_tris.size() + hs.shapes[a.shape].tri_count);
+            for (uint32_t t = 0; t < hs.shapes[a.shape].tri_count; t++)
+                light_tri_body(t, hs.shapes[a.shape], d->vertices, d->tris, hs.light_tris.data() + b.tri_table);
+        }
     }
     hs.materials.resize(d->material_count);
     for (uint32_t i = 0; i < d->material_count; i++) {
@@ -128,7 +136,7 @@ void build(HostScene& hs, const rtcuda_scene_desc* d) {
         hs.textures[t].mip_base = (uint32_t)chain_of[tx.image];
     }
 
-    sc.instances = hs.instances.data(); sc.shapes = hs.shapes.data(); sc.lights = hs.lights.data(); sc.materials = hs.materials.data();
+    sc.instances = hs.instances.data(); sc.shapes = hs.shapes.data(); sc.lights = hs.lights.data(); sc.light_tris = hs.light_tris.data(); sc.materials = hs.materials.data();
     sc.textures = hs.textures.data(); sc.images = hs.images.data(); sc.mips = hs.mips.data(); sc.image_bytes = hs.image_bytes.data();
     sc.vertices = d->vertices; sc.tris = d->tris; sc.normals = d->normals; sc.uvs = d->uvs;
     sc.instance_count = d->instance_count; sc.light_count = d->light_count; sc.material_count = d->material_count;
@@ -357,16 +365,17 @@ int hostsim_render(const rtcuda_scene_desc* d, const rtcuda_settings* st, rtcuda
         const uint32_t np_batch = std::min(np_all, capacity);
         const uint32_t ns_batch = std::max(1u, std::min(st->samples_per_pixel, capacity / np_batch));
         const uint32_t cap = np_batch * ns_batch;
-        std::vector<uint64_t> rng(cap);
-        std::vector<float4> weight(cap), radiance(cap), ro[2], rd[2], hits(cap), spoint(cap), sorigin((size_t)cap * std::max(1u, shadow_k)), scontrib((size_t)cap * std::max(1u, shadow_k));
+        std::vector<RngState> rng(cap);
+        const size_t kk = std::max(1u, shadow_k);
+        std::vector<float4> weight(cap), radiance(cap), ro[2], rd[2], hits(cap), sray_o((size_t)cap * kk), sray_d((size_t)cap * kk), scontrib((size_t)cap * kk);
         for (int i = 0; i < 2; i++) { ro[i].resize(cap); rd[i].resize(cap); }
-        std::vector<uint32_t> squeue(cap);
+        std::vector<uint4> svertex(cap);
         std::vector<float4> accum(np_all, make_float4(0, 0, 0, 0));
         unsigned long long dummy_stats[STAT_TOTAL] = {0};
         Wave w{};
         w.pixel_list = pixels.data(); w.capacity = cap;
         w.rng_state = rng.data(); w.weight = weight.data(); w.radiance = radiance.data(); w.hits = hits.data(); w.stats = dummy_stats;
-        w.shadow_k = shadow_k; w.shadow_queue = squeue.data(); w.shadow_point = spoint.data(); w.shadow_origin = sorigin.data(); w.shadow_contrib = scontrib.data();
+        w.shadow_k = shadow_k; w.svertex = svertex.data(); w.sray_o = sray_o.data(); w.sray_d = sray_d.data(); w.scontrib = scontrib.data();
         for (uint32_t p0 = 0; p0 < np_all; p0 += np_batch) {
             const uint32_t np = std::min(np_batch, np_all - p0);
             for (uint32_t s0 = 0; s0 < st->samples_per_pixel; s0 += ns_batch) {
@@ -395,35 +404,27 @@ int hostsim_render(const rtcuda_scene_desc* d, const rtcuda_settings* st, rtcuda
                     }
                     stats[depth == 0 ? 0 : 1] += n_rays;
                     const TraverseStats ts_mid = ts;
-                    uint32_t n_out = 0, n_shadow = 0;
-                    for (uint32_t q = 0; q < n_rays; q++) {
-                        ShadeOut so;
-                        shade_body(q, sc, rp, w, so);
-                        if (so.continue_path) {
-                            w.ray_o_out[n_out] = make_float4(so.next.o.x, so.next.o.y, so.next.o.z, INFINITY);
-                            w.ray_d_out[n_out] = make_float4(so.next.d.x, so.next.d.y, so.next.d.z, u2f(so.slot));
-                            n_out++;
-                        }
-                        if (so.n_shadow) squeue[n_shadow++] = so.slot;
-                    }
+                    uint32_t n_out = 0, n_shadow = 0, n_sray = 0;
+                    for (uint32_t q = 0; q < n_rays; q++)
+                        shade_vertex(true, q, sc, rp, w, [&](bool cont, bool has_vertex, uint32_t k, uint32_t& rpos, uint32_t& vpos, uint32_t& first) {
+                            rpos = n_out; vpos = n_shadow; first = n_sray;
+                            n_out += cont; n_shadow += has_vertex; n_sray += k;
+                        });
                     uint32_t shadow_rays = 0;
-                    if (std::getenv("HOSTSIM_WARPSIM")) {
-                        std::vector<SimRay> sim;
-                        for (uint32_t i = 0; i < n_shadow; i++) {
-                            const uint32_t slot = squeue[i];
-                            const V3 point = xyz(spoint[slot]);
-                            for (uint32_t j = 0; j < f2u(spoint[slot].w); j++) {
-                                const size_t e = (size_t)j * w.capacity + slot;
-                                if (f2u(sorigin[e].w) & 1u) continue;
-                                const V3 origin = xyz(sorigin[e]), dw = point - origin;
-                                sim.push_back(SimRay{origin, dw / length(dw), 0.001f, scontrib[e].w - 0.001f});
-                            }
-                        }
+                    std::vector<SimRay> sim;
+                    for (uint32_t r = 0; r < n_sray; r++) {   // k_shadow
+                        if (!(sray_o[r].w >= 0.0f)) continue;
+                        shadow_rays++;
+                        if (std::getenv("HOSTSIM_WARPSIM")) sim.push_back(SimRay{xyz(sray_o[r]), xyz(sray_d[r]), 0.001f, sray_o[r].w});
+                        Hit h;
+                        if (traverse<true, true>(sc, xyz(sray_o[r]), xyz(sray_d[r]), 0.001f, sray_o[r].w, h, &ts)) scontrib[r] = make_float4(0, 0, 0, 0);
+                    }
+                    if (!sim.empty()) {
                         char label[32];
                         std::snprintf(label, sizeof label, "shadow d%u", depth);
                         warp_sim<true>(sc, sim, label);
                     }
-                    for (uint32_t i = 0; i < n_shadow; i++) shadow_body<true>(i, sc, w, &ts, &shadow_rays);
+                    for (uint32_t v = 0; v < n_shadow; v++) shadow_gather_body(v, w);
                     stats[2] += shadow_rays;
                     if (std::getenv("HOSTSIM_TRACE"))  // per-depth work profile (DESIGN.md "Measurement": ray-class table)
                         std::fprintf(stderr, "depth %u: extend rays %u nodes %u prims %u | vertices %u shadow rays %u nodes %u prims %u | next %u\n", depth,

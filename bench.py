@@ -25,13 +25,22 @@ WORKLOADS = {
     "C2": ("cb", 512, 512, 64, 8, 1),
     "C4": ("cb_texture", 1920, 1080, 128, 8, 4),
     "C3s": ("cbbunny_area_light", 1920, 1080, 256, 8, 4),
+    # BASELINE config C5: 16,777,216-triangle displaced UV-sphere (4096 x 2048 quads, seed 42) inside the cb.glb box, 4K
+    "C5": ("cb", 3840, 2160, 256, 8, 1),
+    "C5s": ("cb", 1920, 1080, 32, 8, 1),     # same mesh, 1080p / 32 spp (quick check of the HBM-bound regime)
 }
+SYNTHETIC = {"C5": (4096, 2048), "C5s": (4096, 2048)}
+
+
+DATA_NOTE = "scene fixture (reference asset; C5: procedural mesh generated in-process, seed 42)"
 
 
 def load_workload(name, synthetic_tris=0):
     import raytracing_cuda as rc
     fixture, w, h, spp, depth, ls = WORKLOADS[name]
     sc = rc.Scene.load_npz(os.path.join(ROOT, "tests", "golden", "scenes", fixture + ".npz"))
+    if name in SYNTHETIC:
+        sc = rc.test_scenes.synthetic_mesh_scene(sc, *SYNTHETIC[name])
     sc.camera = sc.camera.with_raster_size(w, h)
     st = rc.RaytracerSettings(samples_per_pixel=spp, max_ray_depth=depth, light_sample_count=ls)
     return sc, st
@@ -107,7 +116,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     fixture, W, H, spp, depth, ls = WORKLOADS[args.workload]
-    config = {"workload": f"{args.workload}: {fixture}.glb {W}x{H}, {spp} spp, depth {depth}, light samples {ls}, "
+    what = f"{fixture}.glb" + (f" + synthetic displaced UV-sphere {SYNTHETIC[args.workload][0]}x{SYNTHETIC[args.workload][1]} quads (seed 42)"
+                               if args.workload in SYNTHETIC else "")
+    config = {"workload": f"{args.workload}: {what} {W}x{H}, {spp} spp, depth {depth}, light samples {ls}, "
                           f"independent sampler, seed 42",
               "triangles": None, "partition": f"64x64 tiles round-robin over {world} GPU(s), scene replicated, 1 NCCL sum-reduce per frame",
               "l2": "every step re-streams ~17 GB of wavefront state per batch through L2 (>> 126 MB) and a 512 MiB buffer is "
@@ -123,7 +134,7 @@ def main():
         config["triangles"] = sc.triangle_count()
         line = {"impl": "reference", "metric": "Msamples/s", "value": ms, "unit": "Msamples/s", "mrays_per_s": mr, "n_gpus": 0,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "scene fixture (reference asset), no synthetic data needed",
+                "vs_baseline": None, "dtype": "f32", "data": DATA_NOTE,
                 "config": config,
                 "cpu_baseline": {"value": ms, "unit": "Msamples/s", "cores": threads, "kind": "port",
                                  "sample": f"full {W}x{H} raster at {cpu_spp} spp (of {spp}), depth {depth}, light samples {ls}"},
@@ -151,18 +162,21 @@ def main():
             torch.cuda.synchronize()
 
     def one_step():
-        """render this rank's tiles into HBM planes + (N > 1) one NCCL sum-reduce to rank 0; returns device ms"""
-        planes = dr.render_local(st)
-        stats = dr.renderer.stats()
-        ms = stats["render_ms"]
+        """render this rank's tiles into HBM planes + (N > 1) one NCCL sum-reduce to rank 0; returns device ms between two
+        CUDA events on torch's stream: the first recorded after the L2 flush and (N > 1) a barrier, so that rank skew is
+        not counted, the second after the reduce (rtcuda_render_device returns when the library's stream has drained)."""
+        flush.zero_()
         if world > 1:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        planes = dr.render_local(st)
+        if world > 1:
             rc.multi_gpu.reduce_planes(planes, dst=0)
-            e1.record()
-            torch.cuda.synchronize()
-            ms += e0.elapsed_time(e1)
-        return ms, stats
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), dr.renderer.stats()
 
     for _ in range(args.warmup):
         one_step()
@@ -173,8 +187,6 @@ def main():
     total_ms, agg = 0.0, {}
     wall0 = time.time()
     for _ in range(args.steps):
-        flush.zero_()
-        torch.cuda.synchronize()
         ms, stats = one_step()
         total_ms += ms
         for k in ("samples", "primary_rays", "bounce_rays", "shadow_rays", "kernel_launches", "extend_launches", "extend_ms",
@@ -264,7 +276,7 @@ def main():
     line = {"metric": "Msamples/s", "value": samples / job_s / 1e6, "unit": "Msamples/s", "mrays_per_s": rays / job_s / 1e6,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * job_s / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-            "data": "scene fixture (reference asset), no synthetic data needed", "config": config,
+            "data": DATA_NOTE, "config": config,
             "wall_s_timed_region": wall, "clocks": clocks.summary(),
             "e2e": {"value": (W * H * spp * e2e_steps) / e2e_s / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps, "breakdown": e2e_each,

@@ -7,12 +7,17 @@
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
+#include <type_traits>
 
 #include "kernels.cuh"
 
 namespace rt {
 
 constexpr int BLOCK = 256;
+// resident blocks per SM asked of the Diffuse-only shade kernel (80 registers, ~160 B of spills): measured best of 2 / 3 / 4 on C3
+#ifndef SHADE_BLOCKS
+#define SHADE_BLOCKS 3
+#endif
 static inline uint32_t grid_for(uint32_t n, int block = BLOCK) { return n ? (n + block - 1) / block : 1; }
 
 // ---------------------------------------------------------------------------------------------------
@@ -120,7 +125,8 @@ __global__ void __launch_bounds__(BLOCK) k_extend(const __grid_constant__ SceneD
 // profiles/r1_notes.md). Per chunk ONE block-wide scan hands out the positions of all three outputs — continuation
 // rays, NEE vertices, shadow rays (a variable number per thread, consecutive per vertex) — and two threads issue
 // the block's global atomics (one per queue counter).
-__global__ void __launch_bounds__(BLOCK) k_shade(const __grid_constant__ SceneD sc, const __grid_constant__ RenderParams rp,
+template <typename Surf>
+__global__ void __launch_bounds__(BLOCK, std::is_same<Surf, DiffuseSurface>::value ? SHADE_BLOCKS : 2) k_shade(const __grid_constant__ SceneD sc, const __grid_constant__ RenderParams rp,
                                                   const __grid_constant__ Wave w) {
     __shared__ unsigned long long s_warp[BLOCK / 32][2];   // per warp: [0] continuation rays, [1] vertices | shadow rays << 32
     __shared__ unsigned long long s_base[2];
@@ -129,7 +135,7 @@ __global__ void __launch_bounds__(BLOCK) k_shade(const __grid_constant__ SceneD 
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&w.stats[STAT_SHADED], (unsigned long long)n);
     for (uint32_t base = blockIdx.x * BLOCK; base < n; base += gridDim.x * BLOCK) {
         const uint32_t q = base + threadIdx.x;
-        shade_vertex(q < n, q, sc, rp, w, [&](bool cont, bool has_vertex, uint32_t k, uint32_t& rpos, uint32_t& vpos, uint32_t& first) {
+        shade_vertex<Surf>(q < n, q, sc, rp, w, [&](bool cont, bool has_vertex, uint32_t k, uint32_t& rpos, uint32_t& vpos, uint32_t& first) {
             const unsigned FULL = 0xffffffffu;
             const unsigned mc = __ballot_sync(FULL, cont), mv = __ballot_sync(FULL, has_vertex);
             uint32_t incl = k;   // inclusive warp scan of the shadow-ray counts
@@ -256,7 +262,8 @@ void launch_extend(cudaStream_t st, const SceneD& sc, const Wave& w, uint32_t n_
     lc.launches++;
 }
 void launch_shade(cudaStream_t st, const SceneD& sc, const RenderParams& rp, const Wave& w, uint32_t n_max, LaunchCounter& lc) {
-    k_shade<<<persistent_grid((const void*)k_shade, n_max), BLOCK, 0, st>>>(sc, rp, w);
+    if (sc.all_diffuse) k_shade<DiffuseSurface><<<persistent_grid((const void*)k_shade<DiffuseSurface>, n_max), BLOCK, 0, st>>>(sc, rp, w);
+    else k_shade<Surface><<<persistent_grid((const void*)k_shade<Surface>, n_max), BLOCK, 0, st>>>(sc, rp, w);
     lc.launches++;
 }
 void launch_shadow(cudaStream_t st, const SceneD& sc, const Wave& w, uint32_t n_max, uint32_t* fetch_counter, bool stats, LaunchCounter& lc) {

@@ -523,6 +523,19 @@ RT_HD void get_surface(const SceneD& sc, const MaterialD& m, const MatCtx& c, Su
         }
     }
 }
+// Scenes whose materials are all Diffuse (everything the glTF importer produces, scene.rs:406-407) are shaded by a
+// kernel instantiated on this 3-float surface instead of the general Surface (two Bsdf records + the layered stack):
+// same arithmetic as the Diffuse branches above, a third fewer live registers in k_shade.
+struct DiffuseSurface { V3 albedo; };
+RT_HD bool surface_is_delta(const DiffuseSurface&) { return false; }
+RT_HD V3 surface_eval(const DiffuseSurface& s, V3 wo, V3 wi) { return wo.z * wi.z < 0.0f ? mk3(0.0f) : s.albedo / PI; }
+RT_HD int surface_sample(const DiffuseSurface& s, V3, Sampler& smp, BsdfSample& out) {
+    V3 wi = sample_cosine_hemisphere(smp.uniform2());
+    out.wi = wi; out.f = s.albedo / PI; out.pdf = wi.z / PI; out.component = NONSPEC_REFL;
+    return validate_sample(out);
+}
+RT_HD void get_surface(const SceneD& sc, const MaterialD& m, const MatCtx& c, DiffuseSurface& out) { out.albedo = xyz(tex(sc, m.albedo, c)); }
+
 RT_HD bool get_mip_level(const SceneD& sc, const MaterialD& m, const MatCtx& c, float& level) {  // materials.rs:957-968
     if (m.kind != 0) return false;
     return texture_mip_level(sc, m.albedo, c, level);

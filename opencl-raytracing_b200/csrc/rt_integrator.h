@@ -301,20 +301,22 @@ RT_HD void raygen_body(uint32_t slot, const SceneD& sc, const RenderParams& rp, 
 // hands out running counters). To know the shadow-ray count before the positions, the light samples are
 // evaluated twice from the same sampler state: a counting pass, then a writing pass — shade is bound by the
 // latency of its dependent loads, not by issue slots, so the recomputation is cheaper than staging the entries.
+template <typename Surf>
 struct ShadeState {
     uint32_t slot, flags, sidx;
     Ray ray;
     V3 radiance, path_weight;
     Sampler s;
     HitInfo hit;
-    Surface surf;
+    Surf surf;
     Frame fr;
     V3 wo;
     bool dirty;
 };
 
 // lib.rs:284-322: miss / emission / material setup. False when the path ends here (state already written back).
-RT_HD bool shade_begin(uint32_t q, const SceneD& sc, const RenderParams& rp, const Wave& w, ShadeState& S) {
+template <typename Surf>
+RT_HD bool shade_begin(uint32_t q, const SceneD& sc, const RenderParams& rp, const Wave& w, ShadeState<Surf>& S) {
     const float4 ro4 = w.ray_o_in[q], rd4 = w.ray_d_in[q], h4 = w.hits[q];
     const uint32_t slot = f2u(rd4.w);
     S.slot = slot;
@@ -388,8 +390,8 @@ RT_HD bool shade_begin(uint32_t q, const SceneD& sc, const RenderParams& rp, con
 constexpr uint32_t NEE_STAGE = 8;
 struct NeeStage { float4 o[NEE_STAGE], d[NEE_STAGE], c[NEE_STAGE]; };
 
-template <int MODE>
-RT_HD uint32_t nee_pass(const SceneD& sc, const RenderParams& rp, const Wave& w, const ShadeState& S, Sampler& s, uint32_t first, uint32_t limit,
+template <int MODE, typename Surf>
+RT_HD uint32_t nee_pass(const SceneD& sc, const RenderParams& rp, const Wave& w, const ShadeState<Surf>& S, Sampler& s, uint32_t first, uint32_t limit,
                         NeeStage* stage) {
     uint32_t k = 0;
     for (uint32_t li = 0; li < sc.light_count; li++) {
@@ -431,9 +433,9 @@ RT_HD uint32_t nee_pass(const SceneD& sc, const RenderParams& rp, const Wave& w,
 }
 
 // alloc(continue_path, has_nee_vertex, n_shadow_rays, &ray_pos, &vertex_pos, &first_shadow_ray)
-template <typename Alloc>
+template <typename Surf, typename Alloc>
 RT_HD void shade_vertex(bool active, uint32_t q, const SceneD& sc, const RenderParams& rp, const Wave& w, Alloc&& alloc) {
-    ShadeState S;
+    ShadeState<Surf> S;
     Sampler s2;
     BsdfSample bs;
     NeeStage stage;

@@ -141,6 +141,8 @@ void build(HostScene& hs, const rtcuda_scene_desc* d) {
     sc.vertices = d->vertices; sc.tris = d->tris; sc.normals = d->normals; sc.uvs = d->uvs;
     sc.instance_count = d->instance_count; sc.light_count = d->light_count; sc.material_count = d->material_count;
     sc.texture_count = d->texture_count; sc.env_texture = d->environment_light_texture;
+    sc.all_diffuse = 1;
+    for (uint32_t m = 0; m < d->material_count; m++) if (d->materials[m].kind != 0) sc.all_diffuse = 0;
     sc.prim_count = n_prims; sc.node_count = 0;
     hs.nodes.resize(std::max(1u, n_prims)); hs.prims.resize(std::max(1u, n_prims));
     sc.nodes = hs.nodes.data(); sc.prims = hs.prims.data();
@@ -405,11 +407,14 @@ int hostsim_render(const rtcuda_scene_desc* d, const rtcuda_settings* st, rtcuda
                     stats[depth == 0 ? 0 : 1] += n_rays;
                     const TraverseStats ts_mid = ts;
                     uint32_t n_out = 0, n_shadow = 0, n_sray = 0;
-                    for (uint32_t q = 0; q < n_rays; q++)
-                        shade_vertex(true, q, sc, rp, w, [&](bool cont, bool has_vertex, uint32_t k, uint32_t& rpos, uint32_t& vpos, uint32_t& first) {
-                            rpos = n_out; vpos = n_shadow; first = n_sray;
-                            n_out += cont; n_shadow += has_vertex; n_sray += k;
-                        });
+                    auto alloc = [&](bool cont, bool has_vertex, uint32_t k, uint32_t& rpos, uint32_t& vpos, uint32_t& first) {
+                        rpos = n_out; vpos = n_shadow; first = n_sray;
+                        n_out += cont; n_shadow += has_vertex; n_sray += k;
+                    };
+                    for (uint32_t q = 0; q < n_rays; q++) {
+                        if (sc.all_diffuse) shade_vertex<DiffuseSurface>(true, q, sc, rp, w, alloc);
+                        else shade_vertex<Surface>(true, q, sc, rp, w, alloc);
+                    }
                     uint32_t shadow_rays = 0;
                     std::vector<SimRay> sim;
                     for (uint32_t r = 0; r < n_sray; r++) {   // k_shadow

@@ -8,6 +8,8 @@ from .scene import (Camera, Light, Material, Mesh, Scene, SceneBuilder, Sphere, 
 from .backend import CudaBackendSettings, CudaRenderer, render, render_single_pixel
 from . import test_scenes
 from . import multi_gpu
+from . import exr
+from . import imagecmp
 
 __all__ = ["AovFlags", "RaytracerSettings", "RenderOutput", "Sampler", "SinglePixelOutput", "Camera", "Light",
            "Material", "Mesh", "Scene", "SceneBuilder", "Sphere", "Texture", "scene_from_gltf_file",

@@ -208,6 +208,24 @@ void build(HostScene& hs, const rtcuda_scene_desc* d) {
         hs.n_levels++;
     }
     sc.node_count = counters[1];
+    if (std::getenv("HOSTSIM_NODESTATS")) {
+        uint32_t hist[9] = {0}, inner = 0, leafc = 0, prims = 0, hi_empty = 0;
+        for (uint32_t i = 0; i < counters[1]; i++) {
+            const Node8& nd = hs.nodes[i];
+            uint32_t m[2] = {f2u(nd.n1.z), f2u(nd.n1.w)}, c = 0;
+            for (int k = 0; k < 8; k++) {
+                uint32_t meta = (m[k >> 2] >> (8 * (k & 3))) & 0xff;
+                if (!meta) continue;
+                c++;
+                if ((meta & 0x18) == 0x18) inner++; else { leafc++; prims += __builtin_popcount(meta >> 5); }
+            }
+            hist[c]++;
+            if (!m[1]) hi_empty++;
+        }
+        std::fprintf(stderr, "wide nodes %u: children histogram", counters[1]);
+        for (int k = 0; k <= 8; k++) std::fprintf(stderr, " %d:%u", k, hist[k]);
+        std::fprintf(stderr, " | inner children %u leaf children %u prims %u | upper half empty %u\n", inner, leafc, prims, hi_empty);
+    }
     V3 mn = mk3(key_float(bounds_keys[0]), key_float(bounds_keys[1]), key_float(bounds_keys[2]));
     V3 mx = mk3(key_float(bounds_keys[3]), key_float(bounds_keys[4]), key_float(bounds_keys[5]));
     V3 c = (mx + mn) / 2.0f;

@@ -268,3 +268,37 @@ def test_error_behaviour(rc):
     empty.add_camera(rc.Camera.lookat_camera_perspective((0, 0, 0), (0, 0, -1), (0, 1, 0), False, 0.7, 32, 32))
     out, _ = gpu_render(rc, empty.build(), rc.RaytracerSettings(outputs=A.BEAUTY | A.NORMALS, samples_per_pixel=2))
     assert (out.beauty == 0).all() and (out.normals == 0).all()
+
+
+def test_many_light_samples_two_pass_nee(rc, oracle):
+    """K > NEE_STAGE light samples per vertex: the count pass + write pass of k_shade (rt_integrator.h nee_pass)"""
+    sc = load_scene("cb", 96, 96)
+    sc.lights.append(rc.Light(rc._ffi.LIGHT_POINT, a=(0.1, 0.4, 0.2), b=(0.05, 0.05, 0.05)))
+    st = rc.RaytracerSettings(outputs=A.BEAUTY, samples_per_pixel=4, light_sample_count=12, max_ray_depth=3)
+    out, stats = gpu_render(rc, sc, st)
+    ref, ostats = oracle.render(sc, st)
+    assert stats["shadow_rays"] > 0
+    assert beauty_close(out.beauty, ref.beauty)
+
+
+def test_builders_give_identical_frames(rc, monkeypatch):
+    """PLOC (default) and LBVH trees: bit-identical frames (closest hit is independent of the tree), fewer node fetches"""
+    sc = load_scene("cbbunny_area_light_transforms", 320, 180)
+    st = rc.RaytracerSettings(outputs=A.BEAUTY | A.NORMALS | A.DEBUG_IDS | A.DEBUG_DEPTH, samples_per_pixel=4)
+    a, sa = gpu_render(rc, sc, st, collect_stats=1)
+    monkeypatch.setenv("RTCUDA_BUILDER", "lbvh")
+    b, sb = gpu_render(rc, sc, st, collect_stats=1)
+    for plane in ("beauty", "normals", "debug_ids", "debug_depth"):
+        assert np.array_equal(getattr(a, plane), getattr(b, plane)), plane
+    assert sa["nodes_fetched"] < 0.8 * sb["nodes_fetched"]
+
+
+def test_cached_memory_release(rc):
+    """the path-state arena of a closed renderer is parked and reused; rtcuda_release_cached_memory gives it back"""
+    sc = load_scene("cb", 64, 64)
+    st = rc.RaytracerSettings(outputs=A.BEAUTY, samples_per_pixel=2, light_sample_count=1)
+    a, _ = gpu_render(rc, sc, st)
+    b, _ = gpu_render(rc, sc, st)      # second context takes the parked arena
+    rc._ffi.load_library().rtcuda_release_cached_memory()
+    c, _ = gpu_render(rc, sc, st)
+    assert np.array_equal(a.beauty, b.beauty) and np.array_equal(a.beauty, c.beauty)

@@ -107,3 +107,52 @@ def test_synthetic_mesh_generator(rc):
     assert np.allclose(np.linalg.norm(m.normals, axis=1), 1.0, atol=1e-4)
     m2 = rc.test_scenes.procedural_sphere_mesh(64, 32)
     assert np.array_equal(m.vertices, m2.vertices)
+
+
+def test_exr_round_trip(rc, tmp_path):
+    """the driver's EXR files: channel names of crates/cli/src/main.rs:398-467, sorted, f32, bit-exact round trip"""
+    rng = np.random.default_rng(1)
+    out = rc.RenderOutput.allocate(37, 23, rc.AovFlags.BEAUTY | rc.AovFlags.NORMALS | rc.AovFlags.UV_COORDS | rc.AovFlags.MIP_LEVEL)
+    for plane in ("beauty", "normals", "uv", "mip_level"):
+        getattr(out, plane)[...] = rng.standard_normal(getattr(out, plane).shape).astype(np.float32)
+    ch = rc.exr.channels_of_render_output(out, rc.AovFlags.BEAUTY | rc.AovFlags.NORMALS | rc.AovFlags.UV_COORDS | rc.AovFlags.MIP_LEVEL)
+    assert sorted(ch) == ["B", "G", "Mip Level", "Normal.X", "Normal.Y", "Normal.Z", "R", "U", "V"]
+    path = str(tmp_path / "a.exr")
+    rc.exr.write_exr(path, ch)
+    back, w, h = rc.exr.read_exr(path)
+    assert (w, h) == (37, 23) and list(back) == sorted(ch)
+    for k in ch:
+        assert np.array_equal(back[k], ch[k])
+    import cv2   # an independent reader agrees on the RGB planes
+    os.environ.setdefault("OPENCV_IO_ENABLE_OPENEXR", "1")
+    img = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+    if img is not None:
+        assert np.array_equal(img[..., 2], ch["R"]) and np.array_equal(img[..., 0], ch["B"])
+
+
+def test_flip_and_mse_metrics(rc):
+    rng = np.random.default_rng(0)
+    a = rng.random((48, 64, 3))
+    assert rc.imagecmp.flip(a, a, hdr=False) == 0.0
+    assert rc.imagecmp.mse_maxdiff(a, a) == (0.0, 0.0)
+    b = np.clip(a + 0.02 * rng.standard_normal(a.shape), 0, 1)
+    c = np.clip(a + 0.2 * rng.standard_normal(a.shape), 0, 1)
+    fb, fc = rc.imagecmp.flip(a, b, hdr=False), rc.imagecmp.flip(a, c, hdr=False)
+    assert 0.0 < fb < fc <= 1.0
+    black, white = np.zeros((32, 32, 3)), np.ones((32, 32, 3))
+    assert rc.imagecmp.flip(black, white, hdr=False) > 0.9     # the largest possible achromatic error maps close to 1
+
+
+def test_cli_argument_surface(rc, capsys):
+    """flag surface of crates/cli/src/main.rs:20-107 (+ raster override); list-scenes prints the builtin names as JSON"""
+    from raytracing_cuda import cli
+    assert cli.main(["list-scenes"]) == 0
+    import json
+    names = json.loads(capsys.readouterr().out)
+    assert names[:4] == ["sphere", "cube", "cube_orthographic", "checkered_plane"]
+    a = cli.build_parser().parse_args(["--scene-name", "sphere", "-s", "4", "-d", "5", "-l", "2", "--sampler", "stratified", "-o", "x.exr",
+                                       "full", "--aov", "n,u", "--no-beauty"])
+    assert (a.spp, a.ray_depth, a.light_samples, a.sampler, a.aov, a.no_beauty) == (4, 5, 2, "stratified", "n,u", True)
+    p = cli.build_parser().parse_args(["--scene-name", "cube", "pixel", "10", "20", "3", "1"])
+    assert (p.x, p.y, p.sample_count, p.sample_offset) == (10, 20, 3, 1)
+    assert cli.main([]) == 1 and cli.main(["--scene-name", "cube", "-t", "4", "full"]) == 1

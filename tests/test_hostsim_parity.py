@@ -143,3 +143,29 @@ def test_empty_scene(rc, hostsim):
     b.add_camera(rc.Camera.lookat_camera_perspective((0, 0, 0), (0, 0, -1), (0, 1, 0), False, 0.7, 32, 32))
     out, _ = hostsim.render(b.build(), rc.RaytracerSettings(outputs=A.BEAUTY | A.NORMALS, samples_per_pixel=2))
     assert (out.beauty == 0).all() and (out.normals == 0).all()
+
+
+def test_many_light_samples_two_pass_nee(rc, oracle, hostsim):
+    """more light samples per vertex than the thread-local staging holds (rt_integrator.h NEE_STAGE = 8): shade counts the
+    shadow rays in one pass and writes them in a second one; plus a point light so that K mixes light kinds"""
+    sc = load_scene("cb", 48, 48)
+    sc.lights.append(rc.Light(rc._ffi.LIGHT_POINT, a=(0.1, 0.4, 0.2), b=(0.05, 0.05, 0.05)))
+    st = rc.RaytracerSettings(outputs=A.BEAUTY, samples_per_pixel=2, light_sample_count=12, max_ray_depth=3)
+    out, stats = hostsim.render(sc, st, capacity=2048)
+    ref, ostats = oracle.render(sc, st, num_threads=4)
+    assert stats["shadow_rays"] > 0
+    assert beauty_close(out.beauty, ref.beauty)
+    assert abs(out.beauty.mean() - ref.beauty.mean()) <= 2e-3 * ref.beauty.mean() + 1e-8
+
+
+def test_builders_give_identical_frames(rc, hostsim, monkeypatch):
+    """closest hits do not depend on the tree (conservative culling, id-ordered ties): the PLOC tree and the LBVH tree
+    (RTCUDA_BUILDER=lbvh, the A/B switch of rt_build.h) render bit-identical frames, with fewer node visits for PLOC"""
+    sc = load_scene("cbbunny_area_light_transforms", 64, 36)
+    st = rc.RaytracerSettings(outputs=A.BEAUTY | A.NORMALS | A.DEBUG_IDS | A.DEBUG_DEPTH, samples_per_pixel=2)
+    a, sa = hostsim.render(sc, st)
+    monkeypatch.setenv("RTCUDA_BUILDER", "lbvh")
+    b, sb = hostsim.render(sc, st)
+    for plane in ("beauty", "normals", "debug_ids", "debug_depth"):
+        assert np.array_equal(getattr(a, plane), getattr(b, plane)), plane
+    assert sa["nodes_fetched"] < 0.8 * sb["nodes_fetched"]

@@ -162,21 +162,25 @@ def main():
             torch.cuda.synchronize()
 
     def one_step():
-        """render this rank's tiles into HBM planes + (N > 1) one NCCL sum-reduce to rank 0; returns device ms between two
-        CUDA events on torch's stream: the first recorded after the L2 flush and (N > 1) a barrier, so that rank skew is
-        not counted, the second after the reduce (rtcuda_render_device returns when the library's stream has drained)."""
+        """render this rank's tiles into HBM planes + (N > 1) one NCCL sum-reduce to rank 0. Device ms of the step = the
+        library's CUDA events around the whole render on its launching stream (rtcuda_stats.render_ms: every kernel of
+        every batch plus the launch gaps between them) + (N > 1) torch CUDA events around the reduce, taken after a
+        barrier so that the wait for a slower rank is not counted twice (the job time is the max over ranks anyway)."""
         flush.zero_()
+        torch.cuda.synchronize()
+        planes = dr.render_local(st)
+        stats = dr.renderer.stats()
+        ms = stats["render_ms"]
         if world > 1:
             dist.barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        planes = dr.render_local(st)
-        if world > 1:
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
             rc.multi_gpu.reduce_planes(planes, dst=0)
-        e1.record()
-        torch.cuda.synchronize()
-        return e0.elapsed_time(e1), dr.renderer.stats()
+            e1.record()
+            torch.cuda.synchronize()
+            ms += e0.elapsed_time(e1)
+        return ms, stats
 
     for _ in range(args.warmup):
         one_step()

@@ -448,10 +448,14 @@ void build_bvh(rtcuda_scene* s, const std::vector<Instance>& instances, uint32_t
     CK(cudaMemcpyAsync(queue_a.p, &root, sizeof root, cudaMemcpyHostToDevice, st));
     uint32_t h_counters[4] = {0u, 1u, 0u, 0u};  // next-level size, wide nodes (root allocated), packed prims
     CK(cudaMemcpyAsync(counters.p, h_counters, sizeof h_counters, cudaMemcpyHostToDevice, st));
-    uint32_t n_items = 1;
+    uint32_t n_items = 1, n_levels = 0;
     WorkItem* qin = queue_a.p;
     WorkItem* qout = queue_b.p;
     while (n_items) {
+        // a ray holds at most two stack entries per level of the wide tree (the rest of a node group and a postponed
+        // primitive group, rt_traverse.h): deeper trees than the traversal stack covers are refused, not overrun
+        if (++n_levels > (uint32_t)(TRAVERSE_STACK / 2 - 1))
+            throw RtError{RTCUDA_ERR_UNSUPPORTED, "wide BVH deeper than the traversal stack allows (degenerate primitive distribution)"};
         b.queue_in = qin;
         b.queue_out = qout;
         launch_collapse(st, b, n_items, s->lc);

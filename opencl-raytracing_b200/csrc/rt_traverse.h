@@ -19,7 +19,7 @@ struct Hit {
 
 struct TraverseStats { uint32_t nodes, prims; };
 
-constexpr int TRAVERSE_STACK = 32;
+constexpr int TRAVERSE_STACK = 64;  // 8 B entries; a ray holds at most two per level of the wide tree (api.cu refuses deeper trees)
 
 // geometry.rs:139-227 — the root finding part only (the hit record is rebuilt in shade).
 RT_HD bool sphere_t(V3 center, float radius, V3 o, V3 d, float t_min, float t_max, float& t_out) {

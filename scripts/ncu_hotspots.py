@@ -8,10 +8,10 @@ import csv, os, re, subprocess, sys, tempfile, collections
 
 rep, kre, obj = sys.argv[1], sys.argv[2], sys.argv[3]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
-raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kre], capture_output=True, text=True).stdout
+raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kre.split("<")[0]], capture_output=True, text=True).stdout
 lines = raw.splitlines()
-# first kernel block only
-start = next(i for i, l in enumerate(lines) if l.startswith('"Kernel Name"'))
+# first kernel block whose full name contains the requested text (k_shadow< vs k_shadow_gather)
+start = next(i for i, l in enumerate(lines) if l.startswith('"Kernel Name"') and kre in l)
 end = next((i for i in range(start + 1, len(lines)) if lines[i].startswith('"Kernel Name"')), len(lines))
 kname = next(csv.reader([lines[start]]))[1]
 rows = list(csv.reader(lines[start + 1:end]))
@@ -31,7 +31,8 @@ loc, cur, infn = {}, ("?", 0), False
 for l in dis:
     m = re.match(r"\s*\.section\s+\.text\.(\S+?),", l)
     if m:
-        infn = frag in m.group(1) and (("ILb0" in m.group(1)) == ("<0>" in kname or "<false>" in kname) or "<" not in kname)
+        sec = m.group(1)   # mangled names carry the identifier length: 8k_shadow vs 15k_shadow_gather
+        infn = f"{len(frag)}{frag}" in sec and ("ILb1" not in sec) and (("DiffuseSurface" in sec) == ("DiffuseSurface" in kname))
         continue
     if not infn: continue
     m = re.search(r'//## File "([^"]+)", line (\d+)', l)

@@ -31,6 +31,16 @@ static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
 static inline uint2 make_uint2(uint32_t x, uint32_t y) { return uint2{x, y}; }
 #endif
 
+// Bounds checks of the queue / stack indices for debug builds (`make NVCCFLAGS_EXTRA=-DRT_DEBUG_CHECKS`): the pool's
+// compute-sanitizer is closed, so the invariants are asserted by the kernels themselves and the GPU suite is run once
+// per round with the checks on (profiles/r1_notes.md).
+#if defined(RT_DEBUG_CHECKS)
+#include <cassert>
+#define RT_CHECK(cond) assert(cond)
+#else
+#define RT_CHECK(cond) ((void)0)
+#endif
+
 namespace rt {
 
 constexpr float PI = 3.14159265358979323846f;

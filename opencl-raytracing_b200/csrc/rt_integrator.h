@@ -416,7 +416,7 @@ RT_HD uint32_t nee_pass(const SceneD& sc, const RenderParams& rp, const Wave& w,
                     const float4 eo = make_float4(ls.origin.x, ls.origin.y, ls.origin.z, skip_test ? -1.0f : ls.distance - 0.001f);
                     const float4 ed = make_float4(ls.dir.x, ls.dir.y, ls.dir.z, 0.0f), ec = make_float4(c.x, c.y, c.z, 0.0f);
                     if (MODE == 1) { stage->o[k] = eo; stage->d[k] = ed; stage->c[k] = ec; }
-                    else { const size_t e = (size_t)first + k; w.sray_o[e] = eo; w.sray_d[e] = ed; w.scontrib[e] = ec; }
+                    else { const size_t e = (size_t)first + k; RT_CHECK(e < (size_t)w.capacity * (w.shadow_k ? w.shadow_k : 1u)); w.sray_o[e] = eo; w.sray_d[e] = ed; w.scontrib[e] = ec; }
                 }
                 k++;
             }
@@ -460,9 +460,11 @@ RT_HD void shade_vertex(bool active, uint32_t q, const SceneD& sc, const RenderP
         if (staged)
             for (uint32_t j = 0; j < k; j++) {
                 const size_t e = (size_t)first + j;
+                RT_CHECK(e < (size_t)w.capacity * (w.shadow_k ? w.shadow_k : 1u));
                 w.sray_o[e] = stage.o[j]; w.sray_d[e] = stage.d[j]; w.scontrib[e] = stage.c[j];
             }
         else nee_pass<2>(sc, rp, w, S, S.s, first, k, nullptr);
+        RT_CHECK(vpos < w.capacity && S.slot < w.capacity);
         w.svertex[vpos] = make_uint4(S.slot, first, k, 0u);
     }
     if (S.dirty) w.radiance[S.slot] = make_float4(S.radiance.x, S.radiance.y, S.radiance.z, 0.0f);
@@ -474,6 +476,7 @@ RT_HD void shade_vertex(bool active, uint32_t q, const SceneD& sc, const RenderP
     rs.state = s2.rng.state; rs.inc = s2.rng.inc;
     w.rng_state[S.slot] = rs;
     const V3 nd = S.fr.to_world(bs.wi);
+    RT_CHECK(rpos < w.capacity);
     w.ray_o_out[rpos] = make_float4(S.hit.point.x, S.hit.point.y, S.hit.point.z, RT_INF);
     w.ray_d_out[rpos] = make_float4(nd.x, nd.y, nd.z, u2f(S.slot));
 }
@@ -482,6 +485,7 @@ RT_HD void shade_vertex(bool active, uint32_t q, const SceneD& sc, const RenderP
 // (`occluded`, lights.rs:159-168, is the any-hit traversal in k_shadow, which zeroes the entries it finds blocked)
 RT_HD void shadow_gather_body(uint32_t v, const Wave& w) {
     const uint4 rec = w.svertex[v];
+    RT_CHECK(rec.x < w.capacity && (size_t)rec.y + rec.z <= (size_t)w.capacity * (w.shadow_k ? w.shadow_k : 1u));
     V3 sum = mk3(0.0f);
     for (uint32_t j = 0; j < rec.z; j++) sum += xyz(w.scontrib[(size_t)rec.y + j]);
     const float4 r = w.radiance[rec.x];

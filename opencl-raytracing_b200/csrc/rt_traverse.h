@@ -135,6 +135,7 @@ struct Traversal {
 
     // precondition: has_nodes()
     RT_HD void node_step(const SceneD& sc, TraverseStats* stats) {
+        RT_CHECK(sp + 2 <= TRAVERSE_STACK);
         if (tgroup.y) stack[sp++] = tgroup;  // postponed primitives
         const uint32_t hits = ngroup.y;
         const int bit = bfind32(hits);
@@ -142,6 +143,7 @@ struct Traversal {
         if (ngroup.y & 0xff000000u) stack[sp++] = ngroup;
         const uint32_t slot = ((uint32_t)bit - 24u) ^ octinv;
         const uint32_t rel = (uint32_t)popc32(hits & ~(0xffffffffu << slot) & 0xffu);
+        RT_CHECK(ngroup.x + rel < sc.node_count);
         const Node8* node = sc.nodes + (ngroup.x + rel);
         const float4 n0 = ldg(&node->n0), n1 = ldg(&node->n1), n2 = ldg(&node->n2), n3 = ldg(&node->n3), n4 = ldg(&node->n4);
         if (STATS) stats->nodes++;
@@ -202,6 +204,7 @@ struct Traversal {
         const int b = 31 - clz32(tgroup.y & (0u - tgroup.y));  // lowest set bit
         tgroup.y &= tgroup.y - 1u;
         const uint32_t pi = tgroup.x + (uint32_t)b;
+        RT_CHECK(pi < sc.prim_count);
         const Prim* pr = sc.prims + pi;
         const float4 pa = ldg(&pr->a), pb = ldg(&pr->b), pc = ldg(&pr->c);
         if (STATS) stats->prims++;

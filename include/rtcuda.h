@@ -245,6 +245,13 @@ enum {
     RTCUDA_STATS_KERNEL_TIMES = 1u << 1   /* CUDA events around every extend / shade / shadow launch */
 };
 
+enum {
+    /* Intersect triangles with the watertight test of Woop et al. 2013 instead of the reference's Moller-Trumbore
+     * (crates/raytracing-cpu/src/geometry.rs:301-340, not watertight): no leaks along shared edges / silhouettes.
+     * Off by default: the parity gates compare against the reference's test. */
+    RTCUDA_BACKEND_WATERTIGHT = 1u << 0
+};
+
 /* The analogue of CpuBackendSettings (crates/raytracing-cpu/src/lib.rs:446-457) /
  * OptixBackendSettings (crates/raytracing-optix/src/lib.rs:25-28). */
 typedef struct rtcuda_backend_settings {
@@ -256,7 +263,7 @@ typedef struct rtcuda_backend_settings {
     uint32_t tile_rank;
     uint32_t tile_world;              /* 0 or 1 => whole image */
     uint32_t collect_stats;           /* RTCUDA_STATS_* bits */
-    uint32_t _pad;
+    uint32_t flags;                   /* RTCUDA_BACKEND_* bits */
 } rtcuda_backend_settings;
 
 /* RenderOutput (crates/raytracing/src/renderer/mod.rs:49-59). NULL planes are skipped. */

@@ -103,7 +103,7 @@ class Settings(C.Structure):
 
 class BackendSettings(C.Structure):
     _fields_ = [("device_id", C.c_int32), ("max_paths_in_flight", C.c_uint32), ("tile_rank", C.c_uint32),
-                ("tile_world", C.c_uint32), ("collect_stats", C.c_uint32), ("_pad", C.c_uint32)]
+                ("tile_world", C.c_uint32), ("collect_stats", C.c_uint32), ("flags", C.c_uint32)]
 
 
 class Outputs(C.Structure):
@@ -130,6 +130,7 @@ class Stats(C.Structure):
 
 
 STATS_COUNTERS, STATS_KERNEL_TIMES = 1, 2
+BACKEND_WATERTIGHT = 1
 
 ABI_STRUCTS = [Camera, Shape, Instance, Light, Material, Texture, Image, SceneDesc, Settings, BackendSettings,
                Outputs, PixelOutput, Stats]

@@ -26,11 +26,13 @@ class CudaBackendSettings:
     tile_rank: int = 0                 # this context renders 64x64 tiles i with i % tile_world == tile_rank
     tile_world: int = 1
     collect_stats: int = 0             # _ffi.STATS_COUNTERS | _ffi.STATS_KERNEL_TIMES (True == counters)
+    watertight: bool = False           # Woop's watertight triangle test instead of the reference's Moller-Trumbore
 
     def to_c(self) -> _ffi.BackendSettings:
         b = _ffi.BackendSettings()
         b.device_id, b.max_paths_in_flight = self.device_id, self.max_paths_in_flight
         b.tile_rank, b.tile_world, b.collect_stats = self.tile_rank, self.tile_world, int(self.collect_stats)
+        b.flags = _ffi.BACKEND_WATERTIGHT if self.watertight else 0
         return b
 
 

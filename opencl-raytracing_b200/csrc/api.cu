@@ -598,6 +598,7 @@ void upload_scene(rtcuda_scene* s, const rtcuda_scene_desc* d) {
     sc.vertices = s->vertices.p; sc.tris = s->tris.p; sc.normals = s->normals.p; sc.uvs = s->uvs.p;
     sc.instance_count = d->instance_count; sc.light_count = d->light_count; sc.material_count = d->material_count;
     sc.texture_count = d->texture_count; sc.env_texture = d->environment_light_texture;
+    sc.watertight = (s->ctx->bs.flags & RTCUDA_BACKEND_WATERTIGHT) ? 1u : 0u;
     sc.all_diffuse = 1;
     for (uint32_t m = 0; m < d->material_count; m++) if (d->materials[m].kind != RTCUDA_MATERIAL_DIFFUSE) sc.all_diffuse = 0;
 

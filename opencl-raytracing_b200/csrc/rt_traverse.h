@@ -60,6 +60,50 @@ RT_HD bool triangle_t(V3 p0, V3 p1, V3 p2, V3 o, V3 d, float t_min, float t_max,
     return true;
 }
 
+// Watertight ray / triangle test (Woop, Benthin, Wald 2013), the north star's intersection for meshes whose silhouettes
+// and shared edges must not leak; selected per context (RTCUDA_BACKEND_WATERTIGHT). The reference's Moller-Trumbore above
+// stays the default because it is what the parity gates compare against. The scaled edge functions
+// are evaluated with un-fused multiplies: a shared edge must produce exactly opposite values in its two triangles, which
+// an FMA contraction (one product rounded, the other not) would break. The ray's shear constants are recomputed per test
+// instead of being carried per ray: the mode costs registers only where it is used. No back-face culling, inclusive
+// t range, barycentrics in the (v1, v2) convention of triangle_t.
+#if defined(__CUDA_ARCH__)
+RT_HD float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+RT_HD float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+#else
+RT_HD float mul_rn(float a, float b) { volatile float r = a * b; return r; }
+RT_HD float sub_rn(float a, float b) { volatile float r = a - b; return r; }
+#endif
+RT_HD float comp3(V3 a, int k) { return k == 0 ? a.x : (k == 1 ? a.y : a.z); }
+RT_HD bool triangle_watertight(V3 p0, V3 p1, V3 p2, V3 o, V3 d, float t_min, float t_max, float& t, float& u, float& v) {
+    const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+    const int kz = ax > ay ? (ax > az ? 0 : 2) : (ay > az ? 1 : 2);
+    int kx = kz == 2 ? 0 : kz + 1, ky = kx == 2 ? 0 : kx + 1;
+    const float dz = comp3(d, kz);
+    if (dz < 0.0f) { const int s = kx; kx = ky; ky = s; }
+    const float sz = 1.0f / dz, sx = comp3(d, kx) * sz, sy = comp3(d, ky) * sz;
+    const V3 A = p0 - o, B = p1 - o, C = p2 - o;
+    const float Ax = sub_rn(comp3(A, kx), mul_rn(sx, comp3(A, kz))), Ay = sub_rn(comp3(A, ky), mul_rn(sy, comp3(A, kz)));
+    const float Bx = sub_rn(comp3(B, kx), mul_rn(sx, comp3(B, kz))), By = sub_rn(comp3(B, ky), mul_rn(sy, comp3(B, kz)));
+    const float Cx = sub_rn(comp3(C, kx), mul_rn(sx, comp3(C, kz))), Cy = sub_rn(comp3(C, ky), mul_rn(sy, comp3(C, kz)));
+    float U = sub_rn(mul_rn(Cx, By), mul_rn(Cy, Bx)), V = sub_rn(mul_rn(Ax, Cy), mul_rn(Ay, Cx)), W = sub_rn(mul_rn(Bx, Ay), mul_rn(By, Ax));
+    if (U == 0.0f || V == 0.0f || W == 0.0f) {   // on an edge in single precision: decide in double
+        U = (float)((double)Cx * (double)By - (double)Cy * (double)Bx);
+        V = (float)((double)Ax * (double)Cy - (double)Ay * (double)Cx);
+        W = (float)((double)Bx * (double)Ay - (double)By * (double)Ax);
+    }
+    if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
+    const float det = U + V + W;
+    if (det == 0.0f) return false;
+    const float T = U * (sz * comp3(A, kz)) + V * (sz * comp3(B, kz)) + W * (sz * comp3(C, kz));
+    const float inv = 1.0f / det;
+    t = T * inv;
+    if (!(t >= t_min && t <= t_max)) return false;
+    u = V * inv;
+    v = W * inv;
+    return true;
+}
+
 RT_HD float safe_rcp_dir(float d) {
     float a = fabsf(d) > 1.0e-20f ? d : copysignf(1.0e-20f, d);
     return 1.0f / a;
@@ -211,7 +255,8 @@ struct Traversal {
         float t, u = 0.0f, v = 0.0f;
         bool h;
         if (f2u(pc.w) == 0u) {
-            h = triangle_t(xyz(pa), xyz(pb), xyz(pc), o, d, t_min, closest, t, u, v);
+            h = sc.watertight ? triangle_watertight(xyz(pa), xyz(pb), xyz(pc), o, d, t_min, closest, t, u, v)
+                              : triangle_t(xyz(pa), xyz(pb), xyz(pc), o, d, t_min, closest, t, u, v);
         } else {
             const Instance* inst = sc.instances + f2u(pa.w);
             V3 oo = apply_point(inst->w2o, o), od = apply_vector(inst->w2o, d);

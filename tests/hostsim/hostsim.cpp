@@ -141,6 +141,7 @@ void build(HostScene& hs, const rtcuda_scene_desc* d) {
     sc.vertices = d->vertices; sc.tris = d->tris; sc.normals = d->normals; sc.uvs = d->uvs;
     sc.instance_count = d->instance_count; sc.light_count = d->light_count; sc.material_count = d->material_count;
     sc.texture_count = d->texture_count; sc.env_texture = d->environment_light_texture;
+    sc.watertight = std::getenv("HOSTSIM_WATERTIGHT") ? 1u : 0u;   // test switch for RTCUDA_BACKEND_WATERTIGHT
     sc.all_diffuse = 1;
     for (uint32_t m = 0; m < d->material_count; m++) if (d->materials[m].kind != 0) sc.all_diffuse = 0;
     sc.prim_count = n_prims; sc.node_count = 0;
@@ -334,6 +335,18 @@ static void warp_sim(const SceneD& sc, const std::vector<SimRay>& rays, const ch
 }
 
 extern "C" {
+
+// mode 0: triangle_t (the reference's Moller-Trumbore), mode 1: triangle_watertight. out = t, u, v
+__attribute__((visibility("default")))
+int hostsim_ray_triangle(int mode, const float* p0, const float* p1, const float* p2, const float* o, const float* d, float t_min, float t_max,
+                         float* out) {
+    float t = 0, u = 0, v = 0;
+    const V3 a = mk3(p0[0], p0[1], p0[2]), b = mk3(p1[0], p1[1], p1[2]), c = mk3(p2[0], p2[1], p2[2]);
+    const V3 oo = mk3(o[0], o[1], o[2]), dd = mk3(d[0], d[1], d[2]);
+    const bool h = mode ? triangle_watertight(a, b, c, oo, dd, t_min, t_max, t, u, v) : triangle_t(a, b, c, oo, dd, t_min, t_max, t, u, v);
+    out[0] = t; out[1] = u; out[2] = v;
+    return h ? 1 : 0;
+}
 
 // stats_out[8]: primary, bounce, shadow, aov rays, nodes fetched, prims fetched, wide node count, collapse levels
 __attribute__((visibility("default")))

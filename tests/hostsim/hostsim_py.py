@@ -31,6 +31,9 @@ def lib():
         l.hostsim_render.argtypes = [C.POINTER(_ffi.SceneDesc), C.POINTER(_ffi.Settings), C.POINTER(_ffi.Outputs), C.c_uint32,
                                      C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]
         l.hostsim_render.restype = C.c_int
+        fp = C.POINTER(C.c_float)
+        l.hostsim_ray_triangle.argtypes = [C.c_int, fp, fp, fp, fp, fp, C.c_float, C.c_float, fp]
+        l.hostsim_ray_triangle.restype = C.c_int
         _lib = l
     return _lib
 
@@ -44,3 +47,11 @@ def render(scene, settings, tile_rank=0, tile_world=1, capacity=0):
         raise RuntimeError("hostsim_render failed")
     names = ["primary_rays", "bounce_rays", "shadow_rays", "aov_rays", "nodes_fetched", "prims_fetched", "bvh_node_count", "collapse_levels"]
     return out, dict(zip(names, list(stats)))
+
+
+def ray_triangle(mode, p0, p1, p2, o, d, t_min=0.0, t_max=float("inf")):
+    """(hit, t, u, v) of the kernel-side triangle tests: mode 0 = Moller-Trumbore (reference), 1 = watertight"""
+    fa = lambda v: (C.c_float * 3)(*[float(x) for x in v])
+    out = (C.c_float * 3)()
+    h = lib().hostsim_ray_triangle(mode, fa(p0), fa(p1), fa(p2), fa(o), fa(d), t_min, t_max, out)
+    return bool(h), out[0], out[1], out[2]

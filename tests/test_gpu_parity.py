@@ -302,3 +302,15 @@ def test_cached_memory_release(rc):
     rc._ffi.load_library().rtcuda_release_cached_memory()
     c, _ = gpu_render(rc, sc, st)
     assert np.array_equal(a.beauty, b.beauty) and np.array_equal(a.beauty, c.beauty)
+
+
+def test_watertight_mode(rc, oracle):
+    """RTCUDA_BACKEND_WATERTIGHT: same first hits as the reference's test up to grazing edges, same image statistically"""
+    sc = load_scene("cbbunny_area_light_transforms", 320, 180)
+    st = rc.RaytracerSettings(outputs=dbg() | A.BEAUTY, samples_per_pixel=4)
+    wt, _ = gpu_render(rc, sc, st, watertight=True)
+    mt, _ = gpu_render(rc, sc, st)
+    ref, _ = oracle.render(sc, st)
+    assert_first_hit_parity(wt, ref)
+    assert (wt.debug_ids == mt.debug_ids).all(axis=-1).mean() >= 0.9999
+    assert beauty_close(wt.beauty, mt.beauty)

@@ -169,3 +169,48 @@ def test_builders_give_identical_frames(rc, hostsim, monkeypatch):
     for plane in ("beauty", "normals", "debug_ids", "debug_depth"):
         assert np.array_equal(getattr(a, plane), getattr(b, plane)), plane
     assert sa["nodes_fetched"] < 0.8 * sb["nodes_fetched"]
+
+
+def test_watertight_triangle_never_leaks_on_shared_edges(hostsim):
+    """Woop's test (RTCUDA_BACKEND_WATERTIGHT): a ray through a point of the edge shared by two triangles hits at least one of
+    them, for every such ray; agrees with Moller-Trumbore in the interior. (The reference's test is not watertight,
+    geometry.rs:301-340; it stays the default for parity.)"""
+    rng = np.random.default_rng(3)
+    leaks_wt = leaks_mt = 0
+    for _ in range(600):
+        a, b, c, d = (rng.standard_normal(3).astype(np.float32) for _ in range(4))   # triangles (a, b, c) and (b, a, d) share edge ab
+        s = np.float32(rng.random())
+        on_edge = (a + s * (b - a)).astype(np.float32)
+        o = (on_edge + rng.standard_normal(3) * 3).astype(np.float32)
+        dirv = (on_edge - o).astype(np.float32)
+        hit_wt = hostsim.ray_triangle(1, a, b, c, o, dirv)[0] or hostsim.ray_triangle(1, b, a, d, o, dirv)[0]
+        hit_mt = hostsim.ray_triangle(0, a, b, c, o, dirv)[0] or hostsim.ray_triangle(0, b, a, d, o, dirv)[0]
+        # the silhouette case (both triangles on the same side of the ray plane) may legitimately miss both: only count
+        # rays for which c and d lie on opposite sides of the plane through the ray and the edge
+        n = np.cross(dirv.astype(np.float64), (b - a).astype(np.float64))
+        if np.dot(n, c - on_edge) * np.dot(n, d - on_edge) >= 0:
+            continue
+        leaks_wt += not hit_wt
+        leaks_mt += not hit_mt
+    assert leaks_wt == 0
+    for _ in range(300):   # interior points: same hit, t / barycentrics equal to rounding
+        a, b, c = (rng.standard_normal(3).astype(np.float32) for _ in range(3))
+        w = rng.dirichlet((2, 2, 2))
+        p = (w[0] * a + w[1] * b + w[2] * c).astype(np.float32)
+        o = (p + rng.standard_normal(3) * 2).astype(np.float32)
+        dirv = (p - o).astype(np.float32)
+        h0, t0, u0, v0 = hostsim.ray_triangle(0, a, b, c, o, dirv)
+        h1, t1, u1, v1 = hostsim.ray_triangle(1, a, b, c, o, dirv)
+        if min(w) > 1e-3:
+            assert h0 and h1
+            assert abs(t0 - t1) < 1e-3 * max(1.0, abs(t0)) and abs(u0 - u1) < 1e-3 and abs(v0 - v1) < 1e-3
+
+
+def test_watertight_mode_matches_reference_first_hits(rc, oracle, hostsim, monkeypatch):
+    sc = load_scene("cbbunny_area_light_transforms", 96, 54)
+    st = rc.RaytracerSettings(outputs=dbg() | A.BEAUTY, samples_per_pixel=2)
+    monkeypatch.setenv("HOSTSIM_WATERTIGHT", "1")
+    out, _ = hostsim.render(sc, st)
+    ref, _ = oracle.render(sc, st, num_threads=4)
+    assert_first_hit_parity(out, ref)
+    assert beauty_close(out.beauty, ref.beauty)

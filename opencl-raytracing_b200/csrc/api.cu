@@ -192,6 +192,7 @@ struct rtcuda_scene {
     DevBuf<MipChain> mips;
     DevBuf<Node8> nodes;
     DevBuf<Prim> prims;
+    DevBuf<ShadeRec> shade_recs;
     std::vector<rtcuda_light> host_lights;
     // render state
     DevBuf<uint32_t> pixel_list;
@@ -605,6 +606,12 @@ void upload_scene(rtcuda_scene* s, const rtcuda_scene_desc* d) {
     build_bvh(s, instances, (uint32_t)n_prims);
     sc.nodes = s->nodes.p;
     sc.prims = s->prims.p;
+    sc.shade_recs = nullptr;
+    if (n_prims) {
+        s->shade_recs.alloc(n_prims);
+        launch_shade_recs(st, sc, s->shade_recs.p, s->lc);
+        sc.shade_recs = s->shade_recs.p;
+    }
     CK(cudaEventRecord(e2, st));
     CK(cudaStreamSynchronize(st));
     float ms_up = 0, ms_build = 0;

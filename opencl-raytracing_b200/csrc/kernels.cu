@@ -371,6 +371,16 @@ void launch_light_tris(cudaStream_t st, const ShapeD* shapes, uint32_t shape, ui
     lc.launches++;
 }
 
+__global__ void __launch_bounds__(BLOCK) k_shade_recs(const __grid_constant__ SceneD sc, ShadeRec* out) {
+    const uint32_t i = blockIdx.x * BLOCK + threadIdx.x;
+    if (i < sc.prim_count) shade_rec_body(i, sc, out);
+}
+void launch_shade_recs(cudaStream_t st, const SceneD& sc, ShadeRec* out, LaunchCounter& lc) {
+    if (!sc.prim_count) return;
+    k_shade_recs<<<grid_for(sc.prim_count), BLOCK, 0, st>>>(sc, out);
+    lc.launches++;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // mip pyramid kernels
 // ---------------------------------------------------------------------------------------------------

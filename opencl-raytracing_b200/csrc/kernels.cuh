@@ -42,6 +42,9 @@ void launch_ploc_round(cudaStream_t st, const BuildCtx& b, void* scan_temp, size
 void launch_light_tris(cudaStream_t st, const ShapeD* shapes, uint32_t shape, uint32_t tri_count, const float* vertices, const uint32_t* tris,
                        LightTri* out, LaunchCounter& lc);
 
+// shading records (rt_scene.h ShadeRec), one per packed primitive
+void launch_shade_recs(cudaStream_t st, const SceneD& sc, ShadeRec* out, LaunchCounter& lc);
+
 // mip pyramids
 void launch_to_f32(cudaStream_t st, const uint8_t* src, uint32_t format, float* dst, uint32_t n, LaunchCounter& lc);
 void launch_resize(cudaStream_t st, const float* src, float* dst, uint32_t w, uint32_t h, uint32_t ch, uint32_t n_out, int axis, LaunchCounter& lc);

@@ -120,6 +120,33 @@ struct HitInfo {  // accel.rs:13-25 (+ ids for the debug planes)
 // intersect_shape + ray_mesh_intersect / ray_sphere_intersect + the identity local_to_root step of
 // traverse_bvh (accel.rs:144-164), from the (t, prim, u, v) record the traversal kernel wrote.
 RT_HD void reconstruct_hit(const SceneD& sc, V3 o, V3 d, const Hit& h, bool need_derivs, HitInfo& out) {
+    if (!need_derivs && sc.shade_recs) {   // the gathered record (rt_scene.h ShadeRec): same values, two load levels instead of five
+        const ShadeRec* r = sc.shade_recs + h.prim;
+        const float4 a = ldg(&r->n0_geom), b = ldg(&r->n1_prim), c = ldg(&r->n2_flags), e = ldg(&r->uv2_mat);
+        const uint32_t flags = f2u(c.w);
+        if (!(flags & REC_SPHERE)) {
+            const uint32_t geom = f2u(a.w);
+            const Instance& inst = sc.instances[geom];
+            out.t = h.t;
+            out.geom_id = geom;
+            out.prim_id = f2u(b.w);
+            out.material = f2u(e.z);
+            out.light = f2u(e.w);
+            const float u = h.u, v = h.v, w = 1.0f - u - v;
+            const V3 n_obj = (flags & REC_FLAT) ? xyz(a) : unit(w * xyz(a) + u * xyz(b) + v * xyz(c));
+            V2 uv0 = mk2(0, 0), uv1 = mk2(1, 0), uv2 = mk2(0, 1);
+            if (flags & REC_UV) {
+                const float4 q = ldg(&r->uv01);
+                uv0 = mk2(q.x, q.y); uv1 = mk2(q.z, q.w); uv2 = mk2(e.x, e.y);
+            }
+            out.uv = w * uv0 + u * uv1 + v * uv2;
+            out.point = o + d * h.t;
+            out.normal = unit(unit(apply_vector_transposed(inst.w2o, n_obj)));
+            out.dpdu = apply_vector(inst.o2w, mk3(0.0f));
+            out.dpdv = out.dpdu;
+            return;
+        }
+    }
     const Prim* pr = sc.prims + h.prim;
     const uint32_t geom = f2u(ldg(&pr->a).w), prim_id = f2u(ldg(&pr->b).w), kind = f2u(ldg(&pr->c).w);
     const Instance& inst = sc.instances[geom];

@@ -77,6 +77,21 @@ struct CameraD {
     M4 raster_to_camera, camera_to_world;  // forward matrices only (lib.rs:145-195)
 };
 
+// What shade needs to rebuild the reference's hit record at a triangle, gathered once per scene in BVH primitive order
+// (five 128-bit loads from one place instead of the chain packed primitive -> instance -> index triple -> three vertex
+// normals / uvs, each a dependent round trip in a kernel that is bound by exactly that latency): the object-space vertex
+// normals (or, for meshes without normals, the geometric normal unit(cross(p2 - p0, p1 - p0)), geometry.rs:244-247),
+// the vertex uvs, and the ids shade would otherwise fetch through the instance. Values are copies, so the arithmetic of
+// reconstruct_hit is unchanged. Spheres and the depth-0 anti-aliased path (needs object-space positions) keep the long way.
+struct ShadeRec {
+    float4 n0_geom;    // n0.xyz (or the flat normal) | geom_id
+    float4 n1_prim;    // n1.xyz | prim_id
+    float4 n2_flags;   // n2.xyz | REC_* bits
+    float4 uv01;       // uv0.xy, uv1.xy
+    float4 uv2_mat;    // uv2.xy | material | area light
+};
+enum { REC_FLAT = 1u, REC_UV = 2u, REC_SPHERE = 4u };
+
 // 80-byte compressed 8-wide node (DESIGN.md "BVH8 node"): five 128-bit loads.
 //   n0 = origin.xyz | ex | ey<<8 | ez<<16 | imask<<24
 //   n1 = child_base | prim_base | meta[0..3] | meta[4..7]
@@ -88,6 +103,7 @@ struct SceneD {
     CameraD camera;
     const Node8* nodes;
     const Prim* prims;
+    const ShadeRec* shade_recs;   // by packed primitive index, or null
     uint32_t prim_count;
     uint32_t node_count;
     const Instance* instances;
@@ -126,5 +142,42 @@ RT_HD void light_tri_body(uint32_t tri, const ShapeD& em, const float* vertices,
 }
 
 RT_HD V2 load2(const float* p, uint32_t i) { return mk2(ldg(p + 2 * (size_t)i), ldg(p + 2 * (size_t)i + 1)); }
+
+RT_HD void shade_rec_body(uint32_t i, const SceneD& sc, ShadeRec* out) {
+    const Prim& pr = sc.prims[i];
+    const uint32_t geom = f2u(pr.a.w), prim_id = f2u(pr.b.w), kind = f2u(pr.c.w);
+    const Instance& inst = sc.instances[geom];
+    ShadeRec r;
+    uint32_t flags = 0;
+    V3 n0 = mk3(0.0f), n1 = mk3(0.0f), n2 = mk3(0.0f);
+    V2 uv0 = mk2(0, 0), uv1 = mk2(1, 0), uv2 = mk2(0, 1);
+    if (kind != 0) flags = REC_SPHERE;
+    else {
+        const uint32_t* t = sc.tris + 3 * (size_t)(inst.tri_offset + prim_id);
+        const uint32_t i0 = t[0], i1 = t[1], i2 = t[2];
+        if (inst.normal_offset == NONE) {
+            const V3 p0 = load3(sc.vertices, inst.vertex_offset + i0), p1 = load3(sc.vertices, inst.vertex_offset + i1),
+                     p2 = load3(sc.vertices, inst.vertex_offset + i2);
+            n0 = unit(cross(p2 - p0, p1 - p0));
+            flags |= REC_FLAT;
+        } else {
+            n0 = load3(sc.normals, inst.normal_offset + i0);
+            n1 = load3(sc.normals, inst.normal_offset + i1);
+            n2 = load3(sc.normals, inst.normal_offset + i2);
+        }
+        if (inst.uv_offset != NONE) {
+            uv0 = load2(sc.uvs, inst.uv_offset + i0);
+            uv1 = load2(sc.uvs, inst.uv_offset + i1);
+            uv2 = load2(sc.uvs, inst.uv_offset + i2);
+            flags |= REC_UV;
+        }
+    }
+    r.n0_geom = make_float4(n0.x, n0.y, n0.z, u2f(geom));
+    r.n1_prim = make_float4(n1.x, n1.y, n1.z, u2f(prim_id));
+    r.n2_flags = make_float4(n2.x, n2.y, n2.z, u2f(flags));
+    r.uv01 = make_float4(uv0.x, uv0.y, uv1.x, uv1.y);
+    r.uv2_mat = make_float4(uv2.x, uv2.y, u2f(inst.material), u2f(inst.area_light));
+    out[i] = r;
+}
 
 }  // namespace rt

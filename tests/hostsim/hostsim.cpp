@@ -37,6 +37,7 @@ struct HostScene {
     std::vector<uint8_t> image_bytes;
     std::vector<Node8> nodes;
     std::vector<Prim> prims;
+    std::vector<ShadeRec> shade_recs;
     uint32_t n_levels = 0;
 };
 
@@ -233,6 +234,11 @@ void build(HostScene& hs, const rtcuda_scene_desc* d) {
     sc.scene_center[0] = c.x; sc.scene_center[1] = c.y; sc.scene_center[2] = c.z;
     sc.scene_radius = n == 1 ? INFINITY : length(mx - c);
     if (counters[2] != n) sc.node_count = 0xdeadbeef;  // lost primitives: surfaced through the stats
+    else if (!std::getenv("HOSTSIM_NO_SHADE_RECS")) {
+        hs.shade_recs.resize(n);
+        for (uint32_t i = 0; i < n; i++) shade_rec_body(i, sc, hs.shade_recs.data());
+        sc.shade_recs = hs.shade_recs.data();
+    }
 }
 
 RenderParams make_params(const rtcuda_settings* st) {

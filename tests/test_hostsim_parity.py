@@ -214,3 +214,15 @@ def test_watertight_mode_matches_reference_first_hits(rc, oracle, hostsim, monke
     ref, _ = oracle.render(sc, st, num_threads=4)
     assert_first_hit_parity(out, ref)
     assert beauty_close(out.beauty, ref.beauty)
+
+
+@pytest.mark.parametrize("name", ["cb_texture", "cbbunny_area_light_transforms"])
+def test_shading_records_are_copies(rc, hostsim, monkeypatch, name):
+    """the per-primitive shading records (rt_scene.h ShadeRec) hold copies of the mesh attributes: frames are bit-identical
+    with and without them (HOSTSIM_NO_SHADE_RECS takes the long way through instance -> indices -> vertex arrays)"""
+    sc = load_scene(name, 64, 36)
+    st = rc.RaytracerSettings(outputs=A.BEAUTY, samples_per_pixel=2, antialias_primary_rays=False)
+    a, _ = hostsim.render(sc, st)
+    monkeypatch.setenv("HOSTSIM_NO_SHADE_RECS", "1")
+    b, _ = hostsim.render(sc, st)
+    assert np.array_equal(a.beauty, b.beauty)

@@ -200,8 +200,8 @@ struct rtcuda_scene {
     DevBuf<float4> accum;
     WaveArena arena;
     size_t arena_capacity = 0, arena_shadow_k = 0, arena_depth = 0;
-    View<RngState> rng_state;
-    View<float4> weight, radiance, ray_o[2], ray_d[2], hits, sray_o, sray_d, scontrib;
+    View<PathState> state;
+    View<float4> radiance, ray_o[2], ray_d[2], hits, sray_o, sray_d, scontrib;
     View<uint4> svertex;
     View<uint32_t> counters;
     View<unsigned long long> counters64;
@@ -689,8 +689,7 @@ void ensure_wave(rtcuda_scene* s, uint32_t capacity, uint32_t shadow_k, uint32_t
     const size_t need = cap * (16 + 16 * 7 + 16) + cap * k * 48 + n_counters * 4 + ((size_t)max_depth + 3) * 8 + 16 * 256;
     s->arena.reserve(s->ctx->device, need);
     auto view = [&](auto& v, size_t count) { v.p = s->arena.carve<std::remove_pointer_t<decltype(v.p)>>(count); v.n = count; };
-    view(s->rng_state, cap);
-    view(s->weight, cap);
+    view(s->state, cap);
     view(s->radiance, cap);
     for (int i = 0; i < 2; i++) { view(s->ray_o[i], cap); view(s->ray_d[i], cap); }
     view(s->hits, cap);
@@ -822,7 +821,7 @@ void render_device(rtcuda_scene* s, const rtcuda_settings* settings, const rtcud
             Wave w{};
             w.pixel_list = s->pixel_list.p;
             w.capacity = np_batch * ns_batch;
-            w.rng_state = s->rng_state.p; w.weight = s->weight.p; w.radiance = s->radiance.p; w.hits = s->hits.p;
+            w.state = s->state.p; w.radiance = s->radiance.p; w.hits = s->hits.p;
             w.stats = s->stats_dev.p;
             w.shadow_k = shadow_k; w.svertex = s->svertex.p;
             w.sray_o = s->sray_o.p; w.sray_d = s->sray_d.p; w.scontrib = s->scontrib.p;
@@ -925,7 +924,7 @@ void render_pixel(rtcuda_scene* s, const rtcuda_settings* settings, uint32_t x, 
     Wave w{};
     w.pixel_list = one_pixel.p;
     w.pixel_base = 0; w.n_pixels = 1; w.sample_base = lo; w.n_samples = n; w.capacity = n;
-    w.rng_state = s->rng_state.p; w.weight = s->weight.p; w.radiance = s->radiance.p; w.hits = s->hits.p;
+    w.state = s->state.p; w.radiance = s->radiance.p; w.hits = s->hits.p;
     w.stats = s->stats_dev.p;
     w.shadow_k = shadow_k; w.svertex = s->svertex.p;
     w.sray_o = s->sray_o.p; w.sray_d = s->sray_d.p; w.scontrib = s->scontrib.p;

@@ -63,9 +63,15 @@ __global__ void __launch_bounds__(BLOCK) k_raygen(const __grid_constant__ SceneD
 // of work, which keeps the full-mask ballots / shuffles legal.
 constexpr int REFILL_MIN = 6;
 constexpr int TRI_MIN = 12;
+// Resident blocks per SM asked of the any-hit kernel: 5 (48 registers, ~76 B of spills) hides more of its load latency than the 4
+// that 64 registers allow — k_shadow 174 -> 168 ms on C3; the closest-hit kernel carries more state and lost 1 % (A/B in
+// profiles/r1_notes.md), so it keeps the register count it wants.
+#ifndef SHADOW_BLOCKS
+#define SHADOW_BLOCKS 5
+#endif
 
 template <bool ANY_HIT, bool STATS>
-__device__ __forceinline__ void warp_phase(Traversal<ANY_HIT, STATS>& tr, bool have, const SceneD& sc, TraverseStats* ts) {
+__device__ __forceinline__ void warp_phase(Traversal<ANY_HIT, STATS>& tr, uint32_t have, const SceneD& sc, TraverseStats* ts) {
     const unsigned FULL = 0xffffffffu;
     const bool wt = have && tr.has_tris();
     const bool wn = have && tr.has_nodes() && (!wt || tr.can_stash());
@@ -87,7 +93,7 @@ __global__ void __launch_bounds__(BLOCK) k_extend(const __grid_constant__ SceneD
     tr.stack = stack_mem;
     TraverseStats ts;
     ts.nodes = ts.prims = 0;
-    bool have = false, exhausted = n == 0;
+    uint32_t have = 0u, exhausted = n == 0 ? 1u : 0u;   // 32-bit flags: bools get packed into half registers (PRMT traffic in the loop)
     uint32_t q = 0;
     for (;;) {
         const unsigned need = __ballot_sync(FULL, !have);
@@ -102,16 +108,16 @@ __global__ void __launch_bounds__(BLOCK) k_extend(const __grid_constant__ SceneD
                 if (mine < n) {
                     q = mine;
                     const float4 o4 = w.ray_o_in[q], d4 = w.ray_d_in[q];
-                    have = tr.init(sc, xyz(o4), xyz(d4), t_min, o4.w);
+                    have = tr.init(sc, xyz(o4), xyz(d4), t_min, o4.w) ? 1u : 0u;
                     if (!have) w.hits[q] = make_float4(o4.w, u2f(NONE), 0.0f, 0.0f);
                 }
             }
-            if (base + (uint32_t)cnt >= n) exhausted = true;
+            if (base + (uint32_t)cnt >= n) exhausted = 1u;
         }
         warp_phase(tr, have, sc, &ts);
         if (have && !tr.next()) {
             w.hits[q] = make_float4(tr.hit.t, u2f(tr.hit.prim), tr.hit.u, tr.hit.v);
-            have = false;
+            have = 0u;
         }
     }
     if (STATS) {
@@ -172,7 +178,7 @@ __global__ void __launch_bounds__(BLOCK, std::is_same<Surf, DiffuseSurface>::val
 // vote loop as k_extend. A blocked ray zeroes its contribution entry; k_shadow_gather then adds each vertex's
 // entries to the path in light-sample order (deterministic: one thread per vertex, no float atomics).
 template <bool STATS>
-__global__ void __launch_bounds__(BLOCK) k_shadow(const __grid_constant__ SceneD sc, const __grid_constant__ Wave w, uint32_t* fetch_counter) {
+__global__ void __launch_bounds__(BLOCK, SHADOW_BLOCKS) k_shadow(const __grid_constant__ SceneD sc, const __grid_constant__ Wave w, uint32_t* fetch_counter) {
     const uint32_t n = (uint32_t)(*w.n_shadow >> 32);
     const unsigned FULL = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
@@ -181,7 +187,7 @@ __global__ void __launch_bounds__(BLOCK) k_shadow(const __grid_constant__ SceneD
     tr.stack = stack_mem;
     TraverseStats ts;
     ts.nodes = ts.prims = 0;
-    bool have = false, exhausted = n == 0;
+    uint32_t have = 0u, exhausted = n == 0 ? 1u : 0u;
     uint32_t q = 0, n_rays = 0;
     for (;;) {
         const unsigned need = __ballot_sync(FULL, !have);
@@ -198,16 +204,16 @@ __global__ void __launch_bounds__(BLOCK) k_shadow(const __grid_constant__ SceneD
                     const float4 o4 = w.sray_o[q], d4 = w.sray_d[q];
                     if (o4.w >= 0.0f) {   // negative: never occluded (non-finite origin quirk), not traced
                         n_rays++;
-                        have = tr.init(sc, xyz(o4), xyz(d4), 0.001f, o4.w);
+                        have = tr.init(sc, xyz(o4), xyz(d4), 0.001f, o4.w) ? 1u : 0u;
                     }
                 }
             }
-            if (base + (uint32_t)cnt >= n) exhausted = true;
+            if (base + (uint32_t)cnt >= n) exhausted = 1u;
         }
         warp_phase(tr, have, sc, &ts);
         if (have && !tr.next()) {
             if (tr.found) w.scontrib[q] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            have = false;
+            have = 0u;
         }
     }
     warp_add_stat(&w.stats[STAT_SHADOW], n_rays);

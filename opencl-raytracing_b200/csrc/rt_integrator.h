@@ -22,6 +22,13 @@ struct RenderParams {  // RaytracerSettings (renderer/mod.rs:84-98)
 };
 
 struct alignas(16) RngState { uint64_t state, inc; };
+// Per-slot path state that shade reads and writes back together, interleaved (32 B = one DRAM sector): at depth >= 1 only a
+// fraction of the slots is alive, so slot-indexed accesses are scattered and two separate 16-byte arrays cost two half-used
+// sectors each way. The accumulated radiance stays a dense array of its own (resolve streams it; shadow_gather updates it).
+struct alignas(32) PathState {
+    float4 weight;     // xyz path weight | w: bit0 specular_bounce, bits 8.. stratified dimension
+    RngState rng;      // PCG32 state + inc (inc is a pure function of (x, y, sample); carried so that shade needs no pixel lookup)
+};
 
 // Wavefront state of one batch (all pointers device memory; DESIGN.md "Path state").
 struct Wave {
@@ -30,10 +37,8 @@ struct Wave {
     uint32_t pixel_base, n_pixels, sample_base, n_samples;
     uint32_t capacity;           // slots allocated (>= n_pixels * n_samples)
     uint32_t depth;              // bounce index of the rays in the current queue
-    // path state, by slot
-    RngState* rng_state;         // PCG32 state + inc (inc is a pure function of (x, y, sample); carried so that shade needs no pixel lookup)
-    float4* weight;              // xyz path weight | w: bit0 specular_bounce, bits 8.. stratified dimension
-    float4* radiance;            // xyz accumulated radiance of this sample
+    PathState* state;            // weight + rng, by slot
+    float4* radiance;            // xyz accumulated radiance of this sample, by slot
     // ray queue (compacted), by queue position
     const float4* ray_o_in;      // origin.xyz | t_max
     const float4* ray_d_in;      // direction.xyz | slot
@@ -314,8 +319,8 @@ RT_HD void raygen_body(uint32_t slot, const SceneD& sc, const RenderParams& rp, 
     generate_ray<false>(sc.camera, px, py, s, rp.samples_per_pixel, true, ray, rd);
     RngState rs;
     rs.state = s.rng.state; rs.inc = s.rng.inc;
-    w.rng_state[slot] = rs;
-    w.weight[slot] = make_float4(1.0f, 1.0f, 1.0f, u2f(1u | (s.dimension << 8)));
+    w.state[slot].rng = rs;
+    w.state[slot].weight = make_float4(1.0f, 1.0f, 1.0f, u2f(1u | (s.dimension << 8)));
     w.radiance[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     w.ray_o_out[slot] = make_float4(ray.o.x, ray.o.y, ray.o.z, sc.camera.far_clip);
     w.ray_d_out[slot] = make_float4(ray.d.x, ray.d.y, ray.d.z, u2f(slot));
@@ -356,7 +361,7 @@ RT_HD bool shade_begin(uint32_t q, const SceneD& sc, const RenderParams& rp, con
     if (!has_hit && sc.env_texture == NONE) return false;
 
     const float4 rad4 = w.radiance[slot];
-    const float4 wt4 = w.weight[slot];
+    const float4 wt4 = w.state[slot].weight;
     S.radiance = xyz(rad4);
     S.path_weight = xyz(wt4);
     S.flags = f2u(wt4.w);
@@ -367,7 +372,7 @@ RT_HD bool shade_begin(uint32_t q, const SceneD& sc, const RenderParams& rp, con
         return false;
     }
     const bool specular_bounce = (S.flags & 1u) != 0;
-    const RngState rs = w.rng_state[slot];
+    const RngState rs = w.state[slot].rng;
     S.sidx = w.sample_base + slot / w.n_pixels;
     S.s.init(rp.sampler);
     S.s.rng.state = rs.state;
@@ -498,10 +503,10 @@ RT_HD void shade_vertex(bool active, uint32_t q, const SceneD& sc, const RenderP
     if (!alive) return;
     const V3 pw = S.path_weight * (bs.f * fabsf(bs.wi.z) / bs.pdf);
     const uint32_t spec = (bs.component & SPECULAR) ? 1u : 0u;
-    w.weight[S.slot] = make_float4(pw.x, pw.y, pw.z, u2f(spec | (s2.dimension << 8)));
+    w.state[S.slot].weight = make_float4(pw.x, pw.y, pw.z, u2f(spec | (s2.dimension << 8)));
     RngState rs;
     rs.state = s2.rng.state; rs.inc = s2.rng.inc;
-    w.rng_state[S.slot] = rs;
+    w.state[S.slot].rng = rs;
     const V3 nd = S.fr.to_world(bs.wi);
     RT_CHECK(rpos < w.capacity);
     w.ray_o_out[rpos] = make_float4(S.hit.point.x, S.hit.point.y, S.hit.point.z, RT_INF);

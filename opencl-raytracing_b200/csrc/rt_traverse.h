@@ -115,7 +115,7 @@ RT_HD float safe_rcp_dir(float d) {
 template <int K>
 RT_HD float qfloat(uint32_t w) {
 #if defined(__CUDA_ARCH__)
-    return __uint_as_float(__byte_perm(w, 0x3f800000u, 0x7604u + (K << 4)));
+    return __uint_as_float(__byte_perm(0x3f800000u, w, 0x3240u + (K << 4)));  // selector as the immediate, the constant in a register
 #else
     return u2f(0x3f800000u | (((w >> (8 * K)) & 0xffu) << 8));
 #endif
@@ -149,12 +149,12 @@ struct Traversal {
     int sp;
     Hit hit;
     uint32_t hit_geom, hit_pid;  // ids of the current closest hit (tie-break)
-    bool found;
+    uint32_t found;  // 32-bit flag (a bool would be packed into a half register)
 
     RT_HD bool init(const SceneD& sc, V3 o_, V3 d_, float t_min_, float t_max_) {
         o = o_; d = d_; t_min = t_min_; closest = t_max_;
         hit.prim = NONE; hit.t = t_max_; hit.u = hit.v = 0.0f;
-        found = false;
+        found = 0u;
         hit_geom = hit_pid = 0u;
         sp = 0;
         idir = mk3(safe_rcp_dir(d.x), safe_rcp_dir(d.y), safe_rcp_dir(d.z));
@@ -271,7 +271,7 @@ struct Traversal {
             hit.prim = pi;
             hit.u = u;
             hit.v = v;
-            found = true;
+            found = 1u;
             if (ANY_HIT) { ngroup.y = 0u; tgroup.y = 0u; sp = 0; }
         }
     }
@@ -300,7 +300,7 @@ RT_HD bool traverse(const SceneD& sc, V3 o, V3 d, float t_min, float t_max, Hit&
         } while (tr.next());
     }
     hit = tr.hit;
-    return tr.found;
+    return tr.found != 0u;
 }
 
 }  // namespace rt

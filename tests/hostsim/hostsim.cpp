@@ -404,16 +404,16 @@ int hostsim_render(const rtcuda_scene_desc* d, const rtcuda_settings* st, rtcuda
         const uint32_t np_batch = std::min(np_all, capacity);
         const uint32_t ns_batch = std::max(1u, std::min(st->samples_per_pixel, capacity / np_batch));
         const uint32_t cap = np_batch * ns_batch;
-        std::vector<RngState> rng(cap);
+        std::vector<PathState> state(cap);
         const size_t kk = std::max(1u, shadow_k);
-        std::vector<float4> weight(cap), radiance(cap), ro[2], rd[2], hits(cap), sray_o((size_t)cap * kk), sray_d((size_t)cap * kk), scontrib((size_t)cap * kk);
+        std::vector<float4> radiance(cap), ro[2], rd[2], hits(cap), sray_o((size_t)cap * kk), sray_d((size_t)cap * kk), scontrib((size_t)cap * kk);
         for (int i = 0; i < 2; i++) { ro[i].resize(cap); rd[i].resize(cap); }
         std::vector<uint4> svertex(cap);
         std::vector<float4> accum(np_all, make_float4(0, 0, 0, 0));
         unsigned long long dummy_stats[STAT_TOTAL] = {0};
         Wave w{};
         w.pixel_list = pixels.data(); w.capacity = cap;
-        w.rng_state = rng.data(); w.weight = weight.data(); w.radiance = radiance.data(); w.hits = hits.data(); w.stats = dummy_stats;
+        w.state = state.data(); w.radiance = radiance.data(); w.hits = hits.data(); w.stats = dummy_stats;
         w.shadow_k = shadow_k; w.svertex = svertex.data(); w.sray_o = sray_o.data(); w.sray_d = sray_d.data(); w.scontrib = scontrib.data();
         for (uint32_t p0 = 0; p0 < np_all; p0 += np_batch) {
             const uint32_t np = std::min(np_batch, np_all - p0);

@@ -30,6 +30,10 @@ WORKLOADS = {
     "C5s": ("cb", 1920, 1080, 32, 8, 1),     # same mesh, 1080p / 32 spp (quick check of the HBM-bound regime)
 }
 SYNTHETIC = {"C5": (4096, 2048), "C5s": (4096, 2048)}
+# Tile edge of the multi-GPU deal: BASELINE names 64x64 tiles for C5; the other frames concentrate their cost in part of the
+# raster (C3: the box covers a quarter of it), where 16x16 tiles balance the ranks to < 1 %.
+TILE_SIZE = {"C5": 64, "C5s": 64}
+CPU_SPP = {"C3": 16, "C3s": 16, "C2": 64}   # bounded CPU sample: ~10-30 s of host work on a 16-thread box
 
 
 DATA_NOTE = "scene fixture (reference asset; C5: procedural mesh generated in-process, seed 42)"
@@ -111,6 +115,8 @@ def main():
     ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-spp", type=int, default=0, help="spp of the bounded CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tile-size", type=int, default=0, help="tile edge of the multi-GPU deal (0 = per workload: 64 for C5, else 16)")
+    ap.add_argument("--partition", default="tiles", choices=["tiles", "samples"])
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -118,9 +124,11 @@ def main():
     fixture, W, H, spp, depth, ls = WORKLOADS[args.workload]
     what = f"{fixture}.glb" + (f" + synthetic displaced UV-sphere {SYNTHETIC[args.workload][0]}x{SYNTHETIC[args.workload][1]} quads (seed 42)"
                                if args.workload in SYNTHETIC else "")
+    tile = args.tile_size or TILE_SIZE.get(args.workload, 16)
+    part = (f"{tile}x{tile} tiles round-robin" if args.partition == "tiles" else "sample ranges of every pixel")
     config = {"workload": f"{args.workload}: {what} {W}x{H}, {spp} spp, depth {depth}, light samples {ls}, "
                           f"independent sampler, seed 42",
-              "triangles": None, "partition": f"64x64 tiles round-robin over {world} GPU(s), scene replicated, 1 NCCL sum-reduce per frame",
+              "triangles": None, "partition": f"{part} over {world} GPU(s), scene replicated, 1 NCCL sum-reduce per frame",
               "l2": "every step re-streams ~17 GB of wavefront state per batch through L2 (>> 126 MB) and a 512 MiB buffer is "
                     "written between timed steps; the 3 MB BVH is L2-resident by design"}
 
@@ -129,7 +137,7 @@ def main():
             return
         sc, st = load_workload(args.workload)
         threads = os.cpu_count() or 1
-        cpu_spp = args.cpu_spp or 4
+        cpu_spp = args.cpu_spp or CPU_SPP.get(args.workload, 4)
         ms, mr, t = run_cpu_reference(sc, st, cpu_spp, threads, args.steps, args.warmup)
         config["triangles"] = sc.triangle_count()
         line = {"impl": "reference", "metric": "Msamples/s", "value": ms, "unit": "Msamples/s", "mrays_per_s": mr, "n_gpus": 0,
@@ -152,7 +160,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     sc, st = load_workload(args.workload)
     config["triangles"] = sc.triangle_count()
-    dr = rc.multi_gpu.DistributedRenderer(sc, rank, world, device_id=local_rank, collect_stats=_ffi.STATS_KERNEL_TIMES)
+    dr = rc.multi_gpu.DistributedRenderer(sc, rank, world, device_id=local_rank, partition=args.partition, tile_size=tile,
+                                          collect_stats=_ffi.STATS_KERNEL_TIMES)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")
 
     def sync_all():
@@ -214,25 +223,34 @@ def main():
     e2e_steps = max(1, min(args.steps, 2))
     holder = sc.to_desc()
     h2d = int(holder.vertices.nbytes + holder.tris.nbytes + holder.normals.nbytes + holder.uvs.nbytes + holder.image_bytes.nbytes)
-    def e2e_call():
-        with rc.CudaRenderer(sc, rc.multi_gpu.backend_settings_for_rank(rank, world, local_rank)) as r:
-            return r.render(st)
+    e2e_each = []
+    if world == 1:
+        def e2e_call(record):
+            t_call = time.time()
+            with rc.CudaRenderer(sc, rc.multi_gpu.backend_settings_for_rank(rank, world, local_rank)) as r:
+                t_up = time.time()
+                out = r.render(st)
+                t_rn = time.time()
+                if record:
+                    e2e_each.append({"upload_build_ms": 1e3 * (t_up - t_call), "render_d2h_ms": 1e3 * (t_rn - t_up), "device_render_ms": r.stats()["render_ms"],
+                                     "bvh_build_device_ms": r.stats()["bvh_build_ms"], "setup_ms": r.setup_ms})
+            return out
+        e2e_what = "raytracing_cuda.render(scene, settings): rtcuda_init + scene_upload (H2D, device BVH build) + render + D2H frame"
+    else:
+        def e2e_call(record):   # every rank: upload + build + its tiles into HBM planes; one NCCL reduce; rank 0: D2H of the frame
+            t_call = time.time()
+            out = rc.multi_gpu.render_distributed(sc, st, rank, world, device_id=local_rank, partition=args.partition, tile_size=tile)
+            if record:
+                e2e_each.append({"call_ms": 1e3 * (time.time() - t_call)})
+            return out
+        e2e_what = ("raytracing_cuda.multi_gpu.render_distributed(scene, settings, rank, world) on every rank: rtcuda_init + scene_upload "
+                    "(H2D, device BVH build) + render of the rank's share + NCCL sum-reduce + D2H frame on rank 0")
     if args.warmup:
-        e2e_call()   # one untimed call: the first allocation of a second set of path-state buffers pays the driver's page mapping
+        e2e_call(False)   # one untimed call: the first allocation of a second set of path-state buffers pays the driver's page mapping
     sync_all()
     e0 = time.time()
-    e2e_each = []
     for _ in range(e2e_steps):
-        t_call = time.time()
-        with rc.CudaRenderer(sc, rc.multi_gpu.backend_settings_for_rank(rank, world, local_rank)) as r:
-            t_up = time.time()
-            out = r.render(st)
-            t_rn = time.time()
-            e2e_each.append({"upload_build_ms": 1e3 * (t_up - t_call), "render_d2h_ms": 1e3 * (t_rn - t_up), "device_render_ms": r.stats()["render_ms"], "bvh_build_device_ms": r.stats()["bvh_build_ms"], "setup_ms": r.setup_ms})
-            if world > 1:   # host frames are tile-disjoint: rank 0 receives the others' tiles
-                tt = torch.from_numpy(out.beauty).to(f"cuda:{local_rank}")
-                dist.reduce(tt, dst=0)
-                out.beauty = tt.cpu().numpy()
+        e2e_call(True)
     sync_all()
     e2e_s = (time.time() - e0)
     te = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local_rank}")
@@ -272,7 +290,7 @@ def main():
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         threads = os.cpu_count() or 1
-        cpu_spp = args.cpu_spp or 4
+        cpu_spp = args.cpu_spp or CPU_SPP.get(args.workload, 4)
         ms, mr, tcpu = run_cpu_reference(sc, st, cpu_spp, threads, 1, 0)
         cpu = {"value": ms, "unit": "Msamples/s", "mrays_per_s": mr, "cores": threads, "kind": "port", "seconds": tcpu,
                "sample": f"full {W}x{H} raster at {cpu_spp} spp (of {spp}), depth {depth}, light samples {ls}"}
@@ -284,7 +302,7 @@ def main():
             "wall_s_timed_region": wall, "clocks": clocks.summary(),
             "e2e": {"value": (W * H * spp * e2e_steps) / e2e_s / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps, "breakdown": e2e_each,
-                    "what": "raytracing_cuda.render(scene, settings): rtcuda_init + scene_upload (H2D, device BVH build) + render + D2H frame"},
+                    "what": e2e_what},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
     print(json.dumps(line))
     dr.close()

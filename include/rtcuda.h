@@ -38,7 +38,7 @@ extern "C" {
 #define RTCUDA_API __attribute__((visibility("default")))
 #endif
 
-#define RTCUDA_ABI_VERSION 1u
+#define RTCUDA_ABI_VERSION 2u
 #define RTCUDA_NONE 0xffffffffu
 
 typedef enum rtcuda_status {
@@ -264,6 +264,11 @@ typedef struct rtcuda_backend_settings {
     uint32_t tile_world;              /* 0 or 1 => whole image */
     uint32_t collect_stats;           /* RTCUDA_STATS_* bits */
     uint32_t flags;                   /* RTCUDA_BACKEND_* bits */
+    /* Edge of the square tiles dealt to the ranks: 0 => 64 (the reference's RenderTile grid); a power of two in
+     * [8, 64]. Smaller tiles balance scenes whose cost is concentrated in part of the frame (C3: the box covers a
+     * quarter of the 16:9 raster) at no cost in coherence: inside a tile pixels follow a Morton curve either way. */
+    uint32_t tile_size;
+    uint32_t _reserved;
 } rtcuda_backend_settings;
 
 /* RenderOutput (crates/raytracing/src/renderer/mod.rs:49-59). NULL planes are skipped. */
@@ -330,6 +335,15 @@ RTCUDA_API rtcuda_status rtcuda_render(rtcuda_scene* scene, const rtcuda_setting
 /* Same render, but every non-NULL plane of `outputs` is a DEVICE pointer on this context's GPU
  * (used to hand the frame to an NCCL reduce without a host round trip). */
 RTCUDA_API rtcuda_status rtcuda_render_device(rtcuda_scene* scene, const rtcuda_settings* settings, rtcuda_outputs* device_outputs);
+
+/* Sample-range render (SURVEY §8e "alternate mode", and the progressive hook a viewer needs): traces samples
+ * [sample_lo, sample_hi) of every pixel this context owns, with exactly the streams `rtcuda_render` gives those sample
+ * indices at settings->samples_per_pixel, and writes the UN-NORMALISED radiance sum to the device plane `beauty_sum`
+ * (3 floats / pixel, row-major; pixels of other ranks 0). Summing the planes of disjoint ranges and multiplying by
+ * 1 / samples_per_pixel reproduces `rtcuda_render` up to the association of the float sum over samples (the render
+ * itself adds samples in index order, like render_tile, lib.rs:538-548). Beauty only: AOVs are sample-independent. */
+RTCUDA_API rtcuda_status rtcuda_render_samples_device(rtcuda_scene* scene, const rtcuda_settings* settings,
+                                                      uint32_t sample_lo, uint32_t sample_hi, float* beauty_sum);
 
 /* Replaces raytracing_cpu::render_single_pixel (lib.rs:860-931) in the Range<u32> shape of
  * raytracing_optix::render_single_pixel (crates/raytracing-optix/src/lib.rs:172-234):

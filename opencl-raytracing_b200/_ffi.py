@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 NONE = 0xFFFFFFFF
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # enums (values must match rtcuda.h)
 CAMERA_ORTHOGRAPHIC, CAMERA_PINHOLE, CAMERA_THIN_LENS = 0, 1, 2
@@ -103,7 +103,8 @@ class Settings(C.Structure):
 
 class BackendSettings(C.Structure):
     _fields_ = [("device_id", C.c_int32), ("max_paths_in_flight", C.c_uint32), ("tile_rank", C.c_uint32),
-                ("tile_world", C.c_uint32), ("collect_stats", C.c_uint32), ("flags", C.c_uint32)]
+                ("tile_world", C.c_uint32), ("collect_stats", C.c_uint32), ("flags", C.c_uint32),
+                ("tile_size", C.c_uint32), ("_reserved", C.c_uint32)]
 
 
 class Outputs(C.Structure):
@@ -137,7 +138,7 @@ ABI_STRUCTS = [Camera, Shape, Instance, Light, Material, Texture, Image, SceneDe
 
 # every symbol include/rtcuda.h declares
 EXPORTED_SYMBOLS = ["rtcuda_init", "rtcuda_shutdown", "rtcuda_scene_upload", "rtcuda_scene_release", "rtcuda_release_cached_memory", "rtcuda_render",
-                    "rtcuda_render_device", "rtcuda_render_pixel", "rtcuda_get_stats", "rtcuda_last_error",
+                    "rtcuda_render_device", "rtcuda_render_samples_device", "rtcuda_render_pixel", "rtcuda_get_stats", "rtcuda_last_error",
                     "rtcuda_abi_version", "rtcuda_abi_struct_sizes"]
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
@@ -175,6 +176,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.rtcuda_render.restype = C.c_int
     lib.rtcuda_render_device.argtypes = [C.c_void_p, C.POINTER(Settings), C.POINTER(Outputs)]
     lib.rtcuda_render_device.restype = C.c_int
+    lib.rtcuda_render_samples_device.argtypes = [C.c_void_p, C.POINTER(Settings), C.c_uint32, C.c_uint32, C.c_void_p]
+    lib.rtcuda_render_samples_device.restype = C.c_int
     lib.rtcuda_render_pixel.argtypes = [C.c_void_p, C.POINTER(Settings), C.c_uint32, C.c_uint32, C.c_uint32,
                                         C.c_uint32, C.POINTER(PixelOutput)]
     lib.rtcuda_render_pixel.restype = C.c_int

@@ -23,8 +23,9 @@ class CudaBackendSettings:
     """The analogue of CpuBackendSettings{num_threads} (lib.rs:446-457)."""
     device_id: int = 0
     max_paths_in_flight: int = 0       # 0 => backend default
-    tile_rank: int = 0                 # this context renders 64x64 tiles i with i % tile_world == tile_rank
+    tile_rank: int = 0                 # this context renders the tiles i with i % tile_world == tile_rank
     tile_world: int = 1
+    tile_size: int = 0                 # 0 => 64 (the reference's RenderTile grid); a power of two in [8, 64]
     collect_stats: int = 0             # _ffi.STATS_COUNTERS | _ffi.STATS_KERNEL_TIMES (True == counters)
     watertight: bool = False           # Woop's watertight triangle test instead of the reference's Moller-Trumbore
 
@@ -33,6 +34,7 @@ class CudaBackendSettings:
         b.device_id, b.max_paths_in_flight = self.device_id, self.max_paths_in_flight
         b.tile_rank, b.tile_world, b.collect_stats = self.tile_rank, self.tile_world, int(self.collect_stats)
         b.flags = _ffi.BACKEND_WATERTIGHT if self.watertight else 0
+        b.tile_size = self.tile_size
         return b
 
 
@@ -101,6 +103,13 @@ class CudaRenderer:
             setattr(o, k, v)
         s = settings.to_c()
         _ffi.check(self.lib, self.lib.rtcuda_render_device(self._scene, C.byref(s), C.byref(o)), "rtcuda_render_device")
+
+    def render_samples_device(self, settings: RaytracerSettings, sample_lo: int, sample_hi: int, beauty_sum_ptr: int) -> None:
+        """Samples [sample_lo, sample_hi) of this context's pixels; the un-normalised radiance sum goes to the DEVICE
+        plane at `beauty_sum_ptr` (3 floats / pixel). Sample-range partition across GPUs, progressive display."""
+        s = settings.to_c()
+        _ffi.check(self.lib, self.lib.rtcuda_render_samples_device(self._scene, C.byref(s), sample_lo, sample_hi, beauty_sum_ptr),
+                   "rtcuda_render_samples_device")
 
     def render_pixel(self, settings: RaytracerSettings, x: int, y: int, sample_lo: int, sample_hi: int) -> List[SinglePixelOutput]:
         n = max(0, sample_hi - sample_lo)

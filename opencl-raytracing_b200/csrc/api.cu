@@ -625,19 +625,21 @@ void upload_scene(rtcuda_scene* s, const rtcuda_scene_desc* d) {
 // ---------------------------------------------------------------------------------------------------
 // pixel list: the pixels this context renders, in a ray-coherent order
 // ---------------------------------------------------------------------------------------------------
-// 64x64 tiles in row-major tile order (create_render_jobs, lib.rs:481-504), tile i belongs to this context
-// iff i % tile_world == tile_rank; inside a tile pixels follow a Morton curve so that a warp covers an 8x4
-// block of the image.
+// Square tiles (64x64 unless backend_settings.tile_size says otherwise) in row-major tile order (create_render_jobs,
+// lib.rs:481-504), tile i belongs to this context iff i % tile_world == tile_rank; inside a tile pixels follow a
+// Morton curve so that a warp covers an 8x4 block of the image.
 void build_pixel_list(rtcuda_scene* s) {
-    const uint32_t W = s->width, H = s->height, TS = 64;
+    const uint32_t W = s->width, H = s->height, TS = s->ctx->bs.tile_size ? s->ctx->bs.tile_size : 64u;
+    uint32_t ts_bits = 0;
+    while ((1u << ts_bits) < TS) ts_bits++;
     const uint32_t tiles_x = (W + TS - 1) / TS, tiles_y = (H + TS - 1) / TS;
     const uint32_t world = std::max(1u, s->ctx->bs.tile_world), rank = s->ctx->bs.tile_rank;
     std::vector<uint32_t> list;
     list.reserve((size_t)W * H / world + TS * TS);
-    uint16_t mx[TS * TS], my[TS * TS];
+    std::vector<uint16_t> mx(TS * TS), my(TS * TS);
     for (uint32_t m = 0; m < TS * TS; m++) {
         uint32_t x = 0, y = 0;
-        for (uint32_t bit = 0; bit < 6; bit++) {
+        for (uint32_t bit = 0; bit < ts_bits; bit++) {
             x |= ((m >> (2 * bit)) & 1u) << bit;
             y |= ((m >> (2 * bit + 1)) & 1u) << bit;
         }
@@ -752,11 +754,17 @@ void run_batch(rtcuda_scene* s, const RenderParams& rp, Wave w, uint32_t n_paths
     }
 }
 
-void render_device(rtcuda_scene* s, const rtcuda_settings* settings, const rtcuda_outputs* out) {
+// sample_hi == 0: the whole frame (all samples, mean). Otherwise samples [sample_lo, sample_hi) only and the beauty plane
+// receives their un-normalised sum (rtcuda_render_samples_device).
+void render_device(rtcuda_scene* s, const rtcuda_settings* settings, const rtcuda_outputs* out, uint32_t sample_lo = 0, uint32_t sample_hi = 0) {
     cudaStream_t st = s->ctx->stream;
     REQUIRE(out->width == s->width && out->height == s->height, "output size must equal the camera raster size");
     REQUIRE(settings->samples_per_pixel >= 1, "samples_per_pixel must be >= 1");
     if (settings->sampler_kind == RTCUDA_SAMPLER_STRATIFIED) REQUIRE(settings->x_strata >= 1 && settings->y_strata >= 1, "strata must be >= 1");
+    const bool sum_mode = sample_hi != 0;
+    if (sum_mode) REQUIRE(sample_lo < sample_hi && sample_hi <= settings->samples_per_pixel, "sample range must satisfy lo < hi <= samples_per_pixel");
+    else sample_hi = settings->samples_per_pixel;
+    const uint32_t n_samples_total = sample_hi - sample_lo;
     const RenderParams rp = make_params(settings);
     const bool collect = (s->ctx->bs.collect_stats & RTCUDA_STATS_COUNTERS) != 0;
     s->spans.clear();
@@ -814,7 +822,7 @@ void render_device(rtcuda_scene* s, const rtcuda_settings* settings, const rtcud
             }
             capacity = std::max(capacity, 1024u);
             const uint32_t np_batch = std::min(np_all, capacity);
-            const uint32_t ns_batch = std::max(1u, std::min(settings->samples_per_pixel, capacity / np_batch));
+            const uint32_t ns_batch = std::max(1u, std::min(n_samples_total, capacity / np_batch));
             ensure_wave(s, np_batch * ns_batch, shadow_k, rp.max_ray_depth);
             s->accum.ensure(np_all);
             CK(cudaMemsetAsync(s->accum.p, 0, (size_t)np_all * sizeof(float4), st));
@@ -827,15 +835,15 @@ void render_device(rtcuda_scene* s, const rtcuda_settings* settings, const rtcud
             w.sray_o = s->sray_o.p; w.sray_d = s->sray_d.p; w.scontrib = s->scontrib.p;
             for (uint32_t p0 = 0; p0 < np_all; p0 += np_batch) {
                 const uint32_t np = std::min(np_batch, np_all - p0);
-                for (uint32_t s0 = 0; s0 < settings->samples_per_pixel; s0 += ns_batch) {
-                    const uint32_t ns = std::min(ns_batch, settings->samples_per_pixel - s0);
+                for (uint32_t s0 = sample_lo; s0 < sample_hi; s0 += ns_batch) {
+                    const uint32_t ns = std::min(ns_batch, sample_hi - s0);
                     w.pixel_base = p0; w.n_pixels = np; w.sample_base = s0; w.n_samples = ns;
                     run_batch(s, rp, w, np * ns, collect);
                     launch_resolve(st, w, s->accum.p, s->lc);
                     samples += (uint64_t)np * ns;
                 }
             }
-            launch_finalize(st, s->pixel_list.p, np_all, s->width, s->accum.p, 1.0f / (float)settings->samples_per_pixel, out->beauty, s->lc);
+            launch_finalize(st, s->pixel_list.p, np_all, s->width, s->accum.p, sum_mode ? 1.0f : 1.0f / (float)settings->samples_per_pixel, out->beauty, s->lc);
         }
     }
     CK(cudaEventRecord(e1, st));
@@ -968,6 +976,8 @@ RTCUDA_API rtcuda_status rtcuda_init(const rtcuda_backend_settings* settings, rt
         if (e != cudaSuccess || count == 0) throw RtError{RTCUDA_ERR_NO_DEVICE, "no CUDA device: the cuda backend has no CPU fallback"};
         REQUIRE(settings->device_id >= 0 && settings->device_id < count, "device_id out of range");
         REQUIRE(settings->tile_world <= 1 || settings->tile_rank < settings->tile_world, "tile_rank >= tile_world");
+        REQUIRE(settings->tile_size == 0 || (settings->tile_size >= 8 && settings->tile_size <= 64 && (settings->tile_size & (settings->tile_size - 1)) == 0),
+                "tile_size must be 0 or a power of two in [8, 64]");
         auto ctx = std::make_unique<rtcuda_ctx>();
         ctx->device = settings->device_id;
         ctx->bs = *settings;
@@ -1035,6 +1045,22 @@ RTCUDA_API rtcuda_status rtcuda_render_device(rtcuda_scene* scene, const rtcuda_
         CK(cudaSetDevice(scene->ctx->device));
         tls_stream = scene->ctx->stream;
         render_device(scene, settings, device_outputs);
+    });
+}
+
+RTCUDA_API rtcuda_status rtcuda_render_samples_device(rtcuda_scene* scene, const rtcuda_settings* settings, uint32_t sample_lo,
+                                                      uint32_t sample_hi, float* beauty_sum) {
+    return guarded([&] {
+        REQUIRE(scene && settings && beauty_sum, "null argument");
+        REQUIRE(sample_hi != 0, "empty sample range");
+        CK(cudaSetDevice(scene->ctx->device));
+        tls_stream = scene->ctx->stream;
+        rtcuda_settings st = *settings;
+        st.outputs = RTCUDA_AOV_BEAUTY;
+        rtcuda_outputs o{};
+        o.width = scene->width; o.height = scene->height;
+        o.beauty = beauty_sum;
+        render_device(scene, &st, &o, sample_lo, sample_hi);
     });
 }
 

@@ -30,7 +30,7 @@ def gpu_render(rc, scene, settings, **backend):
 def test_extension_is_loaded(rc):
     import ctypes
     lib = rc._ffi.load_library()
-    assert isinstance(lib, ctypes.CDLL) and lib.rtcuda_abi_version() == 1
+    assert isinstance(lib, ctypes.CDLL) and lib.rtcuda_abi_version() == rc._ffi.ABI_VERSION
 
 
 def test_c1_sphere(rc, oracle):
@@ -219,6 +219,47 @@ def test_tile_partition_is_exact(rc):
         assert (p.beauty[owner != r] == 0).all()
     for plane in ("beauty", "normals", "uv"):
         assert np.array_equal(sum(getattr(p, plane) for p in parts), getattr(full, plane))
+
+
+def test_tile_size_partition_is_exact(rc):
+    """finer deal of the frame (backend_settings.tile_size = 16): same pixels, still a bit-exact gather"""
+    sc = load_scene("cb", 200, 136)
+    st = rc.RaytracerSettings(outputs=A.BEAUTY | A.NORMALS, samples_per_pixel=4, light_sample_count=1)
+    full, _ = gpu_render(rc, sc, st)
+    whole16, _ = gpu_render(rc, sc, st, tile_size=16)
+    assert np.array_equal(whole16.beauty, full.beauty)          # the tile grid only orders the work
+    parts = [gpu_render(rc, sc, st, tile_rank=r, tile_world=4, tile_size=16)[0] for r in range(4)]
+    owner = rc.multi_gpu.tile_owner_map(200, 136, 4, tile=16)
+    for r, p in enumerate(parts):
+        assert (p.beauty[owner != r] == 0).all() and (p.beauty[owner == r] != 0).any()
+    for plane in ("beauty", "normals"):
+        assert np.array_equal(sum(getattr(p, plane) for p in parts), getattr(full, plane))
+    with pytest.raises(rc._ffi.RtCudaError):
+        gpu_render(rc, sc, st, tile_size=24)
+
+
+def test_sample_range_render(rc):
+    """rtcuda_render_samples_device: the sums of disjoint sample ranges add up to the frame (same streams per sample
+    index; only the association of the float sum differs), and the full range reproduces it bit for bit"""
+    import torch
+    sc = load_scene("cb", 96, 64)
+    st = rc.RaytracerSettings(samples_per_pixel=12, light_sample_count=2)
+    with rc.CudaRenderer(sc) as r:
+        full = r.render(st).beauty
+        plane = torch.zeros((64, 96, 3), dtype=torch.float32, device="cuda:0")
+        r.render_samples_device(st, 0, 12, plane.data_ptr())
+        torch.cuda.synchronize()
+        inv = torch.tensor(1.0 / 12, dtype=torch.float32)
+        assert np.array_equal((plane.cpu() * inv).numpy(), full)
+        acc = torch.zeros_like(plane)
+        for lo, hi in ((0, 5), (5, 6), (6, 12)):
+            r.render_samples_device(st, lo, hi, plane.data_ptr())
+            torch.cuda.synchronize()
+            acc += plane
+        np.testing.assert_allclose((acc.cpu() * inv).numpy(), full, rtol=2e-6, atol=1e-7)
+        assert r.stats()["samples"] == 96 * 64 * 6
+        with pytest.raises(rc._ffi.RtCudaError):
+            r.render_samples_device(st, 4, 13, plane.data_ptr())
 
 
 def test_full_size_c2_properties(rc):

@@ -156,3 +156,16 @@ def test_cli_argument_surface(rc, capsys):
     p = cli.build_parser().parse_args(["--scene-name", "cube", "pixel", "10", "20", "3", "1"])
     assert (p.x, p.y, p.sample_count, p.sample_offset) == (10, 20, 3, 1)
     assert cli.main([]) == 1 and cli.main(["--scene-name", "cube", "-t", "4", "full"]) == 1
+
+
+def test_partition_helpers():
+    """multi-GPU host logic: every pixel has one owner at any tile size; sample ranges tile [0, spp) without gaps"""
+    import raytracing_cuda as rc
+    for tile in (64, 16, 8):
+        own = rc.multi_gpu.tile_owner_map(200, 136, 3, tile=tile)
+        assert own.shape == (136, 200) and set(np.unique(own)) == {0, 1, 2}
+        assert (own[:tile, :tile] == 0).all() and own[0, tile] == 1
+    for spp, world in ((256, 8), (5, 8), (7, 2), (1, 1)):
+        rs = [rc.multi_gpu.sample_range_for_rank(spp, r, world) for r in range(world)]
+        assert rs[0][0] == 0 and rs[-1][1] == spp and all(a[1] == b[0] for a, b in zip(rs, rs[1:]))
+        assert max(h - l for l, h in rs) - min(h - l for l, h in rs) <= 1

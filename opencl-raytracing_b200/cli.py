@@ -24,6 +24,7 @@ import numpy as np
 from .renderer import AovFlags, RaytracerSettings, Sampler
 from .backend import CudaBackendSettings, CudaRenderer
 from .scene import scene_from_gltf_file
+from .pbrt import scene_from_pbrt_file
 from . import exr, test_scenes
 
 
@@ -114,12 +115,12 @@ def main(argv=None) -> int:
     settings = RaytracerSettings()
     if args.scene_path:
         ext = os.path.splitext(args.scene_path)[1].lower()
-        if ext == ".pbrt":
-            print("error: the PBRT importer is outside this backend's scope (SURVEY 8f row 3)", file=sys.stderr)
-            return 1
-        if ext not in (".gltf", ".glb"):
-            print(f"warning: unrecognized file extension {ext!r}, trying to import as gltf", file=sys.stderr)
-        scene = scene_from_gltf_file(args.scene_path)
+        if ext == ".pbrt":   # crates/cli/src/main.rs:146-157: dispatch on the extension
+            scene = scene_from_pbrt_file(args.scene_path)
+        else:
+            if ext not in (".gltf", ".glb"):
+                print(f"warning: unrecognized file extension {ext!r}, trying to import as gltf", file=sys.stderr)
+            scene = scene_from_gltf_file(args.scene_path)
     else:
         found = [t for t in test_scenes.all_test_scenes() if t.name == args.scene_name]
         if not found:

@@ -309,6 +309,9 @@ typedef struct rtcuda_stats {
     double upload_ms;
     double extend_ms, shade_ms, shadow_ms, other_ms;   /* RTCUDA_STATS_KERNEL_TIMES */
     uint64_t bvh_node_count, bvh_prim_count;
+    /* NaN / Inf channels of the beauty plane of the last render: the device side of the reference's scan
+     * (lib.rs:813-854); the binding prints its warnings ("R component of (x, y) is NaN", first 10) when non-zero. */
+    uint64_t nonfinite_values;
 } rtcuda_stats;
 
 typedef struct rtcuda_ctx rtcuda_ctx;

@@ -7,6 +7,7 @@ library is missing `_ffi.load_library()` raises.
 from __future__ import annotations
 
 import ctypes as C
+import sys
 import time
 from dataclasses import dataclass
 from typing import List, Optional
@@ -36,6 +37,20 @@ class CudaBackendSettings:
         b.flags = _ffi.BACKEND_WATERTIGHT if self.watertight else 0
         b.tile_size = self.tile_size
         return b
+
+
+def warn_nonfinite(beauty: np.ndarray, log=None) -> int:
+    """The tail of raytracing_cpu::render (lib.rs:813-854): every channel of the beauty plane is classified, the first 10
+    NaN / infinite ones are reported in raster order, then the total. The count comes from the device (k_finalize); this
+    only runs when it is non-zero. Returns the number of warnings."""
+    log = log or (lambda m: print("warning: " + m, file=sys.stderr))
+    bad = np.argwhere(~np.isfinite(beauty))          # row-major: (j, i, channel) in the reference's loop order
+    for j, i, c in bad[:10]:
+        kind = "NaN" if np.isnan(beauty[j, i, c]) else "infty"
+        log(f"{'RGB'[c]} component of ({i}, {j}) is {kind}")
+    if len(bad):
+        log(f"encountered {len(bad)} NaN and infty values in radiance buffer")
+    return len(bad)
 
 
 class CudaRenderer:
@@ -87,13 +102,17 @@ class CudaRenderer:
     def render(self, settings: RaytracerSettings) -> RenderOutput:
         """raytracing_cpu::render: host planes, row-major [H,W,C]."""
         out = RenderOutput.allocate(self.width, self.height, AovFlags(settings.outputs))
-        s, o = settings.to_c(), out.to_c()
-        _ffi.check(self.lib, self.lib.rtcuda_render(self._scene, C.byref(s), C.byref(o)), "rtcuda_render")
+        self.render_into(settings, out)
         return out
 
     def render_into(self, settings: RaytracerSettings, out: RenderOutput) -> None:
         s, o = settings.to_c(), out.to_c()
         _ffi.check(self.lib, self.lib.rtcuda_render(self._scene, C.byref(s), C.byref(o)), "rtcuda_render")
+        if out.beauty is not None:
+            st = _ffi.Stats()
+            self.lib.rtcuda_get_stats(self._scene, C.byref(st))
+            if st.nonfinite_values:
+                warn_nonfinite(out.beauty)
 
     def render_device(self, settings: RaytracerSettings, planes: dict) -> None:
         """Same render with DEVICE plane pointers ({'beauty': ptr, ...}); nothing is copied to the host."""

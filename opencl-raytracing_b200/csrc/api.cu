@@ -843,7 +843,7 @@ void render_device(rtcuda_scene* s, const rtcuda_settings* settings, const rtcud
                     samples += (uint64_t)np * ns;
                 }
             }
-            launch_finalize(st, s->pixel_list.p, np_all, s->width, s->accum.p, sum_mode ? 1.0f : 1.0f / (float)settings->samples_per_pixel, out->beauty, s->lc);
+            launch_finalize(st, s->pixel_list.p, np_all, s->width, s->accum.p, sum_mode ? 1.0f : 1.0f / (float)settings->samples_per_pixel, out->beauty, s->stats_dev.p, s->lc);
         }
     }
     CK(cudaEventRecord(e1, st));
@@ -865,6 +865,7 @@ void render_device(rtcuda_scene* s, const rtcuda_settings* settings, const rtcud
     s->stats.nodes_fetched = h_stats[STAT_EXT_NODES] + h_stats[STAT_SH_NODES] + h_stats[STAT_AOV_NODES];
     s->stats.prims_fetched = h_stats[STAT_EXT_PRIMS] + h_stats[STAT_SH_PRIMS] + h_stats[STAT_AOV_PRIMS];
     s->stats.shaded_vertices = h_stats[STAT_SHADED];
+    s->stats.nonfinite_values = h_stats[STAT_NONFINITE];
     s->stats.kernel_launches = s->lc.launches - launches0;
     s->stats.render_ms = ms;
     double cls_ms[CLS_COUNT] = {0, 0, 0, 0};

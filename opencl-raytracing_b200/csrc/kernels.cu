@@ -233,16 +233,23 @@ __global__ void __launch_bounds__(BLOCK) k_resolve(const __grid_constant__ Wave 
     if (i < w.n_pixels) resolve_body(i, w, accum);
 }
 
+// Pixel mean + the NaN / Inf scan of the beauty plane (lib.rs:813-854: every channel is classified): the count of
+// non-finite channels goes to the stats block; the caller side prints the reference's warnings from it.
 __global__ void __launch_bounds__(BLOCK) k_finalize(const uint32_t* pixel_list, uint32_t n, uint32_t width, const float4* accum,
-                                                     float inv_spp, float* beauty) {
+                                                     float inv_spp, float* beauty, unsigned long long* stats) {
     const uint32_t i = blockIdx.x * BLOCK + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t packed = pixel_list[i];
-    const size_t idx = (size_t)(packed >> 16) * width + (packed & 0xffffu);
-    const float4 a = accum[i];
-    beauty[3 * idx] = a.x * inv_spp;  // `radiance /= spp` is a multiply by the reciprocal (vec3.rs:122-126)
-    beauty[3 * idx + 1] = a.y * inv_spp;
-    beauty[3 * idx + 2] = a.z * inv_spp;
+    uint32_t bad = 0;
+    if (i < n) {
+        const uint32_t packed = pixel_list[i];
+        const size_t idx = (size_t)(packed >> 16) * width + (packed & 0xffffu);
+        const float4 a = accum[i];
+        const float r = a.x * inv_spp, g = a.y * inv_spp, b = a.z * inv_spp;  // `radiance /= spp` is a multiply by the reciprocal (vec3.rs:122-126)
+        beauty[3 * idx] = r;
+        beauty[3 * idx + 1] = g;
+        beauty[3 * idx + 2] = b;
+        bad = (isfinite(r) ? 0u : 1u) + (isfinite(g) ? 0u : 1u) + (isfinite(b) ? 0u : 1u);
+    }
+    if (__any_sync(0xffffffffu, bad != 0u)) warp_add_stat(&stats[STAT_NONFINITE], bad);
 }
 
 void launch_raygen(cudaStream_t st, const SceneD& sc, const RenderParams& rp, const Wave& w, uint32_t n, LaunchCounter& lc) {
@@ -283,8 +290,8 @@ void launch_resolve(cudaStream_t st, const Wave& w, float4* accum, LaunchCounter
     lc.launches++;
 }
 void launch_finalize(cudaStream_t st, const uint32_t* pixel_list, uint32_t n_pixels, uint32_t width, const float4* accum, float inv_spp,
-                     float* beauty, LaunchCounter& lc) {
-    k_finalize<<<grid_for(n_pixels), BLOCK, 0, st>>>(pixel_list, n_pixels, width, accum, inv_spp, beauty);
+                     float* beauty, unsigned long long* stats, LaunchCounter& lc) {
+    k_finalize<<<grid_for(n_pixels), BLOCK, 0, st>>>(pixel_list, n_pixels, width, accum, inv_spp, beauty, stats);
     lc.launches++;
 }
 

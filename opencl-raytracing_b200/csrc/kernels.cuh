@@ -15,7 +15,7 @@ void launch_shade(cudaStream_t st, const SceneD& sc, const RenderParams& rp, con
 void launch_shadow(cudaStream_t st, const SceneD& sc, const Wave& w, uint32_t n_max, uint32_t* fetch_counter, bool stats, LaunchCounter& lc);
 void launch_resolve(cudaStream_t st, const Wave& w, float4* accum, LaunchCounter& lc);
 void launch_finalize(cudaStream_t st, const uint32_t* pixel_list, uint32_t n_pixels, uint32_t width, const float4* accum,
-                     float inv_spp, float* beauty, LaunchCounter& lc);
+                     float inv_spp, float* beauty, unsigned long long* stats, LaunchCounter& lc);
 void launch_aov(cudaStream_t st, const SceneD& sc, const RenderParams& rp, const uint32_t* pixel_list, uint32_t n_pixels,
                 const AovPlanes& planes, unsigned long long* stats, bool collect, LaunchCounter& lc);
 // single-pixel diagnostics (render_single_pixel): one thread per sample index

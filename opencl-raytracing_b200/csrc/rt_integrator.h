@@ -59,7 +59,7 @@ struct Wave {
 };
 
 enum { STAT_PRIMARY = 0, STAT_BOUNCE = 1, STAT_SHADOW = 2, STAT_AOV = 3, STAT_EXT_NODES = 4, STAT_EXT_PRIMS = 5, STAT_SH_NODES = 6,
-       STAT_SH_PRIMS = 7, STAT_AOV_NODES = 8, STAT_AOV_PRIMS = 9, STAT_SHADED = 10, STAT_TOTAL = 12 };
+       STAT_SH_PRIMS = 7, STAT_AOV_NODES = 8, STAT_AOV_PRIMS = 9, STAT_SHADED = 10, STAT_NONFINITE = 11, STAT_TOTAL = 12 };
 
 struct Ray { V3 o, d; };
 

@@ -24,7 +24,10 @@ def dbg():
 def gpu_render(rc, scene, settings, **backend):
     with rc.CudaRenderer(scene, rc.CudaBackendSettings(**backend)) as r:
         out = r.render(settings)
-        return out, r.stats()
+        stats = r.stats()
+        if out.beauty is not None:   # the device side of the reference's NaN / Inf scan (lib.rs:813-854)
+            assert stats["nonfinite_values"] == int((~np.isfinite(out.beauty)).sum())
+        return out, stats
 
 
 def test_extension_is_loaded(rc):

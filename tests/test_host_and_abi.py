@@ -169,3 +169,18 @@ def test_partition_helpers():
         rs = [rc.multi_gpu.sample_range_for_rank(spp, r, world) for r in range(world)]
         assert rs[0][0] == 0 and rs[-1][1] == spp and all(a[1] == b[0] for a, b in zip(rs, rs[1:]))
         assert max(h - l for l, h in rs) - min(h - l for l, h in rs) <= 1
+
+
+def test_nonfinite_warnings_follow_the_reference():
+    """lib.rs:813-854: raster order, channel names, 'NaN' / 'infty', first 10 then the total"""
+    from raytracing_cuda.backend import warn_nonfinite
+    img = np.zeros((4, 5, 3), dtype=np.float32)
+    assert warn_nonfinite(img, log=lambda m: None) == 0
+    img[0, 3, 1] = np.nan
+    img[2, 1, 0] = np.inf
+    img[2, 1, 2] = -np.inf
+    img[3, :, :] = np.nan
+    msgs = []
+    assert warn_nonfinite(img, log=msgs.append) == 18
+    assert msgs[0] == "G component of (3, 0) is NaN" and msgs[1] == "R component of (1, 2) is infty" and msgs[2] == "B component of (1, 2) is infty"
+    assert len(msgs) == 11 and msgs[-1] == "encountered 18 NaN and infty values in radiance buffer"

@@ -18,6 +18,11 @@ constexpr int BLOCK = 256;
 #ifndef SHADE_BLOCKS
 #define SHADE_BLOCKS 3
 #endif
+// queue positions handed out per warp (two atomics per warp with output) instead of per block (one scan + two barriers per
+// chunk): shade 114 -> 110 ms on C3, 10.9 -> 10.0 ms on C5s (A/B: profiles/r1o_ab.log)
+#ifndef SHADE_WARP_ALLOC
+#define SHADE_WARP_ALLOC 1
+#endif
 static inline uint32_t grid_for(uint32_t n, int block = BLOCK) { return n ? (n + block - 1) / block : 1; }
 
 // ---------------------------------------------------------------------------------------------------
@@ -128,16 +133,19 @@ __global__ void __launch_bounds__(BLOCK) k_extend(const __grid_constant__ SceneD
 
 // Shading: persistent blocks walk the ray queue in block-sized chunks (the live queue length is only known on the
 // device; a grid sized for the whole batch spent a third of its warp time in blocks that found nothing to do,
-// profiles/r1_notes.md). Per chunk ONE block-wide scan hands out the positions of all three outputs — continuation
-// rays, NEE vertices, shadow rays (a variable number per thread, consecutive per vertex) — and two threads issue
-// the block's global atomics (one per queue counter).
+// profiles/r1_notes.md). Per chunk ONE warp scan hands out the positions of all three outputs — continuation
+// rays, NEE vertices, shadow rays (a variable number per thread, consecutive per vertex) — and the last lane issues
+// the warp's two global atomics (one per queue counter; the 64-bit one carries vertices | shadow rays << 32).
 template <typename Surf>
 __global__ void __launch_bounds__(BLOCK, std::is_same<Surf, DiffuseSurface>::value ? SHADE_BLOCKS : 2) k_shade(const __grid_constant__ SceneD sc, const __grid_constant__ RenderParams rp,
                                                   const __grid_constant__ Wave w) {
+#if !SHADE_WARP_ALLOC
     __shared__ unsigned long long s_warp[BLOCK / 32][2];   // per warp: [0] continuation rays, [1] vertices | shadow rays << 32
     __shared__ unsigned long long s_base[2];
+    const unsigned warp = threadIdx.x >> 5;
+#endif
     const uint32_t n = *w.n_in;
-    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const unsigned lane = threadIdx.x & 31u;
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&w.stats[STAT_SHADED], (unsigned long long)n);
     for (uint32_t base = blockIdx.x * BLOCK; base < n; base += gridDim.x * BLOCK) {
         const uint32_t q = base + threadIdx.x;
@@ -150,6 +158,23 @@ __global__ void __launch_bounds__(BLOCK, std::is_same<Surf, DiffuseSurface>::val
                 const uint32_t up = __shfl_up_sync(FULL, incl, o);
                 if ((int)lane >= o) incl += up;
             }
+#if SHADE_WARP_ALLOC
+            // per-warp allocation: two atomics per warp that has output, no block barrier (the warps of a block drift apart
+            // on their dependent loads; a barrier per chunk made all of them wait for the slowest)
+            unsigned long long base0 = 0, base1 = 0;
+            if (lane == 31) {
+                const uint32_t n0 = (uint32_t)__popc(mc);
+                const unsigned long long n1 = (unsigned long long)__popc(mv) | ((unsigned long long)incl << 32);
+                if (n0) base0 = (unsigned long long)atomicAdd(w.n_out, n0);
+                if (n1) base1 = atomicAdd(w.n_shadow, n1);
+            }
+            base0 = __shfl_sync(FULL, base0, 31);
+            base1 = __shfl_sync(FULL, base1, 31);
+            const unsigned lt = (1u << lane) - 1u;
+            const unsigned long long b1 = base1;
+            rpos = (uint32_t)base0 + (uint32_t)__popc(mc & lt);
+            vpos = (uint32_t)b1 + (uint32_t)__popc(mv & lt);
+#else
             if (lane == 31) {
                 s_warp[warp][0] = (unsigned long long)__popc(mc);
                 s_warp[warp][1] = (unsigned long long)__popc(mv) | ((unsigned long long)incl << 32);
@@ -169,6 +194,7 @@ __global__ void __launch_bounds__(BLOCK, std::is_same<Surf, DiffuseSurface>::val
             const unsigned long long b1 = s_base[1] + before1;
             rpos = (uint32_t)(s_base[0] + before0) + (uint32_t)__popc(mc & lt);
             vpos = (uint32_t)b1 + (uint32_t)__popc(mv & lt);
+#endif
             first = (uint32_t)(b1 >> 32) + (incl - k);
         });
     }

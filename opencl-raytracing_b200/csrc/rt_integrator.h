@@ -419,7 +419,10 @@ RT_HD bool shade_begin(uint32_t q, const SceneD& sc, const RenderParams& rp, con
 // lib.rs:324-356: every light, every sample; entries with a non-zero unoccluded contribution become shadow rays.
 // MODE 0 counts them, MODE 1 stages up to NEE_STAGE of them in thread-local memory (and counts), MODE 2 writes them
 // (at most `limit`) to the shadow-ray queue starting at `first`. All modes draw the same numbers from `s`.
-constexpr uint32_t NEE_STAGE = 8;
+#ifndef RT_NEE_STAGE
+#define RT_NEE_STAGE 8
+#endif
+constexpr uint32_t NEE_STAGE = RT_NEE_STAGE;
 struct NeeStage { float4 o[NEE_STAGE], d[NEE_STAGE], c[NEE_STAGE]; };
 
 template <int MODE, typename Surf>

@@ -226,7 +226,7 @@ def main():
     for _ in range(args.warmup):
         one_step()
     clocks = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("BENCH_NO_CLOCKS"):   # (diagnostic switch: A/B of the sampler's own footprint)
         clocks.start()
     sync_all()
     total_ms, agg = 0.0, {}

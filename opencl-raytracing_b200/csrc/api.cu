@@ -122,6 +122,12 @@ struct ArenaCache {
         std::lock_guard<std::mutex> g(mu);
         parked.push_back({device, p, bytes});
     }
+    size_t largest(int device) {
+        std::lock_guard<std::mutex> g(mu);
+        size_t b = 0;
+        for (const Slot& sl : parked) if (sl.device == device) b = std::max(b, sl.bytes);
+        return b;
+    }
     size_t parked_bytes(int device) {
         std::lock_guard<std::mutex> g(mu);
         size_t b = 0;
@@ -218,7 +224,16 @@ struct rtcuda_scene {
     struct Span { int cls; size_t e0, e1; };
     std::vector<Span> spans;
     size_t ev_used = 0;
+    // The beauty pass of a frame (every batch: raygen, extend / shade / shadow per depth, resolve; then finalize) captured as a
+    // CUDA graph and replayed while the frame's key (settings, buffers, partition) stays the same: the ~330 launches of a C3
+    // frame then reach the GPU in one submission, so a host thread that loses its core for tens of ms (shared box) no longer
+    // leaves the GPU idle between kernels (5-40 ms gaps per 360 ms frame, profiles/r1s_gap.log).
+    cudaGraphExec_t frame_exec = nullptr;
+    std::vector<uint64_t> frame_key;
+    unsigned long long frame_launches = 0;
+    bool capturing = false;
     ~rtcuda_scene() {
+        if (frame_exec) cudaGraphExecDestroy(frame_exec);
         for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
     }
 };
@@ -681,6 +696,12 @@ uint32_t shadow_entries_per_vertex(const rtcuda_scene* s, const RenderParams& rp
     return (uint32_t)k;
 }
 
+// Bytes of path state for `cap` slots (every buffer ensure_wave carves, plus alignment slack).
+size_t arena_bytes(size_t cap, uint32_t shadow_k, uint32_t max_depth) {
+    const size_t k = std::max(1u, shadow_k), n_counters = 4 * ((size_t)max_depth + 3);
+    return cap * (16 + 16 * 7 + 16) + cap * k * 48 + n_counters * 4 + ((size_t)max_depth + 3) * 8 + 16 * 256;
+}
+
 // Allocate the wavefront state for `capacity` path slots.
 void ensure_wave(rtcuda_scene* s, uint32_t capacity, uint32_t shadow_k, uint32_t max_depth) {
     s->stats_dev.ensure(STAT_TOTAL);
@@ -688,7 +709,7 @@ void ensure_wave(rtcuda_scene* s, uint32_t capacity, uint32_t shadow_k, uint32_t
     if (s->arena.base && capacity <= s->arena_capacity && k <= s->arena_shadow_k && max_depth <= s->arena_depth) return;
     const size_t cap = capacity;
     REQUIRE((uint64_t)cap * k < (1ull << 32), "paths in flight x light samples per vertex must stay below 2^32");
-    const size_t need = cap * (16 + 16 * 7 + 16) + cap * k * 48 + n_counters * 4 + ((size_t)max_depth + 3) * 8 + 16 * 256;
+    const size_t need = arena_bytes(cap, shadow_k, max_depth);
     s->arena.reserve(s->ctx->device, need);
     auto view = [&](auto& v, size_t count) { v.p = s->arena.carve<std::remove_pointer_t<decltype(v.p)>>(count); v.n = count; };
     view(s->state, cap);
@@ -706,13 +727,22 @@ void ensure_wave(rtcuda_scene* s, uint32_t capacity, uint32_t shadow_k, uint32_t
 
 enum { CLS_EXTEND = 0, CLS_SHADE = 1, CLS_SHADOW = 2, CLS_OTHER = 3, CLS_COUNT = 4 };
 
+// The event pool and the span list are shared by direct launches and by the captured frame (whose event-record nodes keep
+// pointing at the pool's events): starting a new span list outside a capture drops the cached frame graph.
+void reset_spans(rtcuda_scene* s, bool drop_frame_graph = true) {
+    s->spans.clear();
+    s->ev_used = 0;
+    if (drop_frame_graph && s->frame_exec) { cudaGraphExecDestroy(s->frame_exec); s->frame_exec = nullptr; }
+}
+
 size_t record_event(rtcuda_scene* s) {
     if (s->ev_used == s->ev_pool.size()) {
         cudaEvent_t e;
         CK(cudaEventCreate(&e));
         s->ev_pool.push_back(e);
     }
-    CK(cudaEventRecord(s->ev_pool[s->ev_used], s->ctx->stream));
+    // inside a capture the record becomes an event-record node of the frame graph (external event: it can be timed after a replay)
+    CK(cudaEventRecordWithFlags(s->ev_pool[s->ev_used], s->ctx->stream, s->capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
     return s->ev_used++;
 }
 struct SpanGuard {  // times one launch when kernel timing is on
@@ -767,8 +797,6 @@ void render_device(rtcuda_scene* s, const rtcuda_settings* settings, const rtcud
     const uint32_t n_samples_total = sample_hi - sample_lo;
     const RenderParams rp = make_params(settings);
     const bool collect = (s->ctx->bs.collect_stats & RTCUDA_STATS_COUNTERS) != 0;
-    s->spans.clear();
-    s->ev_used = 0;
     if (!s->pixel_list.p) build_pixel_list(s);
     const uint32_t np_all = s->n_my_pixels;
     const size_t npix_img = (size_t)s->width * s->height;
@@ -781,6 +809,7 @@ void render_device(rtcuda_scene* s, const rtcuda_settings* settings, const rtcud
     CK(cudaEventRecord(e0, st));
 
     const uint32_t o = settings->outputs;
+    if (!((o & RTCUDA_AOV_BEAUTY) && out->beauty && s->n_my_pixels)) reset_spans(s);   // no beauty pass: no kernel spans
     AovPlanes pl{};
     pl.normals = (o & RTCUDA_AOV_NORMALS) ? out->normals : nullptr;
     pl.albedo = (o & RTCUDA_AOV_ALBEDO) ? out->albedo : nullptr;
@@ -814,6 +843,15 @@ void render_device(rtcuda_scene* s, const rtcuda_settings* settings, const rtcud
             if (!capacity)
                 if (const char* env = std::getenv("RTCUDA_MAX_PATHS")) capacity = (uint32_t)std::strtoul(env, nullptr, 0);  // tuning aid
             if (!capacity) {
+                // Memory already held for path state (this scene's arena, or one parked by a released scene) that fits the
+                // wavefront this job wants settles the size without asking the driver: cudaMemGetInfo is a trip into the
+                // kernel driver (it queues behind NVML queries of a monitoring thread and other processes' calls) and sat
+                // inside the render window with the GPU idle — 5-35 ms per frame on a busy box (profiles/r1s_gap.log).
+                const size_t want = std::min<size_t>(1u << 26, std::max<size_t>(1024, (size_t)np_all * n_samples_total));
+                const size_t held = std::max(s->arena.base ? s->arena.bytes : 0, g_arena_cache.largest(s->ctx->device));
+                if (held >= arena_bytes(want, shadow_k, rp.max_ray_depth)) capacity = (uint32_t)want;
+            }
+            if (!capacity) {
                 const size_t bytes_per_slot = 16 + 16 * 7 + 16 + 48 * (size_t)std::max(1u, shadow_k);
                 size_t free_b = 0, total_b = 0;
                 CK(cudaMemGetInfo(&free_b, &total_b));
@@ -825,7 +863,6 @@ void render_device(rtcuda_scene* s, const rtcuda_settings* settings, const rtcud
             const uint32_t ns_batch = std::max(1u, std::min(n_samples_total, capacity / np_batch));
             ensure_wave(s, np_batch * ns_batch, shadow_k, rp.max_ray_depth);
             s->accum.ensure(np_all);
-            CK(cudaMemsetAsync(s->accum.p, 0, (size_t)np_all * sizeof(float4), st));
             Wave w{};
             w.pixel_list = s->pixel_list.p;
             w.capacity = np_batch * ns_batch;
@@ -833,17 +870,59 @@ void render_device(rtcuda_scene* s, const rtcuda_settings* settings, const rtcud
             w.stats = s->stats_dev.p;
             w.shadow_k = shadow_k; w.svertex = s->svertex.p;
             w.sray_o = s->sray_o.p; w.sray_d = s->sray_d.p; w.scontrib = s->scontrib.p;
-            for (uint32_t p0 = 0; p0 < np_all; p0 += np_batch) {
-                const uint32_t np = std::min(np_batch, np_all - p0);
-                for (uint32_t s0 = sample_lo; s0 < sample_hi; s0 += ns_batch) {
-                    const uint32_t ns = std::min(ns_batch, sample_hi - s0);
-                    w.pixel_base = p0; w.n_pixels = np; w.sample_base = s0; w.n_samples = ns;
-                    run_batch(s, rp, w, np * ns, collect);
-                    launch_resolve(st, w, s->accum.p, s->lc);
-                    samples += (uint64_t)np * ns;
+            samples = (uint64_t)np_all * n_samples_total;
+            auto enqueue_frame = [&] {
+                CK(cudaMemsetAsync(s->accum.p, 0, (size_t)np_all * sizeof(float4), st));
+                for (uint32_t p0 = 0; p0 < np_all; p0 += np_batch) {
+                    const uint32_t np = std::min(np_batch, np_all - p0);
+                    for (uint32_t s0 = sample_lo; s0 < sample_hi; s0 += ns_batch) {
+                        const uint32_t ns = std::min(ns_batch, sample_hi - s0);
+                        w.pixel_base = p0; w.n_pixels = np; w.sample_base = s0; w.n_samples = ns;
+                        run_batch(s, rp, w, np * ns, collect);
+                        launch_resolve(st, w, s->accum.p, s->lc);
+                    }
                 }
+                launch_finalize(st, s->pixel_list.p, np_all, s->width, s->accum.p, sum_mode ? 1.0f : 1.0f / (float)settings->samples_per_pixel, out->beauty, s->stats_dev.p, s->lc);
+            };
+            // frames of at least 4 Mi paths go through the graph (below that instantiating ~40 nodes per batch costs more
+            // than the launches it saves); RTCUDA_NO_GRAPH=1 keeps direct launches (A/B, debugging)
+            static const bool no_graph = std::getenv("RTCUDA_NO_GRAPH") != nullptr;
+            if (no_graph || samples < (1ull << 22)) {
+                reset_spans(s);
+                enqueue_frame();
+            } else {
+                std::vector<uint64_t> key = {settings->max_ray_depth, settings->accumulate_bounces, settings->light_sample_count, settings->samples_per_pixel,
+                                             settings->has_seed, settings->seed, settings->sampler_kind, settings->stratified_jitter, settings->x_strata,
+                                             settings->y_strata, settings->antialias_primary_rays, settings->antialias_secondary_rays,
+                                             (uint64_t)(uintptr_t)out->beauty, (uint64_t)(uintptr_t)s->arena.base, (uint64_t)(uintptr_t)s->accum.p,
+                                             (uint64_t)(uintptr_t)s->stats_dev.p, (uint64_t)(uintptr_t)s->pixel_list.p, np_all, np_batch, ns_batch, sample_lo,
+                                             sample_hi, shadow_k, (uint64_t)s->ctx->bs.collect_stats};
+                if (!s->frame_exec || key != s->frame_key) {
+                    reset_spans(s);
+                    const unsigned long long l0 = s->lc.launches;
+                    cudaGraph_t graph = nullptr;
+                    CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+                    s->capturing = true;
+                    try {
+                        enqueue_frame();
+                    } catch (...) {
+                        s->capturing = false;
+                        cudaStreamEndCapture(st, &graph);
+                        if (graph) cudaGraphDestroy(graph);
+                        throw;
+                    }
+                    s->capturing = false;
+                    CK(cudaStreamEndCapture(st, &graph));
+                    const cudaError_t ie = cudaGraphInstantiate(&s->frame_exec, graph, 0);
+                    cudaGraphDestroy(graph);
+                    CK(ie);
+                    s->frame_launches = s->lc.launches - l0;
+                    s->lc.launches = l0;
+                    s->frame_key = std::move(key);
+                }
+                CK(cudaGraphLaunch(s->frame_exec, st));
+                s->lc.launches += s->frame_launches;
             }
-            launch_finalize(st, s->pixel_list.p, np_all, s->width, s->accum.p, sum_mode ? 1.0f : 1.0f / (float)settings->samples_per_pixel, out->beauty, s->stats_dev.p, s->lc);
         }
     }
     CK(cudaEventRecord(e1, st));
@@ -937,8 +1016,7 @@ void render_pixel(rtcuda_scene* s, const rtcuda_settings* settings, uint32_t x, 
     w.stats = s->stats_dev.p;
     w.shadow_k = shadow_k; w.svertex = s->svertex.p;
     w.sray_o = s->sray_o.p; w.sray_d = s->sray_d.p; w.scontrib = s->scontrib.p;
-    s->spans.clear();
-    s->ev_used = 0;
+    reset_spans(s);
     run_batch(s, rp, w, n, false);
     launch_pixel_radiance(st, s->radiance.p, n, s->pixel_out.p, s->lc);
     static_assert(sizeof(PixelOut) == sizeof(rtcuda_pixel_output), "pixel output layout");

@@ -23,6 +23,7 @@ constexpr int BLOCK = 256;
 #ifndef SHADE_WARP_ALLOC
 #define SHADE_WARP_ALLOC 1
 #endif
+
 static inline uint32_t grid_for(uint32_t n, int block = BLOCK) { return n ? (n + block - 1) / block : 1; }
 
 // ---------------------------------------------------------------------------------------------------
@@ -66,8 +67,22 @@ __global__ void __launch_bounds__(BLOCK) k_raygen(const __grid_constant__ SceneD
 // the box test ran the Moller-Trumbore code at ~8 of 32 lanes. The policy and its constants were tuned with the
 // warp simulator in tests/hostsim (HOSTSIM_WARPSIM). Every lane stays in the loop until the whole warp is out
 // of work, which keeps the full-mask ballots / shuffles legal.
-constexpr int REFILL_MIN = 6;
-constexpr int TRI_MIN = 12;
+#ifndef RT_REFILL_MIN
+#define RT_REFILL_MIN 10
+#endif
+#ifndef RT_TRI_MIN
+#define RT_TRI_MIN 12
+#endif
+constexpr int REFILL_MIN = RT_REFILL_MIN;
+constexpr int TRI_MIN = RT_TRI_MIN;
+// (policy constants re-swept on the B200 after TRI_PER_PHASE = 2: refill threshold 4 / 6 / 10 / 14 / 18 / 24 -> k_extend + k_shadow
+// 261 / 248 / 242 / 244-252 / 270 / 340 ms on C3, primitive-phase threshold 8 / 12 / 16 / 20 -> 258 / 248 / 244 / 249 ms; profiles/r1q_ab.log, r1r_ab.log)
+// Primitives a lane may intersect per primitive phase: with 2, a lane holding several leaf primitives (a leaf has up to 3, a
+// node step can hit several leaves) does not pay the vote / refill bookkeeping of the loop for each of them: k_extend
+// 100.7 -> 93.1 ms, k_shadow 169.3 -> 154.0 ms on C3; 3 gains nothing more and spills in k_shadow (profiles/r1p_ab.log).
+#ifndef TRI_PER_PHASE
+#define TRI_PER_PHASE 2
+#endif
 // Resident blocks per SM asked of the any-hit kernel: 5 (48 registers, ~76 B of spills) hides more of its load latency than the 4
 // that 64 registers allow — k_shadow 174 -> 168 ms on C3; the closest-hit kernel carries more state and lost 1 % (A/B in
 // profiles/r1_notes.md), so it keeps the register count it wants.
@@ -82,12 +97,18 @@ __device__ __forceinline__ void warp_phase(Traversal<ANY_HIT, STATS>& tr, uint32
     const bool wn = have && tr.has_nodes() && (!wt || tr.can_stash());
     const unsigned mt = __ballot_sync(FULL, wt), mn = __ballot_sync(FULL, wn);
     if (mt != 0u && (mn == 0u || __popc(mt) >= TRI_MIN)) {
-        if (wt) tr.tri_step(sc, ts);
+        if (wt) {
+            tr.tri_step(sc, ts);
+#if TRI_PER_PHASE > 1
+#pragma unroll 1
+            for (int r = 1; r < TRI_PER_PHASE && tr.has_tris(); r++) tr.tri_step(sc, ts);
+#endif
+        }
     } else if (wn) tr.node_step(sc, ts);
 }
 
 template <bool STATS>
-__global__ void __launch_bounds__(BLOCK) k_extend(const __grid_constant__ SceneD sc, const __grid_constant__ Wave w, float t_min,
+__global__ void __launch_bounds__(BLOCK, 4) k_extend(const __grid_constant__ SceneD sc, const __grid_constant__ Wave w, float t_min,
                                                    uint32_t* fetch_counter) {
     const uint32_t n = *w.n_in;
     const unsigned FULL = 0xffffffffu;

@@ -12,7 +12,9 @@ python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/${tag}_bench
 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 400 --csv --log-file gpurun_out/${tag}_launches.csv \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/${tag}_ncu_launches.log 2>&1
 python scripts/profile_target.py > gpurun_out/${tag}_profile_plain.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:'k_extend|k_shade|k_shadow' -s 29 -c 3 -f -o gpurun_out/${tag}_prof \
+ncu --set full --clock-control none --import-source on -k regex:'k_extend|k_shade|k_shadow' -s 38 -c 3 -f -o gpurun_out/${tag}_prof \
     python scripts/profile_target.py > gpurun_out/${tag}_ncu_full.log 2>&1
+ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:k_extend -c 72 --csv \
+    --log-file gpurun_out/${tag}_extend_traffic.csv python bench.py --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/${tag}_traffic_run.log 2>&1
 fi
 echo done

@@ -253,8 +253,8 @@ def main():
     # context + scene upload (H2D) + device BVH build + render + D2H of the frame (raytracing_cpu::render also
     # builds its acceleration structures inside every call, lib.rs:655)
     e2e_steps = max(1, min(args.steps, 2))
-    holder = sc.to_desc()
-    h2d = int(holder.vertices.nbytes + holder.tris.nbytes + holder.normals.nbytes + holder.uvs.nbytes + holder.image_bytes.nbytes)
+    holder = sc.to_desc(own_arrays=True)
+    h2d = int(holder.geometry_bytes + holder.image_bytes.nbytes)
     e2e_each = []
     if world == 1:
         def e2e_call(record):

@@ -95,6 +95,16 @@ typedef struct rtcuda_shape {
     uint32_t uv_offset;          /* RTCUDA_NONE when the mesh has no uvs */
     float center[3];             /* sphere, object space */
     float radius;                /* sphere */
+    /* Optional per-shape host arrays (ABI v2): when `vertices` is non-NULL this mesh is read from these pointers
+     * (vertex_count x 3 floats, tri_count x 3 indices, normals / uvs per vertex or NULL) instead of the scene-wide
+     * arrays, and the four offsets above are ignored (the library assigns them). A binding can then point straight at
+     * the caller's `Mesh { vertices, tris, normals, uvs }` Vecs (repr(C), geometry/shapes/mesh.rs:71-76) without
+     * concatenating them: for the 16.8 M-triangle mesh that copy was 95 ms of a 445 ms end-to-end frame. Either every
+     * mesh of a scene uses its own pointers or none does. */
+    const float* vertices;
+    const uint32_t* tris;
+    const float* normals;
+    const float* uvs;
 } rtcuda_shape;
 
 /* One child of the root AggregatePrimitive after Scene::get_descendant flattening

@@ -48,7 +48,9 @@ class Shape(C.Structure):
                 ("vertex_offset", C.c_uint32), ("vertex_count", C.c_uint32),
                 ("tri_offset", C.c_uint32), ("tri_count", C.c_uint32),
                 ("normal_offset", C.c_uint32), ("uv_offset", C.c_uint32),
-                ("center", C.c_float * 3), ("radius", C.c_float)]
+                ("center", C.c_float * 3), ("radius", C.c_float),
+                ("vertices", C.POINTER(C.c_float)), ("tris", C.POINTER(C.c_uint32)),
+                ("normals", C.POINTER(C.c_float)), ("uvs", C.POINTER(C.c_float))]
 
 
 class Instance(C.Structure):

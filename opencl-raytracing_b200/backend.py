@@ -67,7 +67,7 @@ class CudaRenderer:
         t0 = time.perf_counter()
         _ffi.check(self.lib, self.lib.rtcuda_init(C.byref(bs), C.byref(self._ctx)), "rtcuda_init")
         t1 = time.perf_counter()
-        holder = scene.to_desc()
+        holder = scene.to_desc(own_arrays=True)   # zero-copy: the library reads every mesh from its own arrays
         t2 = time.perf_counter()
         try:
             _ffi.check(self.lib, self.lib.rtcuda_scene_upload(self._ctx, C.byref(holder.desc), C.byref(self._scene)),

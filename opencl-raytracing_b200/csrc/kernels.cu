@@ -431,6 +431,18 @@ void launch_light_tris(cudaStream_t st, const ShapeD* shapes, uint32_t shape, ui
     lc.launches++;
 }
 
+// upload-time validation of a mesh's triangle indices (api.cu: validate_desc leaves this to the device)
+__global__ void __launch_bounds__(BLOCK) k_check_indices(const uint32_t* idx, size_t n, uint32_t vertex_count, uint32_t* bad) {
+    bool any = false;
+    for (size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x; i < n; i += (size_t)gridDim.x * BLOCK) any |= idx[i] >= vertex_count;
+    if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31u) == 0) atomicOr(bad, 1u);
+}
+void launch_check_indices(cudaStream_t st, const uint32_t* idx, size_t n, uint32_t vertex_count, uint32_t* bad, LaunchCounter& lc) {
+    const uint32_t grid = (uint32_t)std::min<size_t>((n + BLOCK - 1) / BLOCK, 148 * 16);
+    k_check_indices<<<std::max(grid, 1u), BLOCK, 0, st>>>(idx, n, vertex_count, bad);
+    lc.launches++;
+}
+
 __global__ void __launch_bounds__(BLOCK) k_shade_recs(const __grid_constant__ SceneD sc, ShadeRec* out) {
     const uint32_t i = blockIdx.x * BLOCK + threadIdx.x;
     if (i < sc.prim_count) shade_rec_body(i, sc, out);

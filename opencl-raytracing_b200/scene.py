@@ -255,8 +255,11 @@ class Scene:
     environment_light: Optional[int] = None                   # texture id (EnvironmentLight::radiance)
 
     # -- flattening into the C ABI -----------------------------------------------------------
-    def to_desc(self) -> "SceneDescHolder":
-        return SceneDescHolder(self)
+    def to_desc(self, own_arrays: bool = False) -> "SceneDescHolder":
+        """Flatten into an rtcuda_scene_desc. own_arrays=True points every mesh at its own numpy arrays (rtcuda_shape.vertices /
+        tris / normals / uvs) instead of concatenating them into scene-wide arrays — what the CUDA backend uploads from; the
+        oracle and the CPU harness read the concatenated form."""
+        return SceneDescHolder(self, own_arrays)
 
     def triangle_count(self) -> int:
         return sum(len(self.shapes[s].shape.tris) if isinstance(self.shapes[s].shape, Mesh) else 0 for s, _ in self.instances)
@@ -348,10 +351,11 @@ def _camera_from_json(d: dict) -> Camera:
 class SceneDescHolder:
     """Owns the host arrays an `rtcuda_scene_desc` points into (keep alive until upload returns)."""
 
-    def __init__(self, scene: Scene):
+    def __init__(self, scene: Scene, own_arrays: bool = False):
         self.scene = scene
         shapes = (_ffi.Shape * max(1, len(scene.shapes)))()
         verts, tris, normals, uvs = [], [], [], []
+        keep_arrays = []
         nv = nt = nn = nuv = 0
         for i, bp in enumerate(scene.shapes):
             s = shapes[i]
@@ -363,18 +367,35 @@ class SceneDescHolder:
                 s.kind = _ffi.SHAPE_TRIANGLE_MESH
                 s.vertex_offset, s.vertex_count = nv, len(m.vertices)
                 s.tri_offset, s.tri_count = nt, len(m.tris)
-                verts.append(np.ascontiguousarray(m.vertices, dtype=f32).reshape(-1, 3))
-                tris.append(np.ascontiguousarray(m.tris, dtype=np.uint32).reshape(-1, 3))
-                nv += len(m.vertices)
-                nt += len(m.tris)
-                if m.normals is not None and len(m.normals):
+                mv = np.ascontiguousarray(m.vertices, dtype=f32).reshape(-1, 3)     # no copy when already f32 / u32 and contiguous
+                mt = np.ascontiguousarray(m.tris, dtype=np.uint32).reshape(-1, 3)
+                mn = np.ascontiguousarray(m.normals, dtype=f32).reshape(-1, 3) if m.normals is not None and len(m.normals) else None
+                mu = np.ascontiguousarray(m.uvs, dtype=f32).reshape(-1, 2) if m.uvs is not None and len(m.uvs) else None
+                nv += len(mv)
+                nt += len(mt)
+                if mn is not None:
                     s.normal_offset = nn
-                    normals.append(np.ascontiguousarray(m.normals, dtype=f32).reshape(-1, 3))
-                    nn += len(m.normals)
-                if m.uvs is not None and len(m.uvs):
+                    nn += len(mn)
+                if mu is not None:
                     s.uv_offset = nuv
-                    uvs.append(np.ascontiguousarray(m.uvs, dtype=f32).reshape(-1, 2))
-                    nuv += len(m.uvs)
+                    nuv += len(mu)
+                if own_arrays:
+                    keep_arrays += [mv, mt, mn, mu]
+                    # an empty mesh still needs a non-NULL vertices pointer to say "own arrays"
+                    if not len(mv):
+                        mv = np.zeros((1, 3), dtype=f32)
+                        keep_arrays.append(mv)
+                    s.vertices = mv.ctypes.data_as(C.POINTER(C.c_float))
+                    s.tris = mt.ctypes.data_as(C.POINTER(C.c_uint32)) if len(mt) else None
+                    s.normals = mn.ctypes.data_as(C.POINTER(C.c_float)) if mn is not None else None
+                    s.uvs = mu.ctypes.data_as(C.POINTER(C.c_float)) if mu is not None else None
+                else:
+                    verts.append(mv)
+                    tris.append(mt)
+                    if mn is not None:
+                        normals.append(mn)
+                    if mu is not None:
+                        uvs.append(mu)
             else:
                 s.kind = _ffi.SHAPE_SPHERE
                 s.center[0], s.center[1], s.center[2] = [float(f32(c)) for c in bp.shape.center]
@@ -427,7 +448,9 @@ class SceneDescHolder:
             off += len(b) + pad
         self.image_bytes = np.frombuffer(b"".join(blobs) if blobs else b"\0" * 16, dtype=np.uint8).copy()
 
-        self._keep = (shapes, instances, lights, materials, textures, images)
+        self._keep = (shapes, instances, lights, materials, textures, images, keep_arrays)
+        self.geometry_bytes = sum(a.nbytes for a in keep_arrays if isinstance(a, np.ndarray)) if own_arrays else \
+            int(self.vertices.nbytes + self.tris.nbytes + self.normals.nbytes + self.uvs.nbytes)
         d = _ffi.SceneDesc()
         d.abi_version = _ffi.ABI_VERSION
         d.camera = scene.camera.to_c()

@@ -241,6 +241,27 @@ def test_tile_size_partition_is_exact(rc):
         gpu_render(rc, sc, st, tile_size=24)
 
 
+def test_own_arrays_and_scene_wide_arrays_upload_the_same_scene(rc):
+    """rtcuda_shape.vertices / tris / normals / uvs (zero-copy from the caller's meshes) vs the concatenated scene-wide arrays"""
+    import ctypes as C
+    sc = load_scene("cb_texture", 160, 90)
+    st = rc.RaytracerSettings(outputs=A.BEAUTY | A.NORMALS | A.UV_COORDS | A.DEBUG_IDS, samples_per_pixel=2)
+    a, _ = gpu_render(rc, sc, st)                       # CudaRenderer uploads with own_arrays=True
+    lib = rc._ffi.load_library()
+    ctx, scn = C.c_void_p(), C.c_void_p()
+    bs = rc.CudaBackendSettings().to_c()
+    rc._ffi.check(lib, lib.rtcuda_init(C.byref(bs), C.byref(ctx)), "init")
+    holder = sc.to_desc(own_arrays=False)
+    rc._ffi.check(lib, lib.rtcuda_scene_upload(ctx, C.byref(holder.desc), C.byref(scn)), "upload")
+    b = rc.RenderOutput.allocate(160, 90, A(st.outputs))
+    s, o = st.to_c(), b.to_c()
+    rc._ffi.check(lib, lib.rtcuda_render(scn, C.byref(s), C.byref(o)), "render")
+    lib.rtcuda_scene_release(scn)
+    lib.rtcuda_shutdown(ctx)
+    for plane in ("beauty", "normals", "uv", "debug_ids"):
+        assert np.array_equal(getattr(a, plane), getattr(b, plane)), plane
+
+
 def test_sample_range_render(rc):
     """rtcuda_render_samples_device: the sums of disjoint sample ranges add up to the frame (same streams per sample
     index; only the association of the float sum differs), and the full range reproduces it bit for bit"""
@@ -308,6 +329,11 @@ def test_error_behaviour(rc):
     bad.shapes[0].material = 7
     with pytest.raises(rc._ffi.RtCudaError, match="out of range"):
         rc.CudaRenderer(bad)
+    import copy
+    broken = copy.deepcopy(load_scene("cb", 64, 64))
+    broken.shapes[1].shape.tris[0, 2] = 1000           # checked on the device after the upload
+    with pytest.raises(rc._ffi.RtCudaError, match="triangle index out of range"):
+        rc.CudaRenderer(broken)
     empty = rc.SceneBuilder()
     empty.add_camera(rc.Camera.lookat_camera_perspective((0, 0, 0), (0, 0, -1), (0, 1, 0), False, 0.7, 32, 32))
     out, _ = gpu_render(rc, empty.build(), rc.RaytracerSettings(outputs=A.BEAUTY | A.NORMALS, samples_per_pixel=2))

@@ -92,6 +92,14 @@ def test_scene_desc_round_trip(rc):
     d = h.desc
     assert d.tri_count == 28588 and d.instance_count == 7 and d.light_count == 1
     assert d.shapes[d.lights[0].shape].area_light == 0
+    # own_arrays: every mesh points at its own numpy arrays, nothing is concatenated, same counts
+    o = sc.to_desc(own_arrays=True)
+    assert o.desc.tri_count == 0 and o.desc.vertex_count == 0 and o.geometry_bytes == h.geometry_bytes
+    for i, bp in enumerate(sc.shapes):
+        sh, ref = o.desc.shapes[i], d.shapes[i]
+        assert (sh.vertex_count, sh.tri_count) == (ref.vertex_count, ref.tri_count) and bool(sh.vertices) and bool(sh.tris)
+        assert np.array_equal(np.ctypeslib.as_array(sh.tris, shape=(sh.tri_count * 3,)), np.asarray(bp.shape.tris, dtype=np.uint32).ravel())
+        assert bool(sh.normals) == (ref.normal_offset != rc._ffi.NONE) and bool(sh.uvs) == (ref.uv_offset != rc._ffi.NONE)
 
 
 def test_tile_owner_map(rc):

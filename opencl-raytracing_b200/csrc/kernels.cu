@@ -83,6 +83,7 @@ constexpr int TRI_MIN = RT_TRI_MIN;
 #ifndef TRI_PER_PHASE
 #define TRI_PER_PHASE 2
 #endif
+// (a second node step per node phase for lanes that found inner children only: extend 92 -> 98 ms, shadow 149 -> 165 ms — not kept)
 // Resident blocks per SM asked of the any-hit kernel: 5 (48 registers, ~76 B of spills) hides more of its load latency than the 4
 // that 64 registers allow — k_shadow 174 -> 168 ms on C3; the closest-hit kernel carries more state and lost 1 % (A/B in
 // profiles/r1_notes.md), so it keeps the register count it wants.

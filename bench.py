@@ -303,7 +303,7 @@ def main():
     with rc.CudaRenderer(sc, rc.multi_gpu.backend_settings_for_rank(rank, world, local_rank, collect_stats=_ffi.STATS_COUNTERS)) as rs:
         rs.render_device(st, {"beauty": dr.planes_for(rc.AovFlags.BEAUTY)["beauty"].data_ptr()})
         cs = rs.stats()
-    ext_rays = cs["primary_rays"] + cs["bounce_rays"]
+    ext_rays = cs["primary_rays"] - cs["primary_rays_culled"] + cs["bounce_rays"]   # rays k_extend actually walked (camera rays that miss the scene bounds never reach it)
     ext_bytes = 80 * cs["extend_nodes"] + 48 * cs["extend_prims"] + 64 * ext_rays
     ext_s = agg["extend_ms"] / 1e3 / args.steps
     peak, peak_src = peaks()
@@ -315,7 +315,8 @@ def main():
     roofline = {"kernel": "k_extend (closest-hit BVH8 traversal)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak if achieved else None, "traffic": traffic, "peak_source": peak_src,
                 "bytes_per_ray": ext_bytes / max(1, ext_rays), "nodes_per_ray": cs["extend_nodes"] / max(1, ext_rays),
-                "prims_per_ray": cs["extend_prims"] / max(1, ext_rays), "launches_per_step": agg["extend_launches"] / args.steps,
+                "prims_per_ray": cs["extend_prims"] / max(1, ext_rays), "extend_rays_per_step": ext_rays,
+                "primary_rays_culled_per_step": cs["primary_rays_culled"], "launches_per_step": agg["extend_launches"] / args.steps,
                 "ms_per_launch": 1e3 * ext_s / max(1, agg["extend_launches"] / args.steps),
                 "kernel_share_of_step": {k: agg[k] / agg["render_ms"] for k in ("extend_ms", "shade_ms", "shadow_ms", "other_ms")}}
 

@@ -322,6 +322,9 @@ typedef struct rtcuda_stats {
     /* NaN / Inf channels of the beauty plane of the last render: the device side of the reference's scan
      * (lib.rs:813-854); the binding prints its warnings ("R component of (x, y) is NaN", first 10) when non-zero. */
     uint64_t nonfinite_values;
+    /* Camera rays (counted in primary_rays) that missed the scene bounds and were dropped before the wavefront: the
+     * root-AABB reject of traverse_bvh (accel.rs:95) done in ray generation; only without an environment light. */
+    uint64_t primary_rays_culled;
 } rtcuda_stats;
 
 typedef struct rtcuda_ctx rtcuda_ctx;

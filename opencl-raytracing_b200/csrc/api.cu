@@ -404,6 +404,7 @@ void build_bvh(rtcuda_scene* s, const std::vector<Instance>& instances, uint32_t
         s->prims.alloc(1);
         s->sc.scene_center[0] = s->sc.scene_center[1] = s->sc.scene_center[2] = 0.0f;
         s->sc.scene_radius = 0.0f;
+        set_scene_bounds(s->sc, mk3(0.0f), mk3(0.0f), false);
         return;
     }
     const uint32_t n = n_prims;
@@ -504,6 +505,7 @@ void build_bvh(rtcuda_scene* s, const std::vector<Instance>& instances, uint32_t
     V3 c = (mx + mn) / 2.0f;
     s->sc.scene_center[0] = c.x; s->sc.scene_center[1] = c.y; s->sc.scene_center[2] = c.z;
     s->sc.scene_radius = n == 1 ? INFINITY : length(mx - c);
+    set_scene_bounds(s->sc, mn, mx, true);
 }
 
 void upload_scene(rtcuda_scene* s, const rtcuda_scene_desc* d) {
@@ -992,6 +994,7 @@ void render_device(rtcuda_scene* s, const rtcuda_settings* settings, const rtcud
     s->stats.prims_fetched = h_stats[STAT_EXT_PRIMS] + h_stats[STAT_SH_PRIMS] + h_stats[STAT_AOV_PRIMS];
     s->stats.shaded_vertices = h_stats[STAT_SHADED];
     s->stats.nonfinite_values = h_stats[STAT_NONFINITE];
+    s->stats.primary_rays_culled = h_stats[STAT_CULLED];
     s->stats.kernel_launches = s->lc.launches - launches0;
     s->stats.render_ms = ms;
     double cls_ms[CLS_COUNT] = {0, 0, 0, 0};

@@ -50,11 +50,26 @@ __device__ __forceinline__ void warp_add_stat(unsigned long long* dst, uint32_t 
 // ---------------------------------------------------------------------------------------------------
 // wavefront kernels
 // ---------------------------------------------------------------------------------------------------
+// One thread per path slot; the camera rays that can hit something are compacted into the depth-0 queue (one atomic per block).
+// Every generated sample counts as a primary ray, like the reference's per-sample traverse_bvh call that stops at the root box.
 __global__ void __launch_bounds__(BLOCK) k_raygen(const __grid_constant__ SceneD sc, const __grid_constant__ RenderParams rp,
                                                    const __grid_constant__ Wave w, uint32_t n) {
+    __shared__ uint32_t s_count, s_base;
     const uint32_t i = blockIdx.x * BLOCK + threadIdx.x;
-    if (i == 0) *w.n_out = n;
-    if (i < n) raygen_body(i, sc, rp, w);
+    if (threadIdx.x == 0) s_count = 0;
+    if (i == 0) atomicAdd(&w.stats[STAT_PRIMARY], (unsigned long long)n);
+    __syncthreads();
+    float4 ro, rd;
+    const bool keep = i < n && raygen_body(i, sc, rp, w, ro, rd);
+    const uint32_t pos = block_push(keep, w.n_out, &s_count, &s_base);
+    if (keep) {
+        w.ray_o_out[pos] = ro;
+        w.ray_d_out[pos] = rd;
+    }
+    if (threadIdx.x == 0) {   // after block_push's barriers: s_count = rays this block queued
+        const uint32_t in_block = min(n - blockIdx.x * BLOCK, (uint32_t)BLOCK);
+        if (in_block != s_count) atomicAdd(&w.stats[STAT_CULLED], (unsigned long long)(in_block - s_count));
+    }
 }
 
 // Persistent traversal kernels. A warp keeps pulling work from the launch's queue: whenever at least
@@ -114,7 +129,7 @@ __global__ void __launch_bounds__(BLOCK, 4) k_extend(const __grid_constant__ Sce
     const uint32_t n = *w.n_in;
     const unsigned FULL = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&w.stats[w.depth == 0 ? STAT_PRIMARY : STAT_BOUNCE], (unsigned long long)n);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && w.depth != 0) atomicAdd(&w.stats[STAT_BOUNCE], (unsigned long long)n);   // primary rays: counted by k_raygen
     uint2 stack_mem[TRAVERSE_STACK];
     Traversal<false, STATS> tr;
     tr.stack = stack_mem;

@@ -59,7 +59,7 @@ struct Wave {
 };
 
 enum { STAT_PRIMARY = 0, STAT_BOUNCE = 1, STAT_SHADOW = 2, STAT_AOV = 3, STAT_EXT_NODES = 4, STAT_EXT_PRIMS = 5, STAT_SH_NODES = 6,
-       STAT_SH_PRIMS = 7, STAT_AOV_NODES = 8, STAT_AOV_PRIMS = 9, STAT_SHADED = 10, STAT_NONFINITE = 11, STAT_TOTAL = 12 };
+       STAT_SH_PRIMS = 7, STAT_AOV_NODES = 8, STAT_AOV_PRIMS = 9, STAT_SHADED = 10, STAT_NONFINITE = 11, STAT_CULLED = 12, STAT_TOTAL = 16 };
 
 struct Ray { V3 o, d; };
 
@@ -308,7 +308,25 @@ RT_HD void slot_to_sample(const Wave& w, uint32_t slot, uint32_t& px, uint32_t& 
 }
 
 // ---- raygen: CpuSampler::start_sample + generate_ray(jitter = true) (lib.rs:527-536) -----------------
-RT_HD void raygen_body(uint32_t slot, const SceneD& sc, const RenderParams& rp, const Wave& w) {
+// Slab test of a camera ray against the scene bounds (SceneD::bounds_lo/hi, already grown by a margin far above the rounding
+// of this test): the reference rejects such rays at the BVH root (accel.rs:95) and, without an environment light, their
+// sample is black. t >= 0 only (near_clip >= 0): a box behind the camera cannot be hit either.
+RT_HD bool ray_misses_scene(const SceneD& sc, V3 o, V3 d) {
+    float t0 = 0.0f, t1 = RT_INF;
+    const float oo[3] = {o.x, o.y, o.z}, dd[3] = {d.x, d.y, d.z};
+    for (int k = 0; k < 3; k++) {
+        const float a = fabsf(dd[k]) > 1.0e-20f ? dd[k] : copysignf(1.0e-20f, dd[k]);
+        const float inv = 1.0f / a;
+        const float ta = (sc.bounds_lo[k] - oo[k]) * inv, tb = (sc.bounds_hi[k] - oo[k]) * inv;
+        t0 = fmaxf(t0, fminf(ta, tb));
+        t1 = fminf(t1, fmaxf(ta, tb));
+    }
+    return !(t0 <= t1);
+}
+
+// Initialises the slot's path state and returns the camera ray; false when no ray needs to be traced for this sample
+// (it misses the scene bounds and there is no environment light: its radiance stays 0, the slot is never read again).
+RT_HD bool raygen_body(uint32_t slot, const SceneD& sc, const RenderParams& rp, const Wave& w, float4& ray_o, float4& ray_d) {
     uint32_t px, py, sidx;
     slot_to_sample(w, slot, px, py, sidx);
     Sampler s;
@@ -317,13 +335,15 @@ RT_HD void raygen_body(uint32_t slot, const SceneD& sc, const RenderParams& rp, 
     Ray ray;
     RayDiff rd;
     generate_ray<false>(sc.camera, px, py, s, rp.samples_per_pixel, true, ray, rd);
+    w.radiance[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (sc.env_texture == NONE && ray_misses_scene(sc, ray.o, ray.d)) return false;
     RngState rs;
     rs.state = s.rng.state; rs.inc = s.rng.inc;
     w.state[slot].rng = rs;
     w.state[slot].weight = make_float4(1.0f, 1.0f, 1.0f, u2f(1u | (s.dimension << 8)));
-    w.radiance[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    w.ray_o_out[slot] = make_float4(ray.o.x, ray.o.y, ray.o.z, sc.camera.far_clip);
-    w.ray_d_out[slot] = make_float4(ray.d.x, ray.d.y, ray.d.z, u2f(slot));
+    ray_o = make_float4(ray.o.x, ray.o.y, ray.o.z, sc.camera.far_clip);
+    ray_d = make_float4(ray.d.x, ray.d.y, ray.d.z, u2f(slot));
+    return true;
 }
 
 // ---- shade: one iteration of the ray_radiance loop after traverse_bvh (lib.rs:284-391) ------------------

@@ -125,7 +125,17 @@ struct SceneD {
     uint32_t watertight;      // RTCUDA_BACKEND_WATERTIGHT: Woop's watertight triangle test instead of the reference's Moller-Trumbore
     float scene_center[3];
     float scene_radius;       // +inf when the BVH root is a leaf (bvh2.rs:448-452 quirk, see rt_shade.h)
+    // World bounds of all primitives, grown by 1e-3 of their largest extent: camera rays that miss them are not queued
+    // (raygen_body) — the root-AABB reject of traverse_bvh (accel.rs:95) moved in front of the wavefront. Empty scene: lo > hi.
+    float bounds_lo[3], bounds_hi[3];
 };
+
+RT_HD void set_scene_bounds(SceneD& sc, V3 mn, V3 mx, bool any) {
+    const float pad = any ? 1.0e-3f * fmaxf(mx.x - mn.x, fmaxf(mx.y - mn.y, mx.z - mn.z)) + 1.0e-6f : 0.0f;
+    const float big = 3.0e38f;
+    sc.bounds_lo[0] = any ? mn.x - pad : big; sc.bounds_lo[1] = any ? mn.y - pad : big; sc.bounds_lo[2] = any ? mn.z - pad : big;
+    sc.bounds_hi[0] = any ? mx.x + pad : -big; sc.bounds_hi[1] = any ? mx.y + pad : -big; sc.bounds_hi[2] = any ? mx.z + pad : -big;
+}
 
 RT_HD V3 load3(const float* p, uint32_t i) { return mk3(ldg(p + 3 * (size_t)i), ldg(p + 3 * (size_t)i + 1), ldg(p + 3 * (size_t)i + 2)); }
 RT_HD void light_tri_body(uint32_t tri, const ShapeD& em, const float* vertices, const uint32_t* tris, LightTri* out) {

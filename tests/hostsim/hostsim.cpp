@@ -233,6 +233,7 @@ void build(HostScene& hs, const rtcuda_scene_desc* d) {
     V3 c = (mx + mn) / 2.0f;
     sc.scene_center[0] = c.x; sc.scene_center[1] = c.y; sc.scene_center[2] = c.z;
     sc.scene_radius = n == 1 ? INFINITY : length(mx - c);
+    set_scene_bounds(sc, mn, mx, true);
     if (counters[2] != n) sc.node_count = 0xdeadbeef;  // lost primitives: surfaced through the stats
     else if (!std::getenv("HOSTSIM_NO_SHADE_RECS")) {
         hs.shade_recs.resize(n);
@@ -420,9 +421,13 @@ int hostsim_render(const rtcuda_scene_desc* d, const rtcuda_settings* st, rtcuda
             for (uint32_t s0 = 0; s0 < st->samples_per_pixel; s0 += ns_batch) {
                 const uint32_t ns = std::min(ns_batch, st->samples_per_pixel - s0);
                 w.pixel_base = p0; w.n_pixels = np; w.sample_base = s0; w.n_samples = ns;
-                uint32_t n_rays = np * ns;
+                uint32_t n_rays = 0;
                 w.depth = 0; w.ray_o_out = ro[0].data(); w.ray_d_out = rd[0].data();
-                for (uint32_t i = 0; i < n_rays; i++) raygen_body(i, sc, rp, w);
+                for (uint32_t i = 0; i < np * ns; i++) {   // k_raygen: rays that miss the scene bounds are not queued
+                    float4 o4, d4;
+                    if (raygen_body(i, sc, rp, w, o4, d4)) { ro[0][n_rays] = o4; rd[0][n_rays] = d4; n_rays++; }
+                }
+                stats[0] += np * ns;
                 for (uint32_t depth = 0; depth <= rp.max_ray_depth && n_rays; depth++) {
                     const int in = depth & 1, ot = in ^ 1;
                     w.depth = depth;
@@ -441,7 +446,7 @@ int hostsim_render(const rtcuda_scene_desc* d, const rtcuda_settings* st, rtcuda
                         traverse<false, true>(sc, xyz(w.ray_o_in[q]), xyz(w.ray_d_in[q]), t_min, w.ray_o_in[q].w, h, &ts);
                         hits[q] = make_float4(h.t, u2f(h.prim), h.u, h.v);
                     }
-                    stats[depth == 0 ? 0 : 1] += n_rays;
+                    if (depth) stats[1] += n_rays;
                     const TraverseStats ts_mid = ts;
                     uint32_t n_out = 0, n_shadow = 0, n_sray = 0;
                     auto alloc = [&](bool cont, bool has_vertex, uint32_t k, uint32_t& rpos, uint32_t& vpos, uint32_t& first) {

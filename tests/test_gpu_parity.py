@@ -241,6 +241,23 @@ def test_tile_size_partition_is_exact(rc):
         gpu_render(rc, sc, st, tile_size=24)
 
 
+def test_primary_rays_that_miss_the_scene_bounds_are_not_queued(rc, oracle):
+    """raygen drops camera rays that miss the (grown) scene bounds when there is no environment light — the reference's
+    root-AABB reject (accel.rs:95): same pixels as the oracle, every sample still counted as a primary ray"""
+    sc = load_scene("cbbunny_area_light_transforms", 320, 180)      # the box covers about a quarter of the 16:9 raster
+    st = rc.RaytracerSettings(outputs=A.BEAUTY | A.DEBUG_IDS, samples_per_pixel=4)
+    out, stats = gpu_render(rc, sc, st)
+    ref, ostats = oracle.render(sc, st, num_threads=8)
+    assert stats["primary_rays"] == ostats["primary_rays"] == 320 * 180 * 4
+    assert 0.5 * stats["primary_rays"] < stats["primary_rays_culled"] < 0.8 * stats["primary_rays"]
+    assert beauty_close(out.beauty, ref.beauty)
+    assert (out.beauty[(ref.beauty == 0).all(axis=-1)] == 0).all()          # culled pixels are exactly black, like the oracle's misses
+    env = rc.test_scenes.environment_lighting_scene(rc.test_scenes.synthetic_environment_map())
+    env.camera = rc.Camera.lookat_camera_perspective((0.013, 0, 0.007), (0.1, 1, 0.05), (0, 0, 1), False, 0.66, 64, 64)
+    _, estats = gpu_render(rc, env, rc.RaytracerSettings(samples_per_pixel=2))
+    assert estats["primary_rays_culled"] == 0                                # misses light the pixel through the environment map
+
+
 def test_own_arrays_and_scene_wide_arrays_upload_the_same_scene(rc):
     """rtcuda_shape.vertices / tris / normals / uvs (zero-copy from the caller's meshes) vs the concatenated scene-wide arrays"""
     import ctypes as C

@@ -325,6 +325,10 @@ typedef struct rtcuda_stats {
     /* Camera rays (counted in primary_rays) that missed the scene bounds and were dropped before the wavefront: the
      * root-AABB reject of traverse_bvh (accel.rs:95) done in ray generation; only without an environment light. */
     uint64_t primary_rays_culled;
+    /* Continuation rays of the last depth that could not add radiance (non-specular sample, no environment light:
+     * crates/raytracing-cpu/src/lib.rs:294-298, 318-322) and were not traced; NOT counted in bounce_rays. The reference
+     * traces them: bounce_rays + final_rays_skipped is its bounce-ray count. */
+    uint64_t final_rays_skipped;
 } rtcuda_stats;
 
 typedef struct rtcuda_ctx rtcuda_ctx;

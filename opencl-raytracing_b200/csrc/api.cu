@@ -995,6 +995,7 @@ void render_device(rtcuda_scene* s, const rtcuda_settings* settings, const rtcud
     s->stats.shaded_vertices = h_stats[STAT_SHADED];
     s->stats.nonfinite_values = h_stats[STAT_NONFINITE];
     s->stats.primary_rays_culled = h_stats[STAT_CULLED];
+    s->stats.final_rays_skipped = h_stats[STAT_FINAL_SKIPPED];
     s->stats.kernel_launches = s->lc.launches - launches0;
     s->stats.render_ms = ms;
     double cls_ms[CLS_COUNT] = {0, 0, 0, 0};

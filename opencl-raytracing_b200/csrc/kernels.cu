@@ -186,9 +186,13 @@ __global__ void __launch_bounds__(BLOCK, std::is_same<Surf, DiffuseSurface>::val
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&w.stats[STAT_SHADED], (unsigned long long)n);
     for (uint32_t base = blockIdx.x * BLOCK; base < n; base += gridDim.x * BLOCK) {
         const uint32_t q = base + threadIdx.x;
-        shade_vertex<Surf>(q < n, q, sc, rp, w, [&](bool cont, bool has_vertex, uint32_t k, uint32_t& rpos, uint32_t& vpos, uint32_t& first) {
+        shade_vertex<Surf>(q < n, q, sc, rp, w, [&](bool cont, bool has_vertex, uint32_t k, bool final_skipped, uint32_t& rpos, uint32_t& vpos, uint32_t& first) {
             const unsigned FULL = 0xffffffffu;
             const unsigned mc = __ballot_sync(FULL, cont), mv = __ballot_sync(FULL, has_vertex);
+            if (w.depth + 1 == rp.max_ray_depth) {   // launch-uniform: only the shade launch before the last depth can skip rays
+                const unsigned mf = __ballot_sync(FULL, final_skipped);
+                if (mf && lane == 0) atomicAdd(&w.stats[STAT_FINAL_SKIPPED], (unsigned long long)__popc(mf));
+            }
             uint32_t incl = k;   // inclusive warp scan of the shadow-ray counts
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {

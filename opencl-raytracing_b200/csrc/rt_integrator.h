@@ -59,7 +59,7 @@ struct Wave {
 };
 
 enum { STAT_PRIMARY = 0, STAT_BOUNCE = 1, STAT_SHADOW = 2, STAT_AOV = 3, STAT_EXT_NODES = 4, STAT_EXT_PRIMS = 5, STAT_SH_NODES = 6,
-       STAT_SH_PRIMS = 7, STAT_AOV_NODES = 8, STAT_AOV_PRIMS = 9, STAT_SHADED = 10, STAT_NONFINITE = 11, STAT_CULLED = 12, STAT_TOTAL = 16 };
+       STAT_SH_PRIMS = 7, STAT_AOV_NODES = 8, STAT_AOV_PRIMS = 9, STAT_SHADED = 10, STAT_NONFINITE = 11, STAT_CULLED = 12, STAT_FINAL_SKIPPED = 13, STAT_TOTAL = 16 };
 
 struct Ray { V3 o, d; };
 
@@ -487,7 +487,7 @@ RT_HD uint32_t nee_pass(const SceneD& sc, const RenderParams& rp, const Wave& w,
     return k;
 }
 
-// alloc(continue_path, has_nee_vertex, n_shadow_rays, &ray_pos, &vertex_pos, &first_shadow_ray)
+// alloc(continue_path, has_nee_vertex, n_shadow_rays, final_ray_skipped, &ray_pos, &vertex_pos, &first_shadow_ray)
 template <typename Surf, typename Alloc>
 RT_HD void shade_vertex(bool active, uint32_t q, const SceneD& sc, const RenderParams& rp, const Wave& w, Alloc&& alloc) {
     ShadeState<Surf> S;
@@ -495,7 +495,7 @@ RT_HD void shade_vertex(bool active, uint32_t q, const SceneD& sc, const RenderP
     BsdfSample bs;
     NeeStage stage;
     uint32_t k = 0;
-    bool alive = false;
+    bool alive = false, final_skipped = false;
     // few light samples per vertex (the usual case): one evaluation, entries staged in thread-local memory until their
     // queue position is known; otherwise count first and evaluate again when writing
     const bool staged = w.shadow_k <= NEE_STAGE;
@@ -507,9 +507,16 @@ RT_HD void shade_vertex(bool active, uint32_t q, const SceneD& sc, const RenderP
         if (nee) k = staged ? nee_pass<1>(sc, rp, w, S, s2, 0u, NEE_STAGE, &stage) : nee_pass<0>(sc, rp, w, S, s2, 0u, 0u, nullptr);
         alive = surface_sample(S.surf, S.wo, s2, bs) == S_VALID;
         if (alive && (is_zero(bs.f) || bs.pdf == 0.0f)) alive = false;
+        // The ray of the last depth can only add emitted light after a specular bounce, or the environment on a miss
+        // (lib.rs:294-298, 318-322: the loop ends right after that hit's emission): after a non-specular sample in a scene
+        // without environment light the reference traces it for nothing, and it is not traced here.
+        if (alive && w.depth + 1 == rp.max_ray_depth && sc.env_texture == NONE && !(bs.component & SPECULAR)) {
+            alive = false;
+            final_skipped = true;
+        }
     }
     uint32_t rpos = 0, vpos = 0, first = 0;
-    alloc(alive, k != 0u, k, rpos, vpos, first);
+    alloc(alive, k != 0u, k, final_skipped, rpos, vpos, first);
     if (!active) return;
     if (k) {
         if (staged)

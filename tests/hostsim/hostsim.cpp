@@ -449,9 +449,10 @@ int hostsim_render(const rtcuda_scene_desc* d, const rtcuda_settings* st, rtcuda
                     if (depth) stats[1] += n_rays;
                     const TraverseStats ts_mid = ts;
                     uint32_t n_out = 0, n_shadow = 0, n_sray = 0;
-                    auto alloc = [&](bool cont, bool has_vertex, uint32_t k, uint32_t& rpos, uint32_t& vpos, uint32_t& first) {
+                    auto alloc = [&](bool cont, bool has_vertex, uint32_t k, bool final_skipped, uint32_t& rpos, uint32_t& vpos, uint32_t& first) {
                         rpos = n_out; vpos = n_shadow; first = n_sray;
                         n_out += cont; n_shadow += has_vertex; n_sray += k;
+                        stats[1] += final_skipped;   // reported with the bounce rays: the oracle (like the reference) traces them
                     };
                     for (uint32_t q = 0; q < n_rays; q++) {
                         if (sc.all_diffuse) shade_vertex<DiffuseSurface>(true, q, sc, rp, w, alloc);

@@ -70,7 +70,9 @@ def test_c2_cornell_box_512(rc, oracle):
     ref, ostats = oracle.render(sc, st, num_threads=8)
     assert_first_hit_parity(out, ref)
     assert stats["primary_rays"] == ostats["primary_rays"] == 512 * 512 * 8
-    assert abs(stats["bounce_rays"] - ostats["bounce_rays"]) <= ostats["bounce_rays"] // 2000
+    # the oracle (like the reference) also traces the last-depth rays that cannot add radiance; the backend reports them apart
+    assert stats["final_rays_skipped"] > 0
+    assert abs(stats["bounce_rays"] + stats["final_rays_skipped"] - ostats["bounce_rays"]) <= ostats["bounce_rays"] // 2000
     assert beauty_close(out.beauty, ref.beauty)
     assert abs(luminance(out.beauty).mean() - luminance(ref.beauty).mean()) <= 1e-3 * luminance(ref.beauty).mean()
     assert stats["nodes_fetched"] > 0 and stats["prims_fetched"] > 0
@@ -97,7 +99,7 @@ def test_gltf_scenes(rc, oracle, name, w, h, spp):
     ref, ostats = oracle.render(sc, st, num_threads=8)
     assert_first_hit_parity(out, ref)
     assert stats["primary_rays"] == ostats["primary_rays"]
-    assert abs(stats["bounce_rays"] - ostats["bounce_rays"]) <= max(8, ostats["bounce_rays"] // 1000)
+    assert abs(stats["bounce_rays"] + stats["final_rays_skipped"] - ostats["bounce_rays"]) <= max(8, ostats["bounce_rays"] // 1000)
     assert beauty_close(out.beauty, ref.beauty)
     la, lb = luminance(out.beauty), luminance(ref.beauty)
     assert abs(la.mean() - lb.mean()) <= 2e-3 * lb.mean()

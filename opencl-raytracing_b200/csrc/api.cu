@@ -666,6 +666,9 @@ void upload_scene(rtcuda_scene* s, const rtcuda_scene_desc* d) {
     sc.watertight = (s->ctx->bs.flags & RTCUDA_BACKEND_WATERTIGHT) ? 1u : 0u;
     sc.all_diffuse = 1;
     for (uint32_t m = 0; m < d->material_count; m++) if (d->materials[m].kind != RTCUDA_MATERIAL_DIFFUSE) sc.all_diffuse = 0;
+    sc.tex_uses_derivs = 0;
+    for (uint32_t t = 0; t < d->texture_count; t++)
+        if (d->textures[t].kind == RTCUDA_TEXTURE_IMAGE || d->textures[t].kind == RTCUDA_TEXTURE_CHECKER) sc.tex_uses_derivs = 1;
 
     build_bvh(s, instances, (uint32_t)n_prims);
     sc.nodes = s->nodes.p;

@@ -400,7 +400,7 @@ RT_HD bool shade_begin(uint32_t q, const SceneD& sc, const RenderParams& rp, con
     S.s.dimension = S.flags >> 8;
     S.s.sample_index = S.sidx;
 
-    const bool aa = depth == 0 && rp.antialias_primary_rays;
+    const bool aa = depth == 0 && rp.antialias_primary_rays && sc.tex_uses_derivs;
     reconstruct_hit(sc, S.ray.o, S.ray.d, h, aa, S.hit);
 
     const bool add_zero_bounce = rp.accumulate_bounces || rp.max_ray_depth == depth;

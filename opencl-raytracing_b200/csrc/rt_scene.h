@@ -122,6 +122,8 @@ struct SceneD {
     uint32_t instance_count, light_count, material_count, texture_count;
     uint32_t env_texture;
     uint32_t all_diffuse;     // every material is Diffuse: shade with the DiffuseSurface instantiation
+    uint32_t tex_uses_derivs; // some texture is an image or a checker: the only consumers of the uv derivatives (MatCtx); without
+                              // one, the primary hit skips the camera-ray differentials (same values: nothing would read them)
     uint32_t watertight;      // RTCUDA_BACKEND_WATERTIGHT: Woop's watertight triangle test instead of the reference's Moller-Trumbore
     float scene_center[3];
     float scene_radius;       // +inf when the BVH root is a leaf (bvh2.rs:448-452 quirk, see rt_shade.h)

@@ -262,6 +262,10 @@ struct Traversal {
             V3 oo = apply_point(inst->w2o, o), od = apply_vector(inst->w2o, d);
             h = sphere_t(xyz(pa), pb.x, oo, od, t_min, closest, t);
         }
+        if (ANY_HIT) {   // occlusion only: any hit in range ends the walk, no ids / barycentrics / tie-break needed
+            if (h) { found = 1u; hit.prim = pi; ngroup.y = 0u; tgroup.y = 0u; sp = 0; }
+            return;
+        }
         const uint32_t geom = f2u(pa.w), pid = f2u(pb.w);
         if (h && (t < closest || hit.prim == NONE || geom > hit_geom || (geom == hit_geom && pid > hit_pid))) {
             hit_geom = geom;

@@ -145,6 +145,9 @@ void build(HostScene& hs, const rtcuda_scene_desc* d) {
     sc.watertight = std::getenv("HOSTSIM_WATERTIGHT") ? 1u : 0u;   // test switch for RTCUDA_BACKEND_WATERTIGHT
     sc.all_diffuse = 1;
     for (uint32_t m = 0; m < d->material_count; m++) if (d->materials[m].kind != 0) sc.all_diffuse = 0;
+    sc.tex_uses_derivs = 0;
+    for (uint32_t t = 0; t < d->texture_count; t++)
+        if (d->textures[t].kind == RTCUDA_TEXTURE_IMAGE || d->textures[t].kind == RTCUDA_TEXTURE_CHECKER) sc.tex_uses_derivs = 1;
     sc.prim_count = n_prims; sc.node_count = 0;
     hs.nodes.resize(std::max(1u, n_prims)); hs.prims.resize(std::max(1u, n_prims));
     sc.nodes = hs.nodes.data(); sc.prims = hs.prims.data();

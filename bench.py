@@ -172,6 +172,8 @@ def main():
         cpu_spp = args.cpu_spp or CPU_SPP.get(args.workload, 4)
         ms, mr, t = run_cpu_reference(sc, st, cpu_spp, threads, args.steps, args.warmup)
         config["triangles"] = sc.triangle_count()
+        config["partition"] = f"64x64 tiles popped from a queue by {threads} host threads (lib.rs:481-504, 706-805)"
+        config["l2"] = "n/a (host cores)"
         line = {"impl": "reference", "metric": "Msamples/s", "value": ms, "unit": "Msamples/s", "mrays_per_s": mr, "n_gpus": 0,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": DATA_NOTE,

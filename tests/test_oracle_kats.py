@@ -63,6 +63,38 @@ def test_fxhash_structure(oracle):
     assert oracle.lib().oracle_fxhash_u32x3(3, 5, 7) == rotl(h, 26)
 
 
+def test_fxhasher_constants_against_compiled_rustc_hash():
+    """Evidence for the two constants the reference's tests do not pin (multiplier K and the rotate of
+    `finish`): Rust extension modules in this image that link rustc-hash 2.x (tokenizers, tiktoken, outlines_core) carry K as a
+    64-bit immediate, and the `rol r64, 26` of `finish()` follows it. rustc-hash 2.0.0 rotated by 20; 1.x used another K."""
+    import glob
+    import importlib.util
+    K = bytes.fromhex("c5a9622eea7a35f1")           # 0xf1357aea2e62a9c5, little endian
+    files = []
+    for mod in ("tiktoken", "tokenizers", "outlines_core"):
+        spec = importlib.util.find_spec(mod)
+        if spec and spec.submodule_search_locations:
+            for d in spec.submodule_search_locations:
+                files += glob.glob(d + "/*.so")
+    if not files:
+        pytest.skip("no Rust extension module with rustc-hash in this environment")
+    rol26 = rol20 = with_k = 0
+    for f in files:
+        data = open(f, "rb").read()
+        i = data.find(K)
+        while i >= 0:
+            with_k += 1
+            window = data[i + 8:i + 96]
+            for j in range(len(window) - 3):   # rol r64, imm8 = REX.W(48/49) C1 /0 ib
+                if window[j] in (0x48, 0x49) and window[j + 1] == 0xC1 and 0xC0 <= window[j + 2] <= 0xC7:
+                    rol26 += window[j + 3] == 26
+                    rol20 += window[j + 3] == 20
+            i = data.find(K, i + 8)
+    if not with_k:
+        pytest.skip("rustc-hash 2.x not linked into the Rust extension modules found")
+    assert rol26 >= 5 and rol20 == 0, (with_k, rol26, rol20)
+
+
 def test_uniform_f32_is_24bit(oracle, rc):
     st = rc.RaytracerSettings().to_c()
     out = (C.c_float * 64)()

@@ -70,7 +70,10 @@ struct BuildCtx {
     uint32_t* ploc_out;         // [0] clusters after this round, [1] merges of this round
 };
 
-constexpr int PLOC_RADIUS = 16;
+#ifndef RT_PLOC_RADIUS
+#define RT_PLOC_RADIUS 16
+#endif
+constexpr int PLOC_RADIUS = RT_PLOC_RADIUS;
 
 RT_HD uint32_t instance_of_prim(const BuildCtx& b, uint32_t i) {
     uint32_t lo = 0, hi = b.instance_count;  // last instance with prim_base <= i

@@ -329,6 +329,9 @@ typedef struct rtcuda_stats {
      * crates/raytracing-cpu/src/lib.rs:294-298, 318-322) and were not traced; NOT counted in bounce_rays. The reference
      * traces them: bounce_rays + final_rays_skipped is its bounce-ray count. */
     uint64_t final_rays_skipped;
+    /* 1 when the PLOC tree of the last upload was deeper than the traversal stack covers and the scene was rebuilt as an
+     * LBVH (same pixels, usually more node fetches per ray). */
+    uint64_t bvh_fallback_lbvh;
 } rtcuda_stats;
 
 typedef struct rtcuda_ctx rtcuda_ctx;

@@ -129,7 +129,7 @@ class Stats(C.Structure):
                 ("shadow_launches", C.c_uint64), ("render_ms", C.c_double), ("bvh_build_ms", C.c_double),
                 ("upload_ms", C.c_double), ("extend_ms", C.c_double), ("shade_ms", C.c_double),
                 ("shadow_ms", C.c_double), ("other_ms", C.c_double), ("bvh_node_count", C.c_uint64),
-                ("bvh_prim_count", C.c_uint64), ("nonfinite_values", C.c_uint64), ("primary_rays_culled", C.c_uint64), ("final_rays_skipped", C.c_uint64)]
+                ("bvh_prim_count", C.c_uint64), ("nonfinite_values", C.c_uint64), ("primary_rays_culled", C.c_uint64), ("final_rays_skipped", C.c_uint64), ("bvh_fallback_lbvh", C.c_uint64)]
 
 
 STATS_COUNTERS, STATS_KERNEL_TIMES = 1, 2

@@ -442,7 +442,11 @@ void build_bvh(rtcuda_scene* s, const std::vector<Instance>& instances, uint32_t
     launch_morton(st, b, s->lc);
     launch_sort(st, sort_temp.p, temp_bytes, keys.p, keys_sorted.p, vals.p, vals_sorted.p, n, s->lc);
     const char* builder = std::getenv("RTCUDA_BUILDER");   // A/B aid: "lbvh" selects the Karras tree + refit
-    if (builder && std::strcmp(builder, "lbvh") == 0) {
+    bool use_lbvh = builder && std::strcmp(builder, "lbvh") == 0;
+    uint32_t h_counters[4];
+  for (;;) {   // PLOC first; a tree deeper than the traversal stack covers is rebuilt as an LBVH (depth bounded by the key length)
+    if (use_lbvh) {
+        CK(cudaMemsetAsync(visit.p, 0, (size_t)n * 4, st));
         launch_karras(st, b, s->lc);
         launch_refit(st, b, s->lc);
     } else {
@@ -471,16 +475,17 @@ void build_bvh(rtcuda_scene* s, const std::vector<Instance>& instances, uint32_t
     // collapse, one launch per wide level
     WorkItem root{0u, 0u};
     CK(cudaMemcpyAsync(queue_a.p, &root, sizeof root, cudaMemcpyHostToDevice, st));
-    uint32_t h_counters[4] = {0u, 1u, 0u, 0u};  // next-level size, wide nodes (root allocated), packed prims
+    h_counters[0] = 0u; h_counters[1] = 1u; h_counters[2] = 0u; h_counters[3] = 0u;  // next-level size, wide nodes (root allocated), packed prims
     CK(cudaMemcpyAsync(counters.p, h_counters, sizeof h_counters, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));   // h_counters is reused as the read-back target below
     uint32_t n_items = 1, n_levels = 0;
+    bool too_deep = false;
     WorkItem* qin = queue_a.p;
     WorkItem* qout = queue_b.p;
     while (n_items) {
         // a ray holds at most two stack entries per level of the wide tree (the rest of a node group and a postponed
         // primitive group, rt_traverse.h): deeper trees than the traversal stack covers are refused, not overrun
-        if (++n_levels > (uint32_t)(TRAVERSE_STACK / 2 - 1))
-            throw RtError{RTCUDA_ERR_UNSUPPORTED, "wide BVH deeper than the traversal stack allows (degenerate primitive distribution)"};
+        if (++n_levels > (uint32_t)(TRAVERSE_STACK / 2 - 1)) { too_deep = true; break; }
         b.queue_in = qin;
         b.queue_out = qout;
         launch_collapse(st, b, n_items, s->lc);
@@ -491,6 +496,12 @@ void build_bvh(rtcuda_scene* s, const std::vector<Instance>& instances, uint32_t
         CK(cudaMemcpyAsync(counters.p, &zero, 4, cudaMemcpyHostToDevice, st));
         std::swap(qin, qout);
     }
+    if (!use_lbvh && std::getenv("RTCUDA_TEST_PLOC_TOO_DEEP")) too_deep = true;   // test hook for the fallback below
+    if (!too_deep) break;
+    if (use_lbvh) throw RtError{RTCUDA_ERR_UNSUPPORTED, "wide BVH deeper than the traversal stack allows (degenerate primitive distribution)"};
+    use_lbvh = true;
+    s->stats.bvh_fallback_lbvh = 1;
+  }
     if (h_counters[2] != n) throw RtError{RTCUDA_ERR_CUDA, "BVH build lost primitives"};
     s->sc.node_count = h_counters[1];
     s->stats.bvh_node_count = h_counters[1];

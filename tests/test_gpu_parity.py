@@ -380,6 +380,13 @@ def test_builders_give_identical_frames(rc, monkeypatch):
     for plane in ("beauty", "normals", "debug_ids", "debug_depth"):
         assert np.array_equal(getattr(a, plane), getattr(b, plane)), plane
     assert sa["nodes_fetched"] < 0.8 * sb["nodes_fetched"]
+    assert sa["bvh_fallback_lbvh"] == 0 and sb["bvh_fallback_lbvh"] == 0
+    # a PLOC tree deeper than the traversal stack covers is rebuilt as an LBVH instead of refusing the scene
+    monkeypatch.delenv("RTCUDA_BUILDER")
+    monkeypatch.setenv("RTCUDA_TEST_PLOC_TOO_DEEP", "1")
+    c, sc_stats = gpu_render(rc, sc, st, collect_stats=1)
+    assert sc_stats["bvh_fallback_lbvh"] == 1 and abs(sc_stats["nodes_fetched"] - sb["nodes_fetched"]) < 0.01 * sb["nodes_fetched"]
+    assert np.array_equal(c.beauty, a.beauty) and np.array_equal(c.debug_ids, a.debug_ids)
 
 
 def test_cached_memory_release(rc):

@@ -160,7 +160,7 @@ def main():
     part = (f"{tile}x{tile} tiles round-robin" if args.partition == "tiles" else "sample ranges of every pixel")
     config = {"workload": f"{args.workload}: {what} {W}x{H}, {spp} spp, depth {depth}, light samples {ls}, "
                           f"independent sampler, seed 42",
-              "triangles": None, "partition": f"{part} over {world} GPU(s), scene replicated, 1 NCCL sum-reduce per frame",
+              "triangles": None, "partition": f"{part} over {world} GPU(s), scene replicated, 1 NCCL collective per frame (tiles: gather of the owned pixels to rank 0; samples: sum-reduce)",
               "l2": "every step re-streams ~17 GB of wavefront state per batch through L2 (>> 126 MB) and a 512 MiB buffer is "
                     "written between timed steps; the 3 MB BVH is L2-resident by design"}
 
@@ -205,7 +205,7 @@ def main():
             torch.cuda.synchronize()
 
     def one_step():
-        """render this rank's tiles into HBM planes + (N > 1) one NCCL sum-reduce to rank 0. Device ms of the step = the
+        """render this rank's tiles into HBM planes + (N > 1) one NCCL collective to rank 0 (DistributedRenderer.combine). Device ms of the step = the
         library's CUDA events around the whole render on its launching stream (rtcuda_stats.render_ms: every kernel of
         every batch plus the launch gaps between them) + (N > 1) torch CUDA events around the reduce, taken after a
         barrier so that the wait for a slower rank is not counted twice (the job time is the max over ranks anyway)."""
@@ -219,10 +219,12 @@ def main():
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            rc.multi_gpu.reduce_planes(planes, dst=0)
+            dr.combine(planes)   # tiles: gather of the owned pixels to rank 0; samples: sum-reduce
             e1.record()
             torch.cuda.synchronize()
-            ms += e0.elapsed_time(e1)
+            red = e0.elapsed_time(e1)
+            ms += red
+            stats = dict(stats, reduce_ms=red)
         return ms, stats
 
     for _ in range(args.warmup):
@@ -237,8 +239,8 @@ def main():
         ms, stats = one_step()
         total_ms += ms
         for k in ("samples", "primary_rays", "bounce_rays", "shadow_rays", "kernel_launches", "extend_launches", "extend_ms",
-                  "shade_ms", "shadow_ms", "other_ms", "render_ms"):
-            agg[k] = agg.get(k, 0) + stats[k]
+                  "shade_ms", "shadow_ms", "other_ms", "render_ms", "reduce_ms"):
+            agg[k] = agg.get(k, 0) + stats.get(k, 0.0)
     sync_all()
     wall = time.time() - wall0
     clocks.stop_flag = True
@@ -278,7 +280,7 @@ def main():
                 e2e_each.append({"call_ms": 1e3 * (time.time() - t_call)})
             return out
         e2e_what = ("raytracing_cuda.multi_gpu.render_distributed(scene, settings, rank, world) on every rank: rtcuda_init + scene_upload "
-                    "(H2D, device BVH build) + render of the rank's share + NCCL sum-reduce + D2H frame on rank 0")
+                    "(H2D, device BVH build) + render of the rank's share + NCCL collective + D2H frame on rank 0")
     if args.warmup:
         e2e_call(False)   # one untimed call: the first allocation of a second set of path-state buffers pays the driver's page mapping
     sync_all()
@@ -335,6 +337,7 @@ def main():
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": DATA_NOTE, "config": config,
             "wall_s_timed_region": wall, "clocks": clocks.summary(),
+            "rank0_ms_per_step": {"render": agg["render_ms"] / args.steps, "collective": agg["reduce_ms"] / args.steps},
             "e2e": {"value": (W * H * spp * e2e_steps) / e2e_s / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps, "breakdown": e2e_each,
                     "what": e2e_what},

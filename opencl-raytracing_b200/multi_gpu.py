@@ -1,8 +1,10 @@
 """Multi-GPU rendering: the scene is replicated on every GPU, square image tiles are dealt round-robin to the
 ranks (tile i -> rank i % world, the tile grid of create_render_jobs, crates/raytracing-cpu/src/lib.rs:481-504;
 64x64 like the reference's RenderTile unless `tile_size` asks for a finer deal), and the tile-disjoint frames are
-combined with ONE sum-reduce of each plane to rank 0 over NCCL / NVLink. Pixels a rank does not own are exactly 0
-in its frame, so the sum is a gather and is bit-exact.
+combined with ONE collective per frame over NCCL / NVLink: every rank sends only the pixels it owns (all planes packed
+side by side) and rank 0 copies them into its frame (`gather_tiles`) — bit-exact, 1/world of a frame per rank on the
+wire. (`reduce_planes`, the sum of the zero-filled full frames, gives the same bits with world times the traffic; it
+serves the sample partition, whose partial sums really have to be added.)
 
 Alternate partition (small rasters / high spp): `partition="samples"` gives rank r the sample range
 [r * spp / world, (r + 1) * spp / world) of EVERY pixel; the un-normalised sums are reduced and rank 0 multiplies by
@@ -50,6 +52,43 @@ def reduce_planes(planes: dict, group=None, dst: int = 0) -> None:
         dist.reduce(planes[name], dst=dst, op=dist.ReduceOp.SUM, group=group)
 
 
+def owned_pixel_indices(width: int, height: int, world: int, tile: int = 64) -> list:
+    """Per rank, the flat (y * W + x) indices of the pixels it renders, ascending (numpy int64)."""
+    own = tile_owner_map(width, height, world, tile).reshape(-1)
+    return [np.flatnonzero(own == r) for r in range(max(1, world))]
+
+
+def gather_tiles(planes: dict, owned: list, counts: list, rank: int, world: int, group=None, dst: int = 0) -> None:
+    """Tile partition: every rank sends ONLY the pixels it owns (all planes packed side by side, one collective per frame)
+    and `dst` copies them into its full-frame planes — the frames are tile-disjoint, so this is the same result as summing
+    them (`reduce_planes`), bit for bit, with 1/world of the traffic per rank. `owned[r]` = index tensor (same device as the
+    planes) of rank r's pixels, `counts[r]` its length; ranks other than `dst` only need their own `owned` entry."""
+    import torch
+    import torch.distributed as dist
+    names = sorted(planes)
+    if not names or world <= 1:
+        return
+    chans = [planes[n].shape[-1] for n in names]
+    maxc = max(counts)
+    first = planes[names[0]]
+    send = torch.zeros((maxc, sum(chans)), dtype=first.dtype, device=first.device)
+    c0 = 0
+    for n, c in zip(names, chans):
+        send[:counts[rank], c0:c0 + c] = planes[n].reshape(-1, c).index_select(0, owned[rank])
+        c0 += c
+    recv = [torch.empty_like(send) for _ in range(world)] if rank == dst else None
+    dist.gather(send, recv, dst=dst, group=group)
+    if rank != dst:
+        return
+    for r in range(world):
+        if r == dst:
+            continue
+        c0 = 0
+        for n, c in zip(names, chans):
+            planes[n].reshape(-1, c).index_copy_(0, owned[r], recv[r][:counts[r], c0:c0 + c])
+            c0 += c
+
+
 class DistributedRenderer:
     """One process per GPU (torchrun): rank r owns tiles r, r+world, ...; `render()` returns the full
     RenderOutput on rank 0 (None elsewhere). Frames stay in HBM between the render and the NCCL reduce
@@ -68,6 +107,8 @@ class DistributedRenderer:
         self.renderer = CudaRenderer(scene, bs)
         self.width, self.height = self.renderer.width, self.renderer.height
         self._planes = {}
+        self._owned = None
+        self.tile = backend_kw.get("tile_size", 0) or 64
 
     def planes_for(self, outputs: AovFlags) -> dict:
         torch = self.torch
@@ -105,10 +146,23 @@ class DistributedRenderer:
         self.renderer.render_device(settings, {k: v.data_ptr() for k, v in planes.items()})
         return planes
 
+    def combine(self, planes: dict, group=None) -> None:
+        """Bring the ranks' shares together on rank 0: a gather of the owned pixels for the tile partition (1/world of a
+        frame per rank on the wire), a sum-reduce of the partial sums for the sample partition."""
+        if self.world <= 1:
+            return
+        if self.partition == "samples":
+            reduce_planes(planes, group=group, dst=0)
+            return
+        if self._owned is None:
+            idx = owned_pixel_indices(self.width, self.height, self.world, self.tile)
+            self._owned = [self.torch.from_numpy(i).to(self.device) if (r == self.rank or self.rank == 0) else None for r, i in enumerate(idx)]
+            self._counts = [len(i) for i in idx]
+        gather_tiles(planes, self._owned, self._counts, self.rank, self.world, group=group, dst=0)
+
     def render(self, settings: RaytracerSettings, group=None) -> Optional[RenderOutput]:
         planes = self.render_local(settings)
-        if self.world > 1:
-            reduce_planes(planes, group=group, dst=0)
+        self.combine(planes, group=group)
         if self.rank != 0:
             return None
         out = RenderOutput(self.width, self.height)
@@ -124,8 +178,8 @@ class DistributedRenderer:
 def render_distributed(scene, settings: RaytracerSettings, rank: int, world: int, device_id: Optional[int] = None, group=None,
                        **kw) -> Optional[RenderOutput]:
     """The one-shot call of a torchrun job (the multi-GPU analogue of `render(scene, settings)`): every rank uploads the
-    scene to its GPU and builds the BVH there, renders its tiles into HBM planes, ONE NCCL sum-reduce per plane, and rank 0
-    copies the frame to the host (None on the other ranks)."""
+    scene to its GPU and builds the BVH there, renders its tiles into HBM planes, ONE NCCL collective per frame (`combine`),
+    and rank 0 copies the frame to the host (None on the other ranks)."""
     dr = DistributedRenderer(scene, rank, world, device_id=device_id, **kw)
     try:
         return dr.render(settings, group=group)

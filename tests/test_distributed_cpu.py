@@ -33,11 +33,16 @@ def _worker(rank, world, port, ret):
     bs = rc.multi_gpu.backend_settings_for_rank(rank, world)
     out, _ = hostsim_py.render(sc, st, tile_rank=bs.tile_rank, tile_world=bs.tile_world)
     planes = {"beauty": torch.from_numpy(out.beauty.copy()), "normals": torch.from_numpy(out.normals.copy())}
+    gathered = {k: v.clone() for k, v in planes.items()}
     rc.multi_gpu.reduce_planes(planes, dst=0)
+    # the collective the tile partition uses: only the owned pixels travel
+    idx = rc.multi_gpu.owned_pixel_indices(160, 130, world)
+    rc.multi_gpu.gather_tiles(gathered, [torch.from_numpy(i) for i in idx], [len(i) for i in idx], rank, world, dst=0)
     if rank == 0:
         full, _ = hostsim_py.render(sc, st)
         ret["beauty_equal"] = bool(np.array_equal(planes["beauty"].numpy(), full.beauty))
         ret["normals_equal"] = bool(np.array_equal(planes["normals"].numpy(), full.normals))
+        ret["gather_equal"] = bool(np.array_equal(gathered["beauty"].numpy(), full.beauty) and np.array_equal(gathered["normals"].numpy(), full.normals))
         owner = rc.multi_gpu.tile_owner_map(160, 130, world)
         ret["mine_only"] = bool((out.beauty[owner != 0] == 0).all())
     dist.barrier()
@@ -49,4 +54,4 @@ def test_two_ranks_tile_partition_and_reduce(hostsim):
     mgr = mp.Manager()
     ret = mgr.dict()
     mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
-    assert ret["beauty_equal"] and ret["normals_equal"] and ret["mine_only"]
+    assert ret["beauty_equal"] and ret["normals_equal"] and ret["mine_only"] and ret["gather_equal"]

@@ -349,10 +349,10 @@ RT_HD bool raygen_body(uint32_t slot, const SceneD& sc, const RenderParams& rp, 
 // ---- shade: one iteration of the ray_radiance loop after traverse_bvh (lib.rs:284-391) ------------------
 // A vertex can emit three kinds of output: a continuation ray, up to K shadow rays, and one NEE vertex record.
 // Their queue positions come from `alloc`, which every thread of the launch calls exactly once per queue chunk
-// (on the device it is a block-wide scan + one global atomic per queue per block, kernels.cu; the CPU harness
-// hands out running counters). To know the shadow-ray count before the positions, the light samples are
-// evaluated twice from the same sampler state: a counting pass, then a writing pass — shade is bound by the
-// latency of its dependent loads, not by issue slots, so the recomputation is cheaper than staging the entries.
+// (on the device it is a warp scan + two global atomics per warp, kernels.cu; the CPU harness hands out running
+// counters). The shadow-ray count has to be known before the positions: with up to NEE_STAGE light samples per vertex
+// the entries are evaluated once and staged in thread-local memory until `alloc` returns (nee_pass<1>); with more, a
+// counting pass and a writing pass draw the same numbers from the same sampler state (nee_pass<0>, nee_pass<2>).
 template <typename Surf>
 struct ShadeState {
     uint32_t slot, flags, sidx;

@@ -250,6 +250,12 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    per_rank = None
+    if world > 1:   # every rank's own device time per step (balance of the deal), gathered for the report
+        mine = torch.tensor([agg["render_ms"] / args.steps], dtype=torch.float64, device=f"cuda:{local_rank}")
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = [round(float(x.item()), 3) for x in allr]
     job_s = float(t.item()) / 1e3
     samples, rays, launches = (float(x) for x in cnt.tolist())
 
@@ -338,6 +344,7 @@ def main():
             "data": DATA_NOTE, "config": config,
             "wall_s_timed_region": wall, "clocks": clocks.summary(),
             "rank0_ms_per_step": {"render": agg["render_ms"] / args.steps, "collective": agg["reduce_ms"] / args.steps},
+            "render_ms_per_rank": per_rank,
             "e2e": {"value": (W * H * spp * e2e_steps) / e2e_s / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps, "breakdown": e2e_each,
                     "what": e2e_what},

@@ -267,9 +267,10 @@ enum {
 typedef struct rtcuda_backend_settings {
     int32_t device_id;                /* CUDA device ordinal */
     uint32_t max_paths_in_flight;     /* wavefront size; 0 => default */
-    /* Image-tile partition for multi-GPU: this context renders the 64x64 tiles
-     * (row-major tile order, crates/raytracing-cpu/src/lib.rs:481-504) whose index i satisfies
-     * i % tile_world == tile_rank; all other pixels are left 0 so frames can be summed. */
+    /* Image-tile partition for multi-GPU: this context renders the tiles (tx, ty) of the row-major tile
+     * grid (crates/raytracing-cpu/src/lib.rs:481-504) with (ty * stride + tx) % tile_world == tile_rank, where stride is
+     * the number of tiles per row, plus one when that number is a multiple of tile_world (so that ranks do not own whole
+     * tile columns); all other pixels are left 0 so frames can be summed or gathered. */
     uint32_t tile_rank;
     uint32_t tile_world;              /* 0 or 1 => whole image */
     uint32_t collect_stats;           /* RTCUDA_STATS_* bits */

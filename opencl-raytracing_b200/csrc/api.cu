@@ -712,6 +712,10 @@ void build_pixel_list(rtcuda_scene* s) {
     while ((1u << ts_bits) < TS) ts_bits++;
     const uint32_t tiles_x = (W + TS - 1) / TS, tiles_y = (H + TS - 1) / TS;
     const uint32_t world = std::max(1u, s->ctx->bs.tile_world), rank = s->ctx->bs.tile_rank;
+    // Round-robin over the row-major tile index — with one idle slot per tile row when the row length is a multiple of the
+    // world size: otherwise every rank would own whole tile COLUMNS and a scene that covers 7.5 periods of them gives half
+    // the ranks 8 heavy columns and the other half 7 (C3 at 8 ranks: 37.8 vs 41.5 ms per frame, profiles/r2m_bench_c3_n8.json).
+    const uint32_t stride = tiles_x + (world > 1 && tiles_x % world == 0 ? 1u : 0u);
     std::vector<uint32_t> list;
     list.reserve((size_t)W * H / world + TS * TS);
     std::vector<uint16_t> mx(TS * TS), my(TS * TS);
@@ -726,7 +730,7 @@ void build_pixel_list(rtcuda_scene* s) {
     }
     for (uint32_t ty = 0; ty < tiles_y; ty++)
         for (uint32_t tx = 0; tx < tiles_x; tx++) {
-            if ((ty * tiles_x + tx) % world != rank) continue;
+            if ((ty * stride + tx) % world != rank) continue;
             for (uint32_t m = 0; m < TS * TS; m++) {
                 uint32_t x = tx * TS + mx[m], y = ty * TS + my[m];
                 if (x < W && y < H) list.push_back((y << 16) | x);

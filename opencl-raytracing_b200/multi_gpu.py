@@ -25,11 +25,17 @@ from .backend import CudaBackendSettings, CudaRenderer
 from .renderer import AovFlags, RaytracerSettings, RenderOutput
 
 
+def tile_row_stride(tiles_x: int, world: int) -> int:
+    """Tile (tx, ty) belongs to rank (ty * stride + tx) % world: the row-major round-robin of the tile index, with one idle
+    slot per tile row when the row length is a multiple of the world size (else every rank would own whole tile columns)."""
+    return tiles_x + (1 if world > 1 and tiles_x % world == 0 else 0)
+
+
 def tile_owner_map(width: int, height: int, world: int, tile: int = 64) -> np.ndarray:
     """[H, W] array of the rank that renders each pixel."""
     tiles_x = (width + tile - 1) // tile
     ty, tx = np.meshgrid(np.arange(height) // tile, np.arange(width) // tile, indexing="ij")
-    return ((ty * tiles_x + tx) % max(1, world)).astype(np.int32)
+    return ((ty * tile_row_stride(tiles_x, world) + tx) % max(1, world)).astype(np.int32)
 
 
 def backend_settings_for_rank(rank: int, world: int, device_id: Optional[int] = None, **kw) -> CudaBackendSettings:
@@ -154,10 +160,14 @@ class DistributedRenderer:
         if self.partition == "samples":
             reduce_planes(planes, group=group, dst=0)
             return
-        if self._owned is None:
-            idx = owned_pixel_indices(self.width, self.height, self.world, self.tile)
-            self._owned = [self.torch.from_numpy(i).to(self.device) if (r == self.rank or self.rank == 0) else None for r, i in enumerate(idx)]
-            self._counts = [len(i) for i in idx]
+        if self._owned is None:   # on the device: a one-shot call must not spend tens of ms of numpy on an index table
+            t = self.torch
+            tiles_x = (self.width + self.tile - 1) // self.tile
+            ty = t.arange(self.height, device=self.device) // self.tile
+            tx = t.arange(self.width, device=self.device) // self.tile
+            owner = ((ty[:, None] * tile_row_stride(tiles_x, self.world) + tx[None, :]) % self.world).reshape(-1)
+            self._counts = t.bincount(owner, minlength=self.world).tolist()
+            self._owned = [t.nonzero(owner == r).reshape(-1) if (r == self.rank or self.rank == 0) else None for r in range(self.world)]
         gather_tiles(planes, self._owned, self._counts, self.rank, self.world, group=group, dst=0)
 
     def render(self, settings: RaytracerSettings, group=None) -> Optional[RenderOutput]:

@@ -373,7 +373,7 @@ int hostsim_render(const rtcuda_scene_desc* d, const rtcuda_settings* st, rtcuda
     const uint32_t tiles_x = (W + TS - 1) / TS, tiles_y = (H + TS - 1) / TS;
     for (uint32_t ty = 0; ty < tiles_y; ty++)
         for (uint32_t tx = 0; tx < tiles_x; tx++) {
-            if ((ty * tiles_x + tx) % tile_world != tile_rank) continue;
+            if ((ty * (tiles_x + (tile_world > 1 && tiles_x % tile_world == 0 ? 1u : 0u)) + tx) % tile_world != tile_rank) continue;
             for (uint32_t m = 0; m < TS * TS; m++) {
                 uint32_t x = 0, y = 0;
                 for (uint32_t bit = 0; bit < 6; bit++) { x |= ((m >> (2 * bit)) & 1u) << bit; y |= ((m >> (2 * bit + 1)) & 1u) << bit; }

@@ -249,6 +249,9 @@ struct Traversal {
         tgroup.y &= tgroup.y - 1u;
         const uint32_t pi = tgroup.x + (uint32_t)b;
         RT_CHECK(pi < sc.prim_count);
+#ifdef RT_TRACE_PRIM_HOOK   // CPU harness only (tests/hostsim): which primitives a ray tests
+        RT_TRACE_PRIM_HOOK(pi);
+#endif
         const Prim* pr = sc.prims + pi;
         const float4 pa = ldg(&pr->a), pb = ldg(&pr->b), pc = ldg(&pr->c);
         if (STATS) stats->prims++;

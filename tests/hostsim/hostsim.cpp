@@ -11,6 +11,11 @@
 #include <numeric>
 #include <vector>
 
+#include <vector>
+#include <cstdint>
+// HOSTSIM_STRUCTURAL=1: classify the primitives shadow rays test (profiles/r1_notes.md, "structural" tests)
+static thread_local std::vector<uint32_t>* g_prim_trace = nullptr;
+#define RT_TRACE_PRIM_HOOK(pi) do { if (g_prim_trace) g_prim_trace->push_back(pi); } while (0)
 #include "../../include/rtcuda.h"
 #include "../../opencl-raytracing_b200/csrc/rt_build.h"
 #include "../../opencl-raytracing_b200/csrc/rt_integrator.h"
@@ -451,21 +456,55 @@ int hostsim_render(const rtcuda_scene_desc* d, const rtcuda_settings* st, rtcuda
                     }
                     if (depth) stats[1] += n_rays;
                     const TraverseStats ts_mid = ts;
-                    uint32_t n_out = 0, n_shadow = 0, n_sray = 0;
+                    uint32_t n_out = 0, n_shadow = 0, n_sray = 0, cur_q = 0;
+                    static const bool structural = std::getenv("HOSTSIM_STRUCTURAL") != nullptr;
+                    std::vector<uint32_t> vertex_prim;
                     auto alloc = [&](bool cont, bool has_vertex, uint32_t k, bool final_skipped, uint32_t& rpos, uint32_t& vpos, uint32_t& first) {
                         rpos = n_out; vpos = n_shadow; first = n_sray;
+                        if (structural && has_vertex) vertex_prim.push_back(f2u(hits[cur_q].y));
                         n_out += cont; n_shadow += has_vertex; n_sray += k;
                         stats[1] += final_skipped;   // reported with the bounce rays: the oracle (like the reference) traces them
                     };
                     for (uint32_t q = 0; q < n_rays; q++) {
+                        cur_q = q;
                         if (sc.all_diffuse) shade_vertex<DiffuseSurface>(true, q, sc, rp, w, alloc);
                         else shade_vertex<Surface>(true, q, sc, rp, w, alloc);
                     }
                     uint32_t shadow_rays = 0;
                     std::vector<SimRay> sim;
+                    std::vector<uint32_t> ray_vertex;
+                    if (structural) {
+                        ray_vertex.assign(n_sray, 0u);
+                        for (uint32_t v = 0; v < n_shadow; v++) for (uint32_t j = 0; j < svertex[v].z; j++) ray_vertex[svertex[v].y + j] = v;
+                    }
+                    std::vector<uint32_t> trace;
                     for (uint32_t r = 0; r < n_sray; r++) {   // k_shadow
                         if (!(sray_o[r].w >= 0.0f)) continue;
                         shadow_rays++;
+                        if (structural) {   // one extra walk that records the primitives tested, classified against the ray's two end points
+                            static uint64_t c_rays = 0, c_total = 0, c_emitter = 0, c_exact = 0, c_same_geom = 0, c_other = 0, c_occluded = 0;
+                            trace.clear();
+                            g_prim_trace = &trace;
+                            Hit hh;
+                            TraverseStats dummy{0, 0};
+                            const bool occ = traverse<true, true>(sc, xyz(sray_o[r]), xyz(sray_d[r]), 0.001f, sray_o[r].w, hh, &dummy);
+                            g_prim_trace = nullptr;
+                            const uint32_t vp = vertex_prim[ray_vertex[r]];
+                            const uint32_t vgeom = f2u(sc.prims[vp].a.w);
+                            for (uint32_t pi : trace) {
+                                const uint32_t geom = f2u(sc.prims[pi].a.w);
+                                c_total++;
+                                if (pi == vp) c_exact++;
+                                else if (geom == vgeom) c_same_geom++;
+                                else if (sc.instances[geom].area_light != NONE) c_emitter++;
+                                else c_other++;
+                            }
+                            c_rays++; c_occluded += occ;
+                            if (r + 1 == n_sray)
+                                std::fprintf(stderr, "structural (cumulative): shadow rays %llu occluded %llu | prim tests %llu = end-point triangle %llu + same instance as the end point %llu + emitter instance %llu + other %llu\n",
+                                             (unsigned long long)c_rays, (unsigned long long)c_occluded, (unsigned long long)c_total, (unsigned long long)c_exact,
+                                             (unsigned long long)c_same_geom, (unsigned long long)c_emitter, (unsigned long long)c_other);
+                        }
                         if (std::getenv("HOSTSIM_WARPSIM")) sim.push_back(SimRay{xyz(sray_o[r]), xyz(sray_d[r]), 0.001f, sray_o[r].w});
                         Hit h;
                         if (traverse<true, true>(sc, xyz(sray_o[r]), xyz(sray_d[r]), 0.001f, sray_o[r].w, h, &ts)) scontrib[r] = make_float4(0, 0, 0, 0);

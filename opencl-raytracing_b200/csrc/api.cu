@@ -693,14 +693,6 @@ void upload_scene(rtcuda_scene* s, const rtcuda_scene_desc* d) {
     build_bvh(s, instances, (uint32_t)n_prims);
     sc.nodes = s->nodes.p;
     sc.prims = s->prims.p;
-    if (n_prims && sc.skip_planar) {   // which planar instances sit contiguously in the packed primitive order
-        DevBuf<uint32_t> rlo, rhi;
-        rlo.alloc(d->instance_count); rhi.alloc(d->instance_count);
-        CK(cudaMemsetAsync(rlo.p, 0xff, (size_t)d->instance_count * 4, st));
-        CK(cudaMemsetAsync(rhi.p, 0, (size_t)d->instance_count * 4, st));
-        launch_instance_ranges(st, sc, s->instances.p, rlo.p, rhi.p, s->lc);
-        CK(cudaStreamSynchronize(st));
-    }
     sc.shade_recs = nullptr;
     if (n_prims) {
         s->shade_recs.alloc(n_prims);

@@ -271,8 +271,7 @@ __global__ void __launch_bounds__(BLOCK, SHADOW_BLOCKS) k_shadow(const __grid_co
                     const float4 o4 = w.sray_o[q], d4 = w.sray_d[q];
                     if (o4.w >= 0.0f) {   // negative: never occluded (non-finite origin quirk), not traced
                         n_rays++;
-                        const uint32_t ids = f2u(d4.w);
-                        have = tr.init(sc, xyz(o4), xyz(d4), 0.001f, o4.w, skip_range(sc, ids & 0xffffu), skip_range(sc, ids >> 16)) ? 1u : 0u;
+                        have = tr.init(sc, xyz(o4), xyz(d4), 0.001f, o4.w, f2u(d4.w)) ? 1u : 0u;
                     }
                 }
             }
@@ -450,32 +449,6 @@ void launch_light_tris(cudaStream_t st, const ShapeD* shapes, uint32_t shape, ui
     if (!tri_count) return;
     k_light_tris<<<grid_for(tri_count), BLOCK, 0, st>>>(shapes, shape, tri_count, vertices, tris, out);
     lc.launches++;
-}
-
-// Packed-primitive range of the small planar instances (Instance::skip_lo / skip_n): min / max packed index per candidate
-// instance, then one thread per instance keeps the range if the tree packed all its triangles contiguously.
-__global__ void __launch_bounds__(BLOCK) k_instance_range_minmax(const __grid_constant__ SceneD sc, uint32_t* lo, uint32_t* hi) {
-    const uint32_t p = blockIdx.x * BLOCK + threadIdx.x;
-    if (p >= sc.prim_count) return;
-    const uint32_t g = f2u(sc.prims[p].a.w);
-    const Instance& in = sc.instances[g];
-    if (in.kind != 0u || in.tri_count == 0u || in.tri_count > 3u || !(in.plane[3] < 3.0e38f)) return;
-    atomicMin(&lo[g], p);
-    atomicMax(&hi[g], p);
-}
-__global__ void __launch_bounds__(BLOCK) k_instance_range_store(Instance* instances, uint32_t n, const uint32_t* lo, const uint32_t* hi) {
-    const uint32_t g = blockIdx.x * BLOCK + threadIdx.x;
-    if (g >= n) return;
-    Instance& in = instances[g];
-    const bool ok = in.kind == 0u && in.tri_count >= 1u && in.tri_count <= 3u && in.plane[3] < 3.0e38f && lo[g] <= hi[g] && hi[g] - lo[g] + 1u == in.tri_count;
-    in.skip_lo = ok ? lo[g] : 0u;
-    in.skip_n = ok ? in.tri_count : 0u;
-}
-void launch_instance_ranges(cudaStream_t st, const SceneD& sc, Instance* instances, uint32_t* lo, uint32_t* hi, LaunchCounter& lc) {
-    if (!sc.prim_count || !sc.instance_count) return;
-    k_instance_range_minmax<<<grid_for(sc.prim_count), BLOCK, 0, st>>>(sc, lo, hi);
-    k_instance_range_store<<<grid_for(sc.instance_count), BLOCK, 0, st>>>(instances, sc.instance_count, lo, hi);
-    lc.launches += 2;
 }
 
 // upload-time validation of a mesh's triangle indices (api.cu: validate_desc leaves this to the device)

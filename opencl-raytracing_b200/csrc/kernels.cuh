@@ -39,7 +39,6 @@ size_t ploc_scan_temp_bytes(uint32_t n);
 void launch_ploc_round(cudaStream_t st, const BuildCtx& b, void* scan_temp, size_t scan_temp_bytes, LaunchCounter& lc);
 
 // emitter triangle table (rt_scene.h LightTri)
-void launch_instance_ranges(cudaStream_t st, const SceneD& sc, Instance* instances, uint32_t* lo, uint32_t* hi, LaunchCounter& lc);
 void launch_check_indices(cudaStream_t st, const uint32_t* idx, size_t n, uint32_t vertex_count, uint32_t* bad, LaunchCounter& lc);
 void launch_light_tris(cudaStream_t st, const ShapeD* shapes, uint32_t shape, uint32_t tri_count, const float* vertices, const uint32_t* tris,
                        LightTri* out, LaunchCounter& lc);

@@ -447,11 +447,11 @@ RT_HD uint32_t planar_skip_ids(const SceneD& sc, const LightD& light, uint32_t s
     const float mag = fmaxf(fmaxf(fmaxf(fabsf(from.x), fabsf(from.y)), fmaxf(fabsf(from.z), fabsf(to.x))), fmaxf(fabsf(to.y), fabsf(to.z)));
     const float eps = 7.6293945e-6f * mag;   // 64 * 2^-23
     uint32_t ids = 0xffffffffu;
-    if (light.kind == 2 && light.geom < 0xffffu && sc.instances[light.geom].skip_n) {
+    if (light.kind == 2 && light.geom < 0xffffu) {
         const float* p = sc.instances[light.geom].plane;
         if (p[3] + eps < 2.5e-4f * fabsf(dir.x * p[0] + dir.y * p[1] + dir.z * p[2])) ids = (ids & 0xffff0000u) | light.geom;
     }
-    if (surf_geom < 0xffffu && sc.instances[surf_geom].skip_n) {
+    if (surf_geom < 0xffffu) {
         const float* p = sc.instances[surf_geom].plane;
         if (p[3] + eps < 2.5e-4f * fabsf(dir.x * p[0] + dir.y * p[1] + dir.z * p[2])) ids = (ids & 0x0000ffffu) | (surf_geom << 16);
     }

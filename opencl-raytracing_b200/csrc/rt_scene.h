@@ -26,15 +26,13 @@ struct Instance {
     M4 w2o;       // Transform::inverse
     uint32_t shape, kind, material, area_light;
     uint32_t vertex_offset, tri_offset, normal_offset, uv_offset;
-    uint32_t tri_count, prim_base;   // prim_base: first build-primitive of this instance
-    uint32_t skip_lo, skip_n;        // planar instance of <= 3 triangles that the tree packed contiguously: first packed primitive, count (0 = none)
+    uint32_t tri_count, prim_base, _p0, _p1;   // prim_base: first build-primitive of this instance
     float center[3];
     float radius;
     // World-space plane of a PLANAR mesh instance (walls, quad lights): unit normal | the largest distance of any of its
     // vertices from the plane through the first one; w = +inf for everything else (instance_plane below). A shadow ray that
-    // starts or ends in such a plane and is not grazing cannot hit any triangle of the instance inside its t range:
-    // nee_pass names those instances in the ray record and k_shadow drops their packed primitives (skip_lo, skip_n) from the
-    // leaf hits of every node it visits, so the leaves holding only them are never entered.
+    // starts or ends in such a plane and is not grazing cannot hit any other triangle of the instance inside its t range:
+    // nee_pass names those instances in the ray record and k_shadow does not intersect their triangles.
     float plane[4];
 };
 

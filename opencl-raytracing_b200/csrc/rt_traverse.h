@@ -150,11 +150,11 @@ struct Traversal {
     Hit hit;
     uint32_t hit_geom, hit_pid;  // ids of the current closest hit (tie-break)
     uint32_t found;  // 32-bit flag (a bool would be packed into a half register)
-    uint32_t skip_a, skip_b;  // any-hit only: packed primitive ranges (first | count << 30, 0 = none) this ray cannot hit inside its range (planar_skip_ids)
+    uint32_t skip2;  // any-hit only: two 16-bit instance ids whose triangles this ray cannot hit inside its range (planar_skip_ids)
 
-    RT_HD bool init(const SceneD& sc, V3 o_, V3 d_, float t_min_, float t_max_, uint32_t skip_a_ = 0u, uint32_t skip_b_ = 0u) {
+    RT_HD bool init(const SceneD& sc, V3 o_, V3 d_, float t_min_, float t_max_, uint32_t skip2_ = 0xffffffffu) {
         o = o_; d = d_; t_min = t_min_; closest = t_max_;
-        skip_a = skip_a_; skip_b = skip_b_;
+        skip2 = skip2_;
         hit.prim = NONE; hit.t = t_max_; hit.u = hit.v = 0.0f;
         found = 0u;
         hit_geom = hit_pid = 0u;
@@ -243,20 +243,6 @@ struct Traversal {
         ngroup.y = (hitmask & 0xff000000u) | imask;
         tgroup.x = f2u(n1.y);
         tgroup.y = hitmask & 0x00ffffffu;
-        if (ANY_HIT) {   // primitives this ray provably cannot hit never become pending: their leaves are not entered
-            tgroup.y = drop_range(tgroup.y, tgroup.x, skip_a);
-            tgroup.y = drop_range(tgroup.y, tgroup.x, skip_b);
-        }
-    }
-
-    // clear the pending bits of the packed primitives [first, first + count) (packed = first | count << 30) in a node's
-    // leaf-hit mask, whose bit i stands for primitive base + i
-    RT_HD static uint32_t drop_range(uint32_t mask, uint32_t base, uint32_t packed) {
-        const uint32_t n = packed >> 30;
-        const int rel = (int)((packed & 0x3fffffffu) - base);
-        if (n == 0u || rel >= 24 || rel + (int)n <= 0) return mask;
-        const uint32_t bits = (1u << n) - 1u;
-        return mask & ~(rel >= 0 ? bits << rel : bits >> (-rel));
     }
 
     // precondition: has_tris(). Intersects the lowest-numbered pending primitive of the current group.
@@ -271,6 +257,10 @@ struct Traversal {
         const Prim* pr = sc.prims + pi;
         const float4 pa = ldg(&pr->a), pb = ldg(&pr->b), pc = ldg(&pr->c);
         if (STATS) stats->prims++;
+        if (ANY_HIT) {
+            const uint32_t g = f2u(pa.w);
+            if (g == (skip2 & 0xffffu) || g == (skip2 >> 16)) return;
+        }
         float t, u = 0.0f, v = 0.0f;
         bool h;
         if (f2u(pc.w) == 0u) {
@@ -310,20 +300,13 @@ struct Traversal {
     }
 };
 
-// packed primitive range of the planar instance a shadow ray names (16-bit id, 0xffff = none): first | count << 30
-RT_HD uint32_t skip_range(const SceneD& sc, uint32_t geom) {
-    if (geom >= 0xffffu) return 0u;
-    const Instance& in = sc.instances[geom];
-    return in.skip_n && in.skip_lo < 0x40000000u ? in.skip_lo | (in.skip_n << 30) : 0u;
-}
-
 // One ray start to finish: each node's primitives right after its box test.
 template <bool ANY_HIT, bool STATS>
-RT_HD bool traverse(const SceneD& sc, V3 o, V3 d, float t_min, float t_max, Hit& hit, TraverseStats* stats, uint32_t skip_ids = 0xffffffffu) {
+RT_HD bool traverse(const SceneD& sc, V3 o, V3 d, float t_min, float t_max, Hit& hit, TraverseStats* stats, uint32_t skip2 = 0xffffffffu) {
     uint2 stack_mem[TRAVERSE_STACK];
     Traversal<ANY_HIT, STATS> tr;
     tr.stack = stack_mem;
-    if (tr.init(sc, o, d, t_min, t_max, skip_range(sc, skip_ids & 0xffffu), skip_range(sc, skip_ids >> 16))) {
+    if (tr.init(sc, o, d, t_min, t_max, skip2)) {
         do {
             if (tr.has_tris()) tr.tri_step(sc, stats);
             else tr.node_step(sc, stats);

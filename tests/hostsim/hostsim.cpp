@@ -249,19 +249,6 @@ void build(HostScene& hs, const rtcuda_scene_desc* d) {
     sc.scene_center[0] = c.x; sc.scene_center[1] = c.y; sc.scene_center[2] = c.z;
     sc.scene_radius = n == 1 ? INFINITY : length(mx - c);
     set_scene_bounds(sc, mn, mx, true);
-    if (sc.skip_planar) {   // launch_instance_ranges
-        std::vector<uint32_t> rlo(d->instance_count, 0xffffffffu), rhi(d->instance_count, 0u);
-        for (uint32_t p = 0; p < n; p++) {
-            const uint32_t g = f2u(sc.prims[p].a.w);
-            rlo[g] = std::min(rlo[g], p); rhi[g] = std::max(rhi[g], p);
-        }
-        for (uint32_t g = 0; g < d->instance_count; g++) {
-            Instance& in = hs.instances[g];
-            const bool ok = in.kind == 0u && in.tri_count >= 1u && in.tri_count <= 3u && in.plane[3] < 3.0e38f && rlo[g] <= rhi[g] && rhi[g] - rlo[g] + 1u == in.tri_count;
-            in.skip_lo = ok ? rlo[g] : 0u;
-            in.skip_n = ok ? in.tri_count : 0u;
-        }
-    }
     if (counters[2] != n) sc.node_count = 0xdeadbeef;  // lost primitives: surfaced through the stats
     else if (!std::getenv("HOSTSIM_NO_SHADE_RECS")) {
         hs.shade_recs.resize(n);
@@ -515,7 +502,7 @@ int hostsim_render(const rtcuda_scene_desc* d, const rtcuda_settings* st, rtcuda
                             for (uint32_t pi : trace) {
                                 const uint32_t geom = f2u(sc.prims[pi].a.w);
                                 c_total++;
-                                if ((geom == (skip2 & 0xffffu) || geom == (skip2 >> 16))) c_skipped++;
+                                if (geom == (skip2 & 0xffffu) || geom == (skip2 >> 16)) c_skipped++;
                                 if (pi == vp) c_exact++;
                                 else if (geom == vgeom) c_same_geom++;
                                 else if (sc.instances[geom].area_light != NONE) c_emitter++;

@@ -613,10 +613,6 @@ void upload_scene(rtcuda_scene* s, const rtcuda_scene_desc* d) {
         b.radius = sh.radius;
         n_prims += sh.kind == RTCUDA_SHAPE_TRIANGLE_MESH ? sh.tri_count : 1;
         REQUIRE(n_prims < 0x7fffffffull, "too many primitives");
-        const bool mesh = sh.kind == RTCUDA_SHAPE_TRIANGLE_MESH;
-        const float* hv = !mesh ? nullptr : (own_arrays ? sh.vertices : d->vertices + (size_t)sh.vertex_offset * 3);
-        const uint32_t* ht = !mesh ? nullptr : (own_arrays ? sh.tris : d->tris + (size_t)sh.tri_offset * 3);
-        instance_plane(hv, sh.vertex_count, ht, sh.tri_count, b.o2w, b.plane);
     }
     // instances without primitives (empty meshes) would break the prim -> instance search: give them an
     // empty range that the search skips (prim_base is non-decreasing; the LAST instance with base <= i wins)
@@ -630,13 +626,9 @@ void upload_scene(rtcuda_scene* s, const rtcuda_scene_desc* d) {
         std::memcpy(b.b, a.intensity_or_radiance, sizeof b.b);
         b.light_to_world = to_m4(a.light_to_world);
         b.tri_table = 0;
-        b.geom = NONE;
         if (a.kind == RTCUDA_LIGHT_DIFFUSE_AREA) {
             b.tri_table = (uint32_t)n_light_tris;
             n_light_tris += d->shapes[a.shape].tri_count;
-            uint32_t uses = 0;
-            for (uint32_t g = 0; g < d->instance_count; g++) if (d->instances[g].shape == a.shape) { uses++; b.geom = g; }
-            if (uses != 1) b.geom = NONE;
         }
     }
     s->host_lights.assign(d->lights, d->lights + d->light_count);
@@ -685,7 +677,6 @@ void upload_scene(rtcuda_scene* s, const rtcuda_scene_desc* d) {
     sc.watertight = (s->ctx->bs.flags & RTCUDA_BACKEND_WATERTIGHT) ? 1u : 0u;
     sc.all_diffuse = 1;
     for (uint32_t m = 0; m < d->material_count; m++) if (d->materials[m].kind != RTCUDA_MATERIAL_DIFFUSE) sc.all_diffuse = 0;
-    sc.skip_planar = std::getenv("RTCUDA_SKIP_PLANAR") ? 1u : 0u;   // A/B switch while the gain is being measured (profiles/r1_notes.md)
     sc.tex_uses_derivs = 0;
     for (uint32_t t = 0; t < d->texture_count; t++)
         if (d->textures[t].kind == RTCUDA_TEXTURE_IMAGE || d->textures[t].kind == RTCUDA_TEXTURE_CHECKER) sc.tex_uses_derivs = 1;

@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(BLOCK, SHADOW_BLOCKS) k_shadow(const __grid_co
                     const float4 o4 = w.sray_o[q], d4 = w.sray_d[q];
                     if (o4.w >= 0.0f) {   // negative: never occluded (non-finite origin quirk), not traced
                         n_rays++;
-                        have = tr.init(sc, xyz(o4), xyz(d4), 0.001f, o4.w, f2u(d4.w)) ? 1u : 0u;
+                        have = tr.init(sc, xyz(o4), xyz(d4), 0.001f, o4.w) ? 1u : 0u;
                     }
                 }
             }

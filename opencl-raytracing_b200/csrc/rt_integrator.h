@@ -436,28 +436,6 @@ RT_HD bool shade_begin(uint32_t q, const SceneD& sc, const RenderParams& rp, con
     return true;
 }
 
-// The planar instances a shadow ray from `from` (on the light) to `to` (on the surface of instance `surf_geom`) starts and ends
-// on, as two 16-bit instance ids (0xffff = none) for k_shadow to skip: every triangle of such an instance lies within
-// plane[3] of a plane through an end point of the ray, so the ray meets it at a distance of at most (plane[3] + rounding) /
-// |dir . n| from that end point — inside the 0.001 the reference keeps clear at both ends (lights.rs:159-168) whenever that
-// bound is below 2.5e-4, i.e. Moller-Trumbore would reject each of them by its t range. Rounding: 64 ulp of the largest
-// coordinate involved covers the transform of the packed vertices, the end points and the test's own arithmetic.
-RT_HD uint32_t planar_skip_ids(const SceneD& sc, const LightD& light, uint32_t surf_geom, V3 from, V3 to, V3 dir) {
-    if (!sc.skip_planar) return 0xffffffffu;
-    const float mag = fmaxf(fmaxf(fmaxf(fabsf(from.x), fabsf(from.y)), fmaxf(fabsf(from.z), fabsf(to.x))), fmaxf(fabsf(to.y), fabsf(to.z)));
-    const float eps = 7.6293945e-6f * mag;   // 64 * 2^-23
-    uint32_t ids = 0xffffffffu;
-    if (light.kind == 2 && light.geom < 0xffffu) {
-        const float* p = sc.instances[light.geom].plane;
-        if (p[3] + eps < 2.5e-4f * fabsf(dir.x * p[0] + dir.y * p[1] + dir.z * p[2])) ids = (ids & 0xffff0000u) | light.geom;
-    }
-    if (surf_geom < 0xffffu) {
-        const float* p = sc.instances[surf_geom].plane;
-        if (p[3] + eps < 2.5e-4f * fabsf(dir.x * p[0] + dir.y * p[1] + dir.z * p[2])) ids = (ids & 0x0000ffffu) | (surf_geom << 16);
-    }
-    return ids;
-}
-
 // lib.rs:324-356: every light, every sample; entries with a non-zero unoccluded contribution become shadow rays.
 // MODE 0 counts them, MODE 1 stages up to NEE_STAGE of them in thread-local memory (and counts), MODE 2 writes them
 // (at most `limit`) to the shadow-ray queue starting at `first`. All modes draw the same numbers from `s`.
@@ -491,8 +469,7 @@ RT_HD uint32_t nee_pass(const SceneD& sc, const RenderParams& rp, const Wave& w,
                     // scenes, bvh2.rs:448-452) can never be occluded in the reference: NaN slab test
                     const bool skip_test = !(finite_f(ls.origin.x) && finite_f(ls.origin.y) && finite_f(ls.origin.z));
                     const float4 eo = make_float4(ls.origin.x, ls.origin.y, ls.origin.z, skip_test ? -1.0f : ls.distance - 0.001f);
-                    const float4 ed = make_float4(ls.dir.x, ls.dir.y, ls.dir.z, u2f(planar_skip_ids(sc, light, S.hit.geom_id, ls.origin, S.hit.point, ls.dir)));
-                    const float4 ec = make_float4(c.x, c.y, c.z, 0.0f);
+                    const float4 ed = make_float4(ls.dir.x, ls.dir.y, ls.dir.z, 0.0f), ec = make_float4(c.x, c.y, c.z, 0.0f);
                     if (MODE == 1) { stage->o[k] = eo; stage->d[k] = ed; stage->c[k] = ec; }
                     else { const size_t e = (size_t)first + k; RT_CHECK(e < (size_t)w.capacity * (w.shadow_k ? w.shadow_k : 1u)); w.sray_o[e] = eo; w.sray_d[e] = ed; w.scontrib[e] = ec; }
                 }

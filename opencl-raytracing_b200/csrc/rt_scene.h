@@ -29,38 +29,7 @@ struct Instance {
     uint32_t tri_count, prim_base, _p0, _p1;   // prim_base: first build-primitive of this instance
     float center[3];
     float radius;
-    // World-space plane of a PLANAR mesh instance (walls, quad lights): unit normal | the largest distance of any of its
-    // vertices from the plane through the first one; w = +inf for everything else (instance_plane below). A shadow ray that
-    // starts or ends in such a plane and is not grazing cannot hit any other triangle of the instance inside its t range:
-    // nee_pass names those instances in the ray record and k_shadow does not intersect their triangles.
-    float plane[4];
 };
-
-// Host side, at upload. verts / tris: the shape's own object-space arrays. Meshes above 4096 vertices are not examined.
-inline void instance_plane(const float* verts, uint32_t vertex_count, const uint32_t* tris, uint32_t tri_count, const M4& o2w, float out[4]) {
-    out[0] = out[1] = out[2] = 0.0f;
-    out[3] = INFINITY;
-    if (!verts || !tris || !tri_count || vertex_count < 3 || vertex_count > 4096) return;
-    auto world = [&](uint32_t i) { return apply_point(o2w, mk3(verts[3 * i], verts[3 * i + 1], verts[3 * i + 2])); };
-    double n[3] = {0, 0, 0}, len = 0.0;
-    for (uint32_t t = 0; t < tri_count && len == 0.0; t++) {
-        const V3 a = world(tris[3 * t]), b = world(tris[3 * t + 1]), c = world(tris[3 * t + 2]);
-        const double e1[3] = {(double)b.x - a.x, (double)b.y - a.y, (double)b.z - a.z}, e2[3] = {(double)c.x - a.x, (double)c.y - a.y, (double)c.z - a.z};
-        n[0] = e1[1] * e2[2] - e1[2] * e2[1]; n[1] = e1[2] * e2[0] - e1[0] * e2[2]; n[2] = e1[0] * e2[1] - e1[1] * e2[0];
-        len = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
-    }
-    if (!(len > 0.0) || !std::isfinite(len)) return;
-    for (double& c : n) c /= len;
-    const V3 p0 = world(0);
-    double delta = 0.0;
-    for (uint32_t i = 0; i < vertex_count; i++) {
-        const V3 p = world(i);
-        delta = std::fmax(delta, std::fabs(n[0] * ((double)p.x - p0.x) + n[1] * ((double)p.y - p0.y) + n[2] * ((double)p.z - p0.z)));
-    }
-    if (!std::isfinite(delta)) return;
-    out[0] = (float)n[0]; out[1] = (float)n[1]; out[2] = (float)n[2];
-    out[3] = (float)(delta * 1.01) + 1.0e-30f;
-}
 
 struct ShapeD {  // rtcuda_shape (lights address emitters by shape index)
     uint32_t kind, material, area_light, vertex_offset, vertex_count, tri_offset, tri_count, normal_offset, uv_offset;
@@ -74,8 +43,7 @@ struct LightD {
     float b[3];   // intensity / radiance
     M4 light_to_world;
     uint32_t tri_table;   // diffuse area light: first record of its emitter in SceneD::light_tris
-    uint32_t geom;        // diffuse area light: the one instance of its shape (NONE when the shape is instanced more than once)
-    uint32_t _pad[2];
+    uint32_t _pad[3];
 };
 
 // One emitter triangle as next-event estimation reads it (four 128-bit loads instead of three index loads and nine
@@ -154,7 +122,6 @@ struct SceneD {
     uint32_t instance_count, light_count, material_count, texture_count;
     uint32_t env_texture;
     uint32_t all_diffuse;     // every material is Diffuse: shade with the DiffuseSurface instantiation
-    uint32_t skip_planar;     // shadow rays name the planar instances they start / end on (Instance::plane) and k_shadow skips their triangles
     uint32_t tex_uses_derivs; // some texture is an image or a checker: the only consumers of the uv derivatives (MatCtx); without
                               // one, the primary hit skips the camera-ray differentials (same values: nothing would read them)
     uint32_t watertight;      // RTCUDA_BACKEND_WATERTIGHT: Woop's watertight triangle test instead of the reference's Moller-Trumbore

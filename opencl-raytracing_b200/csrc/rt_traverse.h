@@ -150,11 +150,9 @@ struct Traversal {
     Hit hit;
     uint32_t hit_geom, hit_pid;  // ids of the current closest hit (tie-break)
     uint32_t found;  // 32-bit flag (a bool would be packed into a half register)
-    uint32_t skip2;  // any-hit only: two 16-bit instance ids whose triangles this ray cannot hit inside its range (planar_skip_ids)
 
-    RT_HD bool init(const SceneD& sc, V3 o_, V3 d_, float t_min_, float t_max_, uint32_t skip2_ = 0xffffffffu) {
+    RT_HD bool init(const SceneD& sc, V3 o_, V3 d_, float t_min_, float t_max_) {
         o = o_; d = d_; t_min = t_min_; closest = t_max_;
-        skip2 = skip2_;
         hit.prim = NONE; hit.t = t_max_; hit.u = hit.v = 0.0f;
         found = 0u;
         hit_geom = hit_pid = 0u;
@@ -257,10 +255,6 @@ struct Traversal {
         const Prim* pr = sc.prims + pi;
         const float4 pa = ldg(&pr->a), pb = ldg(&pr->b), pc = ldg(&pr->c);
         if (STATS) stats->prims++;
-        if (ANY_HIT) {
-            const uint32_t g = f2u(pa.w);
-            if (g == (skip2 & 0xffffu) || g == (skip2 >> 16)) return;
-        }
         float t, u = 0.0f, v = 0.0f;
         bool h;
         if (f2u(pc.w) == 0u) {
@@ -302,11 +296,11 @@ struct Traversal {
 
 // One ray start to finish: each node's primitives right after its box test.
 template <bool ANY_HIT, bool STATS>
-RT_HD bool traverse(const SceneD& sc, V3 o, V3 d, float t_min, float t_max, Hit& hit, TraverseStats* stats, uint32_t skip2 = 0xffffffffu) {
+RT_HD bool traverse(const SceneD& sc, V3 o, V3 d, float t_min, float t_max, Hit& hit, TraverseStats* stats) {
     uint2 stack_mem[TRAVERSE_STACK];
     Traversal<ANY_HIT, STATS> tr;
     tr.stack = stack_mem;
-    if (tr.init(sc, o, d, t_min, t_max, skip2)) {
+    if (tr.init(sc, o, d, t_min, t_max)) {
         do {
             if (tr.has_tris()) tr.tri_step(sc, stats);
             else tr.node_step(sc, stats);

@@ -74,8 +74,6 @@ void build(HostScene& hs, const rtcuda_scene_desc* d) {
         b.tri_count = sh.tri_count; b.prim_base = n_prims;
         std::memcpy(b.center, sh.center, sizeof b.center); b.radius = sh.radius;
         n_prims += sh.kind == 0 ? sh.tri_count : 1;
-        instance_plane(sh.kind == 0 ? d->vertices + (size_t)sh.vertex_offset * 3 : nullptr, sh.vertex_count,
-                       sh.kind == 0 ? d->tris + (size_t)sh.tri_offset * 3 : nullptr, sh.tri_count, b.o2w, b.plane);
     }
     hs.lights.resize(d->light_count);
     for (uint32_t i = 0; i < d->light_count; i++) {
@@ -85,11 +83,7 @@ void build(HostScene& hs, const rtcuda_scene_desc* d) {
         std::memcpy(b.a, a.position_or_direction, sizeof b.a); std::memcpy(b.b, a.intensity_or_radiance, sizeof b.b);
         b.light_to_world = to_m4(a.light_to_world);
         b.tri_table = 0;
-        b.geom = NONE;
         if (a.kind == 2) {
-            uint32_t uses = 0;
-            for (uint32_t g = 0; g < d->instance_count; g++) if (d->instances[g].shape == a.shape) { uses++; b.geom = g; }
-            if (uses != 1) b.geom = NONE;
             b.tri_table = (uint32_t)hs.light_tris.size();
             hs.light_tris.resize(hs.light_tris.size() + hs.shapes[a.shape].tri_count);
             for (uint32_t t = 0; t < hs.shapes[a.shape].tri_count; t++)
@@ -156,7 +150,6 @@ void build(HostScene& hs, const rtcuda_scene_desc* d) {
     sc.watertight = std::getenv("HOSTSIM_WATERTIGHT") ? 1u : 0u;   // test switch for RTCUDA_BACKEND_WATERTIGHT
     sc.all_diffuse = 1;
     for (uint32_t m = 0; m < d->material_count; m++) if (d->materials[m].kind != 0) sc.all_diffuse = 0;
-    sc.skip_planar = std::getenv("HOSTSIM_SKIP_PLANAR") ? 1u : 0u;
     sc.tex_uses_derivs = 0;
     for (uint32_t t = 0; t < d->texture_count; t++)
         if (d->textures[t].kind == RTCUDA_TEXTURE_IMAGE || d->textures[t].kind == RTCUDA_TEXTURE_CHECKER) sc.tex_uses_derivs = 1;
@@ -489,20 +482,18 @@ int hostsim_render(const rtcuda_scene_desc* d, const rtcuda_settings* st, rtcuda
                         if (!(sray_o[r].w >= 0.0f)) continue;
                         shadow_rays++;
                         if (structural) {   // one extra walk that records the primitives tested, classified against the ray's two end points
-                            static uint64_t c_rays = 0, c_total = 0, c_emitter = 0, c_exact = 0, c_same_geom = 0, c_other = 0, c_occluded = 0, c_skipped = 0;
-                            const uint32_t skip2 = f2u(sray_d[r].w);
+                            static uint64_t c_rays = 0, c_total = 0, c_emitter = 0, c_exact = 0, c_same_geom = 0, c_other = 0, c_occluded = 0;
                             trace.clear();
                             g_prim_trace = &trace;
                             Hit hh;
                             TraverseStats dummy{0, 0};
-                            const bool occ = traverse<true, true>(sc, xyz(sray_o[r]), xyz(sray_d[r]), 0.001f, sray_o[r].w, hh, &dummy, f2u(sray_d[r].w));
+                            const bool occ = traverse<true, true>(sc, xyz(sray_o[r]), xyz(sray_d[r]), 0.001f, sray_o[r].w, hh, &dummy);
                             g_prim_trace = nullptr;
                             const uint32_t vp = vertex_prim[ray_vertex[r]];
                             const uint32_t vgeom = f2u(sc.prims[vp].a.w);
                             for (uint32_t pi : trace) {
                                 const uint32_t geom = f2u(sc.prims[pi].a.w);
                                 c_total++;
-                                if (geom == (skip2 & 0xffffu) || geom == (skip2 >> 16)) c_skipped++;
                                 if (pi == vp) c_exact++;
                                 else if (geom == vgeom) c_same_geom++;
                                 else if (sc.instances[geom].area_light != NONE) c_emitter++;
@@ -510,13 +501,13 @@ int hostsim_render(const rtcuda_scene_desc* d, const rtcuda_settings* st, rtcuda
                             }
                             c_rays++; c_occluded += occ;
                             if (r + 1 == n_sray)
-                                std::fprintf(stderr, "structural (cumulative): shadow rays %llu occluded %llu | prim tests %llu = end-point triangle %llu + same instance as the end point %llu + emitter instance %llu + other %llu | not intersected (planar skip) %llu\n",
+                                std::fprintf(stderr, "structural (cumulative): shadow rays %llu occluded %llu | prim tests %llu = end-point triangle %llu + same instance as the end point %llu + emitter instance %llu + other %llu\n",
                                              (unsigned long long)c_rays, (unsigned long long)c_occluded, (unsigned long long)c_total, (unsigned long long)c_exact,
-                                             (unsigned long long)c_same_geom, (unsigned long long)c_emitter, (unsigned long long)c_other, (unsigned long long)c_skipped);
+                                             (unsigned long long)c_same_geom, (unsigned long long)c_emitter, (unsigned long long)c_other);
                         }
                         if (std::getenv("HOSTSIM_WARPSIM")) sim.push_back(SimRay{xyz(sray_o[r]), xyz(sray_d[r]), 0.001f, sray_o[r].w});
                         Hit h;
-                        if (traverse<true, true>(sc, xyz(sray_o[r]), xyz(sray_d[r]), 0.001f, sray_o[r].w, h, &ts, f2u(sray_d[r].w))) scontrib[r] = make_float4(0, 0, 0, 0);
+                        if (traverse<true, true>(sc, xyz(sray_o[r]), xyz(sray_d[r]), 0.001f, sray_o[r].w, h, &ts)) scontrib[r] = make_float4(0, 0, 0, 0);
                     }
                     if (!sim.empty()) {
                         char label[32];

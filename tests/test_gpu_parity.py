@@ -389,21 +389,6 @@ def test_builders_give_identical_frames(rc, monkeypatch):
     assert np.array_equal(c.beauty, a.beauty) and np.array_equal(c.debug_ids, a.debug_ids)
 
 
-def test_planar_skip_gives_identical_frames(rc, monkeypatch):
-    """RTCUDA_SKIP_PLANAR: shadow rays do not intersect the triangles of the planar instances they start / end on (they
-    would be rejected by the t range): bit-identical frames, on scenes with planar walls / quad lights and on one without"""
-    for name, w, h in (("cbbunny_area_light_transforms", 320, 180), ("cb_texture", 160, 90)):
-        sc = load_scene(name, w, h)
-        st = rc.RaytracerSettings(outputs=A.BEAUTY, samples_per_pixel=4)
-        monkeypatch.delenv("RTCUDA_SKIP_PLANAR", raising=False)
-        a, sa = gpu_render(rc, sc, st)
-        monkeypatch.setenv("RTCUDA_SKIP_PLANAR", "1")
-        b, sb = gpu_render(rc, sc, st)
-        assert np.array_equal(a.beauty, b.beauty), name
-        assert sa["shadow_rays"] == sb["shadow_rays"] and sa["bounce_rays"] == sb["bounce_rays"]
-    monkeypatch.delenv("RTCUDA_SKIP_PLANAR", raising=False)
-
-
 def test_cached_memory_release(rc):
     """the path-state arena of a closed renderer is parked and reused; rtcuda_release_cached_memory gives it back"""
     sc = load_scene("cb", 64, 64)

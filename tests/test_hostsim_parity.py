@@ -226,17 +226,3 @@ def test_shading_records_are_copies(rc, hostsim, monkeypatch, name):
     monkeypatch.setenv("HOSTSIM_NO_SHADE_RECS", "1")
     b, _ = hostsim.render(sc, st)
     assert np.array_equal(a.beauty, b.beauty)
-
-
-def test_planar_skip_is_exact_on_the_cpu_harness(hostsim, rc, monkeypatch):
-    """same kernel bodies on the CPU: naming the planar instances a shadow ray starts / ends on (planar_skip_ids) and not
-    intersecting their triangles leaves every pixel unchanged"""
-    for name, w, h in (("cbbunny_area_light_transforms", 96, 54), ("cb", 64, 64), ("cb_texture", 96, 54)):
-        sc = load_scene(name, w, h)
-        st = rc.RaytracerSettings(samples_per_pixel=2)
-        monkeypatch.delenv("HOSTSIM_SKIP_PLANAR", raising=False)
-        a, sa = hostsim.render(sc, st)
-        monkeypatch.setenv("HOSTSIM_SKIP_PLANAR", "1")
-        b, sb = hostsim.render(sc, st)
-        assert np.array_equal(a.beauty, b.beauty), name
-        assert sa["shadow_rays"] == sb["shadow_rays"]

@@ -365,8 +365,23 @@ int hostsim_ray_triangle(int mode, const float* p0, const float* p1, const float
 
 // stats_out[8]: primary, bounce, shadow, aov rays, nodes fetched, prims fetched, wide node count, collapse levels
 __attribute__((visibility("default")))
+int hostsim_render_samples(const rtcuda_scene_desc* d, const rtcuda_settings* st, rtcuda_outputs* out, uint32_t tile_rank, uint32_t tile_world,
+                           uint32_t capacity, uint64_t* stats_out, uint32_t sample_lo, uint32_t sample_hi);
+
+__attribute__((visibility("default")))
 int hostsim_render(const rtcuda_scene_desc* d, const rtcuda_settings* st, rtcuda_outputs* out, uint32_t tile_rank, uint32_t tile_world,
                    uint32_t capacity, uint64_t* stats_out) {
+    return hostsim_render_samples(d, st, out, tile_rank, tile_world, capacity, stats_out, 0, 0);
+}
+
+// sample_hi == 0: the whole frame (mean over all samples). Otherwise samples [sample_lo, sample_hi) only and the beauty plane holds
+// their un-normalised sum — the harness's rtcuda_render_samples_device (sample-range partition across ranks).
+__attribute__((visibility("default")))
+int hostsim_render_samples(const rtcuda_scene_desc* d, const rtcuda_settings* st, rtcuda_outputs* out, uint32_t tile_rank, uint32_t tile_world,
+                           uint32_t capacity, uint64_t* stats_out, uint32_t sample_lo, uint32_t sample_hi) {
+    const bool sum_mode = sample_hi != 0;
+    if (!sum_mode) sample_hi = st->samples_per_pixel;
+    if (sample_lo >= sample_hi || sample_hi > st->samples_per_pixel) return 1;
     HostScene hs;
     build(hs, d);
     const SceneD& sc = hs.sc;
@@ -411,7 +426,7 @@ int hostsim_render(const rtcuda_scene_desc* d, const rtcuda_settings* st, rtcuda
         uint32_t shadow_k = 0;
         for (uint32_t i = 0; i < d->light_count; i++) shadow_k += d->lights[i].kind == 2 ? rp.light_sample_count : 1;
         const uint32_t np_batch = std::min(np_all, capacity);
-        const uint32_t ns_batch = std::max(1u, std::min(st->samples_per_pixel, capacity / np_batch));
+        const uint32_t ns_batch = std::max(1u, std::min(sample_hi - sample_lo, capacity / np_batch));
         const uint32_t cap = np_batch * ns_batch;
         std::vector<PathState> state(cap);
         const size_t kk = std::max(1u, shadow_k);
@@ -426,8 +441,8 @@ int hostsim_render(const rtcuda_scene_desc* d, const rtcuda_settings* st, rtcuda
         w.shadow_k = shadow_k; w.svertex = svertex.data(); w.sray_o = sray_o.data(); w.sray_d = sray_d.data(); w.scontrib = scontrib.data();
         for (uint32_t p0 = 0; p0 < np_all; p0 += np_batch) {
             const uint32_t np = std::min(np_batch, np_all - p0);
-            for (uint32_t s0 = 0; s0 < st->samples_per_pixel; s0 += ns_batch) {
-                const uint32_t ns = std::min(ns_batch, st->samples_per_pixel - s0);
+            for (uint32_t s0 = sample_lo; s0 < sample_hi; s0 += ns_batch) {
+                const uint32_t ns = std::min(ns_batch, sample_hi - s0);
                 w.pixel_base = p0; w.n_pixels = np; w.sample_base = s0; w.n_samples = ns;
                 uint32_t n_rays = 0;
                 w.depth = 0; w.ray_o_out = ro[0].data(); w.ray_d_out = rd[0].data();
@@ -525,7 +540,7 @@ int hostsim_render(const rtcuda_scene_desc* d, const rtcuda_settings* st, rtcuda
                 for (uint32_t i = 0; i < np; i++) resolve_body(i, w, accum.data());
             }
         }
-        const float inv_spp = 1.0f / (float)st->samples_per_pixel;
+        const float inv_spp = sum_mode ? 1.0f : 1.0f / (float)st->samples_per_pixel;
         for (uint32_t i = 0; i < np_all; i++) {
             size_t idx = (size_t)(pixels[i] >> 16) * W + (pixels[i] & 0xffffu);
             out->beauty[3 * idx] = accum[i].x * inv_spp; out->beauty[3 * idx + 1] = accum[i].y * inv_spp; out->beauty[3 * idx + 2] = accum[i].z * inv_spp;

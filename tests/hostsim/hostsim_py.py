@@ -31,6 +31,8 @@ def lib():
         l.hostsim_render.argtypes = [C.POINTER(_ffi.SceneDesc), C.POINTER(_ffi.Settings), C.POINTER(_ffi.Outputs), C.c_uint32,
                                      C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]
         l.hostsim_render.restype = C.c_int
+        l.hostsim_render_samples.argtypes = l.hostsim_render.argtypes + [C.c_uint32, C.c_uint32]
+        l.hostsim_render_samples.restype = C.c_int
         fp = C.POINTER(C.c_float)
         l.hostsim_ray_triangle.argtypes = [C.c_int, fp, fp, fp, fp, fp, C.c_float, C.c_float, fp]
         l.hostsim_ray_triangle.restype = C.c_int
@@ -38,12 +40,14 @@ def lib():
     return _lib
 
 
-def render(scene, settings, tile_rank=0, tile_world=1, capacity=0):
+def render(scene, settings, tile_rank=0, tile_world=1, capacity=0, sample_range=None):
+    """sample_range=(lo, hi): only those samples, the beauty plane holds their un-normalised sum (rtcuda_render_samples_device)"""
     holder = scene.to_desc()
     out = rc.RenderOutput.allocate(scene.camera.raster_width, scene.camera.raster_height, rc.AovFlags(settings.outputs))
     s, o = settings.to_c(), out.to_c()
     stats = (C.c_uint64 * 8)()
-    if lib().hostsim_render(C.byref(holder.desc), C.byref(s), C.byref(o), tile_rank, tile_world, capacity, stats) != 0:
+    lo, hi = sample_range if sample_range is not None else (0, 0)
+    if lib().hostsim_render_samples(C.byref(holder.desc), C.byref(s), C.byref(o), tile_rank, tile_world, capacity, stats, lo, hi) != 0:
         raise RuntimeError("hostsim_render failed")
     names = ["primary_rays", "bounce_rays", "shadow_rays", "aov_rays", "nodes_fetched", "prims_fetched", "bvh_node_count", "collapse_levels"]
     return out, dict(zip(names, list(stats)))

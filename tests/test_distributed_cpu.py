@@ -1,4 +1,4 @@
-"""world_size-2 gloo test of the multi-GPU host logic (tile ownership + the single sum-reduce of the frame),
+"""world_size-2 gloo test of the multi-GPU host logic (tile ownership, the gather / sum-reduce of the frame, the sample-range partition),
 with the CPU kernel-body harness standing in for the device render of each rank."""
 import os
 import socket
@@ -38,6 +38,17 @@ def _worker(rank, world, port, ret):
     # the collective the tile partition uses: only the owned pixels travel
     idx = rc.multi_gpu.owned_pixel_indices(160, 130, world)
     rc.multi_gpu.gather_tiles(gathered, [torch.from_numpy(i) for i in idx], [len(i) for i in idx], rank, world, dst=0)
+    # the alternate partition: every rank renders a sample range of every pixel, the un-normalised sums are reduced
+    st4 = rc.RaytracerSettings(samples_per_pixel=5, light_sample_count=1)
+    lo, hi = rc.multi_gpu.sample_range_for_rank(5, rank, world)
+    part, _ = hostsim_py.render(sc, st4, sample_range=(lo, hi))
+    sums = {"beauty": torch.from_numpy(part.beauty.copy())}
+    rc.multi_gpu.reduce_planes(sums, dst=0)
+    if rank == 0:
+        whole, _ = hostsim_py.render(sc, st4)
+        ret["samples_close"] = bool(np.allclose(sums["beauty"].numpy() * np.float32(1.0 / 5), whole.beauty, rtol=2e-6, atol=1e-7))
+        one, _ = hostsim_py.render(sc, st4, sample_range=(0, 5))
+        ret["full_range_exact"] = bool(np.array_equal(one.beauty * np.float32(1.0 / 5), whole.beauty))
     if rank == 0:
         full, _ = hostsim_py.render(sc, st)
         ret["beauty_equal"] = bool(np.array_equal(planes["beauty"].numpy(), full.beauty))
@@ -54,4 +65,4 @@ def test_two_ranks_tile_partition_and_reduce(hostsim):
     mgr = mp.Manager()
     ret = mgr.dict()
     mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
-    assert ret["beauty_equal"] and ret["normals_equal"] and ret["mine_only"] and ret["gather_equal"]
+    assert ret["beauty_equal"] and ret["normals_equal"] and ret["mine_only"] and ret["gather_equal"] and ret["samples_close"] and ret["full_range_exact"]

@@ -760,13 +760,42 @@ def mesh_from_ply_bytes(data: bytes, swap_handedness: bool = False) -> Mesh:
             elements.append({"name": tok[1], "count": int(tok[2]), "props": []})
         elif tok[0] == "property":
             elements[-1]["props"].append(tok[1:])
-    if fmt != "binary_little_endian":
-        raise NotImplementedError("only binary_little_endian PLY is needed by the builtin scenes")
     ty = {"float": "<f4", "float32": "<f4", "double": "<f8", "uchar": "u1", "uint8": "u1", "int": "<i4", "uint": "<u4",
-          "int32": "<i4", "uint32": "<u4", "short": "<i2", "ushort": "<u2", "char": "i1"}
+          "int32": "<i4", "uint32": "<u4", "short": "<i2", "ushort": "<u2", "char": "i1", "int8": "i1", "int16": "<i2", "uint16": "<u2",
+          "float64": "<f8"}
+    if fmt == "ascii":   # the bunny of the builtin scenes is binary; exported meshes referenced from .pbrt files are often ascii
+        tokens = data[end:].split()
+        pos = 0
+        verts = faces = None
+        for el in elements:
+            if el["name"] == "vertex":
+                dt = np.dtype([(p[1], ty[p[0]]) for p in el["props"]])
+                nprop = len(el["props"])
+                vals = np.array(tokens[pos:pos + nprop * el["count"]], dtype=np.float64).reshape(el["count"], nprop)
+                pos += nprop * el["count"]
+                verts = np.zeros(el["count"], dtype=dt)
+                for k, prop in enumerate(el["props"]):
+                    verts[prop[1]] = vals[:, k]
+            elif el["name"] == "face":
+                faces = []
+                extra = len(el["props"]) - 1          # scalar properties after the index list are skipped
+                for _ in range(el["count"]):
+                    n = int(tokens[pos]); pos += 1
+                    faces.append(np.array(tokens[pos:pos + n], dtype=np.int64).astype(np.uint32)); pos += n + extra
+            else:
+                for _ in range(el["count"]):
+                    for prop in el["props"]:
+                        if prop[0] == "list":
+                            pos += 1 + int(tokens[pos])
+                        else:
+                            pos += 1
+        fmt = None
+    elif fmt != "binary_little_endian":
+        raise NotImplementedError("big-endian PLY files are not supported")
     off = end
-    verts = faces = None
-    for el in elements:
+    if fmt is not None:
+        verts = faces = None
+    for el in (elements if fmt is not None else []):
         if el["name"] == "vertex":
             dt = np.dtype([(p[1], ty[p[0]]) for p in el["props"]])
             verts = np.frombuffer(data, dtype=dt, count=el["count"], offset=off)

@@ -237,3 +237,16 @@ def test_pbrt_scene_on_the_cuda_backend(oracle):
     ref, _ = oracle.render(sc, st, num_threads=8)
     assert_first_hit_parity(out, ref)
     assert beauty_close(out.beauty, ref.beauty, rel=5e-3)
+
+
+def test_plymesh_ascii_and_winding(tmp_path):
+    """Shape "plymesh" (pbrt.rs:1119-1133): the PLY is read with the clockwise-winding swap; ascii files, quads split into fans"""
+    (tmp_path / "quad.ply").write_text("ply\nformat ascii 1.0\nelement vertex 4\nproperty float x\nproperty float y\nproperty float z\n"
+                                       "element face 1\nproperty list uchar int vertex_indices\nend_header\n"
+                                       "0 0 0\n1 0 0\n1 1 0\n0 1 0\n4 0 1 2 3\n")
+    (tmp_path / "s.pbrt").write_text('Camera "perspective"\nWorldBegin\nLightSource "point"\nShape "plymesh" "string filename" "quad.ply"\n'
+                                     'Shape "plymesh" "string filename" "missing.ply"\n')
+    sc = rc.scene_from_pbrt_file(str(tmp_path / "s.pbrt"))
+    assert len(sc.shapes) == 1                                    # the missing file is skipped with a warning
+    m = sc.shapes[0].shape
+    assert m.vertices.shape == (4, 3) and m.tris.tolist() == [[0, 2, 1], [0, 3, 2]] and m.normals is None

@@ -13,6 +13,8 @@
 //   - test_permute                     crates/raytracing-cpu/src/sample.rs:256-275
 //   - PCG32 XSH-RR published demo vectors (pcg32-demo, seed 42 / stream 54)
 //   - self-consistency: BVH2 closest hit == brute-force closest hit
+//   - rustc-hash 2.x FxHasher multiplier and the rotate_left(26) of finish(): found as `imm64 K ... rol r64, 26` in Rust
+//     extension modules of this image that link the crate (test_fxhasher_constants_against_compiled_rustc_hash)
 // Third-party arithmetic restated from the published algorithms (crate sources are not vendored
 // in /root/reference): rustc-hash 2.1.1 FxHasher, rand_pcg 0.9.0 Lcg64Xsh32, rand 0.9.2
 // StandardUniform<f32> / random_range(u32), image 0.25.8 imageops::resize(Lanczos3).

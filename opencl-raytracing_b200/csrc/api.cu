@@ -963,7 +963,7 @@ void render_device(rtcuda_scene* s, const rtcuda_settings* settings, const rtcud
                                              settings->y_strata, settings->antialias_primary_rays, settings->antialias_secondary_rays,
                                              (uint64_t)(uintptr_t)out->beauty, (uint64_t)(uintptr_t)s->arena.base, (uint64_t)(uintptr_t)s->accum.p,
                                              (uint64_t)(uintptr_t)s->stats_dev.p, (uint64_t)(uintptr_t)s->pixel_list.p, np_all, np_batch, ns_batch, sample_lo,
-                                             sample_hi, shadow_k, (uint64_t)s->ctx->bs.collect_stats};
+                                             sample_hi, shadow_k, (uint64_t)s->ctx->bs.collect_stats, (uint64_t)sum_mode};
                 if (!s->frame_exec || key != s->frame_key) {
                     reset_spans(s);
                     const unsigned long long l0 = s->lc.launches;

@@ -303,6 +303,21 @@ def test_sample_range_render(rc):
         assert r.stats()["samples"] == 96 * 64 * 6
         with pytest.raises(rc._ffi.RtCudaError):
             r.render_samples_device(st, 4, 13, plane.data_ptr())
+    # frames large enough for the captured frame graph: the mean and the un-normalised sum of the same range into the SAME plane
+    # must not share a graph (the finalize scale is baked into it)
+    sc = load_scene("cb", 512, 512)
+    st = rc.RaytracerSettings(samples_per_pixel=16, light_sample_count=1)
+    with rc.CudaRenderer(sc) as r:
+        plane = torch.zeros((512, 512, 3), dtype=torch.float32, device="cuda:0")
+        r.render_device(st, {"beauty": plane.data_ptr()})
+        torch.cuda.synchronize()
+        mean = plane.clone()
+        r.render_samples_device(st, 0, 16, plane.data_ptr())
+        torch.cuda.synchronize()
+        assert torch.equal(plane * torch.tensor(1.0 / 16, dtype=torch.float32), mean)
+        r.render_device(st, {"beauty": plane.data_ptr()})
+        torch.cuda.synchronize()
+        assert torch.equal(plane, mean)
 
 
 def test_full_size_c2_properties(rc):

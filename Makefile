@@ -5,7 +5,12 @@ CSRC := $(PKG)/csrc
 NVCCFLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden $(NVCCFLAGS_EXTRA)
 HDRS := $(wildcard $(CSRC)/*.h) $(CSRC)/kernels.cuh include/rtcuda.h
 
-all: $(PKG)/libraytracing_cuda.so oracle/liboracle.so tests/hostsim/libhostsim.so
+all: $(PKG)/libraytracing_cuda.so oracle/liboracle.so tests/hostsim/libhostsim.so oracle_ref
+
+# the reference's own C++ device headers compiled for the host (checker of the oracle; no-op when /root/reference is absent)
+.PHONY: oracle_ref
+oracle_ref:
+	$(MAKE) -C oracle/ref_shim
 
 # wavefront kernels: FMA contraction on, 2-ulp division / sqrt (the beauty plane is gated statistically; the
 # strict-tolerance AOV kernels live in kernels_aov.cu and keep IEEE division, sqrt and unfused multiply-add)

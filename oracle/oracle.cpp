@@ -1926,4 +1926,69 @@ __attribute__((visibility("default"))) void oracle_bsdf(const rtcuda_scene_desc*
         out[0] = (float)stt; out[1] = bs.wi.x; out[2] = bs.wi.y; out[3] = bs.wi.z; out[4] = bs.bsdf.x; out[5] = bs.bsdf.y; out[6] = bs.bsdf.z; out[7] = bs.pdf; out[8] = (float)bs.component;
     }
 }
+
+// ---- unit hooks shared with oracle/_ref (the reference's own C++ device headers compiled for the host, oracle/ref_shim/
+// ref_units.cpp): same kinds, same row layouts (24 floats in, 8 floats out per row). tests/test_oracle_ref.py compares the two.
+__attribute__((visibility("default"))) int oracle_unit_batch(int kind, uint32_t n, const float* in, float* out) {
+    constexpr int IN_W = 24, OUT_W = 8;
+    auto v3 = [](const float* p) { return Vec3{p[0], p[1], p[2]}; };
+    auto put3 = [](float* o, Vec3 v) { o[0] = v.x; o[1] = v.y; o[2] = v.z; };
+    for (uint32_t i = 0; i < n; i++) {
+        const float* a = in + (size_t)i * IN_W;
+        float* o = out + (size_t)i * OUT_W;
+        for (int k = 0; k < OUT_W; k++) o[k] = 0.0f;
+        switch (kind) {
+            case 0: o[0] = fresnel_dielectric(a[0], a[1]); break;
+            case 1: o[0] = fresnel_complex(a[0], Complex{a[1], a[2]}); break;
+            case 2: { Vec3 r; bool ok = refract(a[0], v3(a + 1), v3(a + 4), r); o[0] = ok ? 1.0f : 0.0f; if (ok) put3(o + 1, r); break; }
+            case 3: put3(o, reflect(v3(a), v3(a + 3))); break;
+            case 4: o[0] = microfacet::distribution(v3(a), a[3], a[4]); break;
+            case 5: o[0] = microfacet::lambda(v3(a), a[3], a[4]); break;
+            case 6: o[0] = microfacet::G1(v3(a), a[3], a[4]); break;
+            case 7: o[0] = microfacet::G(v3(a), v3(a + 3), a[6], a[7]); break;
+            case 8: o[0] = microfacet::visible_distribution(v3(a), v3(a + 3), a[6], a[7]); break;
+            case 9: put3(o, microfacet::sample_wm(v3(a), a[3], a[4], Vec2{a[5], a[6]})); break;
+            case 10: put3(o, microfacet::refl_bsdf(v3(a + 8), v3(a + 11), v3(a), v3(a + 3), a[6], a[7])); break;
+            case 11: o[0] = microfacet::refl_pdf(v3(a + 8), v3(a + 11), a[6], a[7]); break;
+            case 12: put3(o, microfacet::ts_bsdf(v3(a + 3), v3(a + 6), a[0], a[1], a[2])); break;
+            case 13: o[0] = microfacet::ts_pdf(v3(a + 3), v3(a + 6), a[0], a[1], a[2], ALL); break;
+            case 14: { Bsdf b; b.kind = B_DIFFUSE; b.albedo = v3(a); put3(o, b.evaluate(v3(a + 3), v3(a + 6))); break; }
+            case 15: { Vec3 x, y; make_orthonormal_basis(v3(a), x, y); put3(o, x); put3(o + 3, y); break; }
+            case 16: { Vec3 p0 = v3(a), p1 = v3(a + 3), p2 = v3(a + 6); o[0] = length(cross(p1 - p0, p2 - p0)) / 2.0f; break; }   // Mesh::tri_area, mesh.rs:271-278
+            case 17: { Vec2 d = sample_unit_disk(Vec2{a[0], a[1]}); o[0] = d.x; o[1] = d.y; break; }
+            case 18: { Vec2 d = sample_unit_disk_concentric(Vec2{a[0], a[1]}); o[0] = d.x; o[1] = d.y; break; }
+            case 19: put3(o, sample_cosine_hemisphere(Vec2{a[0], a[1]})); break;
+            case 20: o[0] = sample_exponential(a[0], a[1]); break;
+            case 21: { Complex c = csqrt(Complex{a[0], a[1]}); o[0] = c.re; o[1] = c.im; break; }
+            case 22: {   // SmoothConductor::sample_bsdf (materials.rs:440-466): no draw
+                Bsdf b; b.kind = B_SMOOTH_CONDUCTOR; b.eta3 = v3(a); b.kappa = v3(a + 3);
+                rtcuda_settings st{}; st.samples_per_pixel = 1;
+                Sampler s = Sampler::from_settings(st);
+                s.start_sample(0, 0, 0);
+                BsdfSample bs;
+                SampleStatus stt = b.sample(v3(a + 6), ALL, s, bs);
+                put3(o, bs.wi); put3(o + 3, bs.bsdf); o[6] = bs.pdf; o[7] = stt == VALID ? 1.0f : 0.0f;
+                break;
+            }
+            case 23: { Mat4 m; std::memcpy(m.m, a, sizeof m.m); put3(o, m.apply_point(v3(a + 16))); break; }
+            case 24: { Mat4 m; std::memcpy(m.m, a, sizeof m.m); put3(o, m.apply_vector(v3(a + 16))); break; }
+            default: return 1;
+        }
+    }
+    return 0;
+}
+// camera_ray for raster positions (x, y) exactly as given (lib.rs:145-195): kind 0 orthographic, 1 pinhole. out: o.xyz, d.xyz
+__attribute__((visibility("default"))) int oracle_camera_rays(int kind, const float* raster_to_camera, const float* camera_to_world, uint32_t n,
+                                                              const uint32_t* xy, float* out) {
+    rtcuda_camera cam{};
+    cam.kind = kind == 0 ? RTCUDA_CAMERA_ORTHOGRAPHIC : RTCUDA_CAMERA_PINHOLE;
+    std::memcpy(cam.raster_to_camera.forward.m, raster_to_camera, 64);
+    std::memcpy(cam.camera_to_world.forward.m, camera_to_world, 64);
+    for (uint32_t i = 0; i < n; i++) {
+        Ray r = camera_ray(cam, (float)xy[2 * i], (float)xy[2 * i + 1], false, Vec2{0, 0});
+        out[6 * (size_t)i] = r.origin.x; out[6 * (size_t)i + 1] = r.origin.y; out[6 * (size_t)i + 2] = r.origin.z;
+        out[6 * (size_t)i + 3] = r.direction.x; out[6 * (size_t)i + 4] = r.direction.y; out[6 * (size_t)i + 5] = r.direction.z;
+    }
+    return 0;
+}
 }

@@ -1,16 +1,34 @@
-"""Shared parity predicates (BASELINE.json north_star gates)."""
+"""Shared parity predicates (BASELINE.json north_star gates).
+
+Every fraction is taken over the pixels that HIT something in the reference render, never over the whole raster: on the
+C3 family 74 % of the frame is background that is exactly 0 in both renders, and a whole-raster median or outlier
+fraction says nothing about the box (VERDICT r1 "what's weak" 1-2)."""
 import numpy as np
 
-ID_AGREEMENT = 0.9999     # primary-hit geom/prim id agreement
+ID_AGREEMENT = 0.9999     # primary-hit geom/prim id agreement (over all pixels: a miss must be a miss in both)
 AOV_ATOL = 1e-4           # normal / uv / depth absolute tolerance ...
 AOV_RTOL = 2e-5           # ... plus a relative term: planes holding values >> 1 (uv = +-500 on the checkered
                           # plane, depth ~ 100 at grazing angles) cannot meet 1e-4 absolute in f32
 # albedo / mip level are not gated by the north star; they amplify the (in-tolerance) uv difference by the
 # texture gradient (a 2048^2 checker image turns 5e-6 in uv into 1e-3 in albedo) and log2 of a derivative
 PLANE_ATOL = {"albedo": 5e-3, "mip_level": 2e-3}
+# Fraction of the HIT pixels allowed outside the tolerance: silhouettes / sphere poles / uv seams where ulp-level input
+# differences are amplified (acos near +-1, grazing hits; checkered_plane: uv = +-500 and t up to ~1000 at the horizon).
 AOV_OUTLIER_FRAC = 2e-3
-# (checkered_plane: uv = +-500 and t up to ~1000 at the horizon -> a few 1e-3 of its pixels sit at f32 resolution)   # pixels on silhouettes / sphere poles / uv seams where ulp-level input differences are
-                          # amplified (acos near +-1, grazing hits): allowed to exceed the tolerance
+NONE_ID = 0xffffffff
+
+# Same-seed beauty gates, relative to the mean of the reference over its hit pixels (per-pixel max over channels):
+# the two renders draw the same numbers, so they walk the same paths until a rounding flips a branch (a hit on an edge, a
+# specular / diffuse lobe choice); the pixel then carries one different sample of `spp`.
+BEAUTY_P50 = 2e-5         # half of the hit pixels agree to rounding (measured: 3e-7 on the CPU harness, ~1e-6 on the B200)
+BEAUTY_P99 = 2e-2         # ... 99 % to 2 % of the mean
+BEAUTY_DIVERGED = 2e-2    # at most this fraction of hit pixels differs by more than 1 % of the mean (diffuse scenes)
+
+
+# Scenes with specular / glossy lobes: once a rounding flips a lobe choice or a refraction, the rest of that path is another
+# path, so same-seed renders agree per pixel only in the median; the tail is gated by the divergent fraction and, in the
+# tests, by the mean luminance (2e-3) at >= 16 spp. This is a statistical criterion for the tail, stated as such.
+SPECULAR_GATES = dict(p50=1e-3, p99=float("inf"), diverged=0.25)
 
 
 def luminance(img):
@@ -21,31 +39,53 @@ def id_agreement(a, b):
     return float((a == b).all(axis=-1).mean())
 
 
-def aov_close(a, b, same_hit=None, atol=AOV_ATOL):
-    """fraction of samples outside atol + rtol*|b| (NaN == NaN counts as equal)"""
+def hit_mask(ids):
+    """pixels whose un-jittered primary ray hit something (debug_ids plane: NONE on a miss)"""
+    return np.asarray(ids)[..., 0] != NONE_ID
+
+
+def aov_outliers(a, b, mask, atol=AOV_ATOL):
+    """number of `mask` pixels outside atol + rtol*|b| (NaN == NaN counts as equal)"""
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     both_nan = np.isnan(a) & np.isnan(b)
     bad = ~(np.abs(a - b) <= atol + AOV_RTOL * np.abs(b)) & ~both_nan
     if bad.ndim == 3:
         bad = bad.any(axis=-1)
-    if same_hit is not None:
-        bad &= same_hit
-    return float(bad.mean())
+    return int((bad & mask).sum())
 
 
-def assert_first_hit_parity(out, ref):
-    same = None
-    if out.debug_ids is not None:
-        agree = id_agreement(out.debug_ids, ref.debug_ids)
-        assert agree >= ID_AGREEMENT, f"primary-hit id agreement {agree:.6f}"
+def first_hit_report(out, ref):
+    """dict of the first-hit parity figures: id agreement over all pixels, id mismatches counted (not forgiven), and per
+    plane the fraction of the reference's HIT pixels outside the tolerance. A pixel whose ids disagree is an outlier of
+    every plane it differs in — it is not masked out."""
+    rep = {}
+    mask = None
+    if out.debug_ids is not None and ref.debug_ids is not None:
         same = (out.debug_ids == ref.debug_ids).all(axis=-1)
+        mask = hit_mask(ref.debug_ids) | hit_mask(out.debug_ids)
+        rep["id_agreement"] = float(same.mean())
+        rep["id_mismatch_pixels"] = int((~same).sum())
+        rep["hit_pixels"] = int(mask.sum())
     for plane in ("normals", "uv", "debug_depth", "albedo", "mip_level"):
         a, b = getattr(out, plane), getattr(ref, plane)
-        if a is None:
+        if a is None or b is None:
             continue
-        frac = aov_close(a, b, same, PLANE_ATOL.get(plane, AOV_ATOL))
-        assert frac <= AOV_OUTLIER_FRAC, f"{plane}: {frac:.2e} of pixels outside {PLANE_ATOL.get(plane, AOV_ATOL)} (+2e-5 rel)"
+        m = mask if mask is not None else np.ones(np.asarray(b).shape[:2], dtype=bool)
+        n = max(1, int(m.sum()))
+        rep[plane] = aov_outliers(a, b, m, PLANE_ATOL.get(plane, AOV_ATOL)) / n
+    return rep
+
+
+def assert_first_hit_parity(out, ref, outlier_frac=AOV_OUTLIER_FRAC):
+    rep = first_hit_report(out, ref)
+    if "id_agreement" in rep:
+        assert rep["id_agreement"] >= ID_AGREEMENT, f"primary-hit id agreement {rep['id_agreement']:.6f} ({rep['id_mismatch_pixels']} pixels)"
+    for plane in ("normals", "uv", "debug_depth", "albedo", "mip_level"):
+        if plane in rep:
+            assert rep[plane] <= outlier_frac, \
+                f"{plane}: {rep[plane]:.2e} of the {rep.get('hit_pixels', 'all')} hit pixels outside {PLANE_ATOL.get(plane, AOV_ATOL)} (+2e-5 rel)"
+    return rep
 
 
 def mean_luminance_z(a, b, spp_a, spp_b):
@@ -60,10 +100,37 @@ def mean_luminance_z(a, b, spp_a, spp_b):
     return float(d[:bh, :bw].mean() / max(se, 1e-30))
 
 
-def beauty_close(a, b, rel=1e-3):
-    """Same seed => same sampler streams => both renders walk the same paths up to float rounding: the median
-    per-pixel relative difference is tiny (a few pixels diverge where a rounding flips a hit / branch)."""
+def beauty_report(a, b, mask=None):
+    """Same-seed comparison of two beauty planes over `mask` (default: pixels that are non-zero in either render, i.e. the
+    pixels some path contributed to). Differences are per pixel (max over channels) relative to the mean of `b` over the mask."""
     a = np.nan_to_num(np.asarray(a, dtype=np.float64))
     b = np.nan_to_num(np.asarray(b, dtype=np.float64))
-    scale = max(float(np.abs(b).mean()), 1e-12)
-    return float(np.median(np.abs(a - b))) <= rel * scale
+    if mask is None:
+        mask = (a != 0).any(axis=-1) | (b != 0).any(axis=-1)
+    n = int(mask.sum())
+    if n == 0:
+        return {"pixels": 0, "p50": 0.0, "p99": 0.0, "diverged": 0.0, "mean_rel": 0.0, "outside_mask_max": float(np.abs(a - b).max(initial=0.0))}
+    scale = max(float(np.abs(b[mask]).mean()), 1e-12)
+    d = np.abs(a - b).max(axis=-1)
+    rel = d[mask] / scale
+    outside = d[~mask]
+    return {"pixels": n, "p50": float(np.percentile(rel, 50)), "p99": float(np.percentile(rel, 99)),
+            "diverged": float((rel > 1e-2).mean()), "mean_rel": float(abs(a[mask].mean() - b[mask].mean()) / scale),
+            "outside_mask_max": float(outside.max()) if outside.size else 0.0}
+
+
+def beauty_close(a, b, mask=None, p50=BEAUTY_P50, p99=BEAUTY_P99, diverged=BEAUTY_DIVERGED, report=None):
+    """Same seed => same sampler streams => both renders walk the same paths up to float rounding. Gate on the pixels that
+    carry light: the median AND the 99th percentile of the per-pixel relative difference, and the fraction of pixels that
+    diverge by more than 1 % of the mean. Pixels outside the mask must agree exactly (both black)."""
+    rep = beauty_report(a, b, mask)
+    if report is not None:
+        report.update(rep)
+    return rep["p50"] <= p50 and rep["p99"] <= p99 and rep["diverged"] <= diverged and (mask is not None or rep["outside_mask_max"] == 0.0)
+
+
+def assert_beauty_parity(a, b, ids=None, what="", **gates):
+    rep = {}
+    ok = beauty_close(a, b, None if ids is None else hit_mask(ids), report=rep, **gates)
+    assert ok, f"beauty {what}: {rep}"
+    return rep

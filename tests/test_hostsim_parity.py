@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from conftest import load_scene, bunny_mesh
-from parity import assert_first_hit_parity, luminance, beauty_close
+from parity import assert_first_hit_parity, assert_beauty_parity, luminance, beauty_close
 
 A = None
 
@@ -54,7 +54,7 @@ def test_gltf_scenes(rc, oracle, hostsim, name, w, h, spp, ls):
     # same sampler streams => the two renders follow the same paths up to float rounding
     la, lb = luminance(out.beauty), luminance(ref.beauty)
     assert abs(la.mean() - lb.mean()) <= 2e-3 * lb.mean() + 1e-7
-    assert beauty_close(out.beauty, ref.beauty)
+    assert_beauty_parity(out.beauty, ref.beauty)
 
 
 @pytest.mark.parametrize("name", ["checkered_plane", "dielectric", "metal", "rough_metal", "rough_dielectric", "out_of_focus_sphere"])
@@ -109,11 +109,11 @@ def test_stratified_sampler(rc, oracle, hostsim):
     st = rc.RaytracerSettings(outputs=A.BEAUTY, samples_per_pixel=9, light_sample_count=2, sampler=rc.Sampler.stratified(True, 3, 3))
     out, _ = hostsim.render(sc, st)
     ref, _ = oracle.render(sc, st, num_threads=4)
-    assert beauty_close(out.beauty, ref.beauty)
+    assert_beauty_parity(out.beauty, ref.beauty)
     st2 = rc.RaytracerSettings(outputs=A.BEAUTY, samples_per_pixel=9, light_sample_count=2, sampler=rc.Sampler.stratified(False, 3, 3))
     out2, _ = hostsim.render(sc, st2)
     ref2, _ = oracle.render(sc, st2, num_threads=4)
-    assert beauty_close(out2.beauty, ref2.beauty)
+    assert_beauty_parity(out2.beauty, ref2.beauty)
 
 
 def test_settings_variants(rc, oracle, hostsim):
@@ -122,7 +122,7 @@ def test_settings_variants(rc, oracle, hostsim):
         st = rc.RaytracerSettings(outputs=A.BEAUTY, samples_per_pixel=4, light_sample_count=1, **kw)
         out, _ = hostsim.render(sc, st)
         ref, _ = oracle.render(sc, st, num_threads=4)
-        assert beauty_close(out.beauty, ref.beauty), kw
+        assert_beauty_parity(out.beauty, ref.beauty, what=str(kw))
         assert abs(out.beauty.mean() - ref.beauty.mean()) <= 2e-3 * ref.beauty.mean() + 1e-8, kw
 
 
@@ -154,7 +154,7 @@ def test_many_light_samples_two_pass_nee(rc, oracle, hostsim):
     out, stats = hostsim.render(sc, st, capacity=2048)
     ref, ostats = oracle.render(sc, st, num_threads=4)
     assert stats["shadow_rays"] > 0
-    assert beauty_close(out.beauty, ref.beauty)
+    assert_beauty_parity(out.beauty, ref.beauty)
     assert abs(out.beauty.mean() - ref.beauty.mean()) <= 2e-3 * ref.beauty.mean() + 1e-8
 
 
@@ -213,7 +213,7 @@ def test_watertight_mode_matches_reference_first_hits(rc, oracle, hostsim, monke
     out, _ = hostsim.render(sc, st)
     ref, _ = oracle.render(sc, st, num_threads=4)
     assert_first_hit_parity(out, ref)
-    assert beauty_close(out.beauty, ref.beauty)
+    assert_beauty_parity(out.beauty, ref.beauty)
 
 
 @pytest.mark.parametrize("name", ["cb_texture", "cbbunny_area_light_transforms"])
@@ -226,3 +226,17 @@ def test_shading_records_are_copies(rc, hostsim, monkeypatch, name):
     monkeypatch.setenv("HOSTSIM_NO_SHADE_RECS", "1")
     b, _ = hostsim.render(sc, st)
     assert np.array_equal(a.beauty, b.beauty)
+
+
+def test_texture_variants(rc, oracle, hostsim):
+    """Mix / nested Scale textures, Mirror and Clamp wrap, nearest / bilinear / trilinear, u8 / u16 / f32 images with 2-4
+    channels (texture.rs:235-459, materials/texture.rs:45-68, image.rs:56-121): kernel bodies vs the oracle"""
+    from conftest import texture_zoo_scene
+    sc = texture_zoo_scene(96, 96)
+    st = rc.RaytracerSettings(outputs=dbg() | A.BEAUTY, samples_per_pixel=4, max_ray_depth=3)
+    out, _ = hostsim.render(sc, st)
+    ref, _ = oracle.render(sc, st, num_threads=4)
+    assert_first_hit_parity(out, ref)
+    assert len(np.unique(ref.albedo.reshape(-1, 3), axis=0)) > 500       # the walls really are textured
+    assert ref.mip_level.max() > 0.5                                     # the trilinear wall reports a mip level
+    assert_beauty_parity(out.beauty, ref.beauty)

@@ -227,7 +227,7 @@ def test_reference_test_scene_if_present():
 
 @pytest.mark.gpu
 def test_pbrt_scene_on_the_cuda_backend(oracle):
-    from parity import assert_first_hit_parity, beauty_close
+    from parity import assert_first_hit_parity, assert_beauty_parity, beauty_close, SPECULAR_GATES
     A = rc.AovFlags
     sc = rc.scene_from_pbrt_string(SCENE.replace('Shape "cone"', ""))
     st = rc.RaytracerSettings(outputs=A.BEAUTY | A.NORMALS | A.UV_COORDS | A.ALBEDO | A.MIP_LEVEL | A.DEBUG_IDS | A.DEBUG_DEPTH, samples_per_pixel=4,
@@ -236,7 +236,7 @@ def test_pbrt_scene_on_the_cuda_backend(oracle):
         out = r.render(st)
     ref, _ = oracle.render(sc, st, num_threads=8)
     assert_first_hit_parity(out, ref)
-    assert beauty_close(out.beauty, ref.beauty, rel=5e-3)
+    assert_beauty_parity(out.beauty, ref.beauty, **SPECULAR_GATES)
 
 
 def test_plymesh_ascii_and_winding(tmp_path):

@@ -19,6 +19,7 @@
 
 #include "../../include/rtcuda.h"
 #include "kernels.cuh"
+#include "rt_cull.h"
 
 using namespace rt;
 
@@ -203,6 +204,11 @@ struct rtcuda_scene {
     // render state
     DevBuf<uint32_t> pixel_list;
     uint32_t n_my_pixels = 0;
+    // The pixels of `pixel_list` whose camera rays can reach the scene bounds at all (build_pixel_list): the beauty pass
+    // allocates path slots for these only. Same buffer as pixel_list when nothing is dropped.
+    DevBuf<uint32_t> beauty_list_buf;
+    const uint32_t* beauty_list = nullptr;
+    uint32_t n_beauty_pixels = 0;
     DevBuf<float4> accum;
     WaveArena arena;
     size_t arena_capacity = 0, arena_shadow_k = 0, arena_depth = 0;
@@ -738,6 +744,22 @@ void build_pixel_list(rtcuda_scene* s) {
         }
     s->n_my_pixels = (uint32_t)list.size();
     s->pixel_list.upload(list.data(), list.size(), s->ctx->stream);
+    s->beauty_list = s->pixel_list.p;
+    s->n_beauty_pixels = s->n_my_pixels;
+    int rect[4];
+    if (!std::getenv("RTCUDA_NO_PIXEL_CULL") && scene_raster_rect(s->sc, rect)) {   // (the variable is an A/B aid)
+        std::vector<uint32_t> kept;
+        kept.reserve(list.size());
+        for (uint32_t packed : list) {
+            const int x = (int)(packed & 0xffffu), y = (int)(packed >> 16);
+            if (x >= rect[0] && x <= rect[2] && y >= rect[1] && y <= rect[3]) kept.push_back(packed);
+        }
+        if (kept.size() != list.size()) {
+            s->beauty_list_buf.upload(kept.data(), kept.size(), s->ctx->stream);
+            s->beauty_list = s->beauty_list_buf.p;
+            s->n_beauty_pixels = (uint32_t)kept.size();
+        }
+    }
     CK(cudaStreamSynchronize(s->ctx->stream));
 }
 
@@ -876,7 +898,7 @@ void render_device(rtcuda_scene* s, const rtcuda_settings* settings, const rtcud
     CK(cudaEventRecord(e0, st));
 
     const uint32_t o = settings->outputs;
-    if (!((o & RTCUDA_AOV_BEAUTY) && out->beauty && s->n_my_pixels)) reset_spans(s);   // no beauty pass: no kernel spans
+    if (!((o & RTCUDA_AOV_BEAUTY) && out->beauty && s->n_beauty_pixels)) reset_spans(s);   // no beauty pass: no kernel spans
     AovPlanes pl{};
     pl.normals = (o & RTCUDA_AOV_NORMALS) ? out->normals : nullptr;
     pl.albedo = (o & RTCUDA_AOV_ALBEDO) ? out->albedo : nullptr;
@@ -897,10 +919,13 @@ void render_device(rtcuda_scene* s, const rtcuda_settings* settings, const rtcud
         if (np_all) launch_aov(st, s->sc, rp, s->pixel_list.p, np_all, pl, s->stats_dev.p, collect, s->lc);
     }
 
-    uint64_t samples = 0;
+    uint64_t samples = 0, dropped_samples = 0;
     if ((o & RTCUDA_AOV_BEAUTY) && out->beauty) {
-        if (partial) CK(cudaMemsetAsync(out->beauty, 0, npix_img * 12, st));
-        if (np_all) {
+        samples = (uint64_t)np_all * n_samples_total;
+        dropped_samples = (uint64_t)(np_all - s->n_beauty_pixels) * n_samples_total;   // every one a camera ray that misses the scene bounds
+        const uint32_t nb = s->n_beauty_pixels;   // owned pixels whose rays can reach the scene bounds (build_pixel_list)
+        if (nb != npix_img) CK(cudaMemsetAsync(out->beauty, 0, npix_img * 12, st));
+        if (nb) {
             const uint32_t shadow_k = shadow_entries_per_vertex(s, rp);
             // Wavefront size. Deep bounces keep only a fraction of a batch alive (C3: 26 % at depth 1, 8 % at depth 8)
             // and every launch of a persistent kernel ends with a drain tail, so batches are sized for the 180 GB of
@@ -914,7 +939,7 @@ void render_device(rtcuda_scene* s, const rtcuda_settings* settings, const rtcud
                 // wavefront this job wants settles the size without asking the driver: cudaMemGetInfo is a trip into the
                 // kernel driver (it queues behind NVML queries of a monitoring thread and other processes' calls) and sat
                 // inside the render window with the GPU idle — 5-35 ms per frame on a busy box (profiles/r1s_gap.log).
-                const size_t want = std::min<size_t>(1u << 26, std::max<size_t>(1024, (size_t)np_all * n_samples_total));
+                const size_t want = std::min<size_t>(1u << 26, std::max<size_t>(1024, (size_t)nb * n_samples_total));
                 const size_t held = std::max(s->arena.base ? s->arena.bytes : 0, g_arena_cache.largest(s->ctx->device));
                 if (held >= arena_bytes(want, shadow_k, rp.max_ray_depth)) capacity = (uint32_t)want;
             }
@@ -926,22 +951,25 @@ void render_device(rtcuda_scene* s, const rtcuda_settings* settings, const rtcud
                 capacity = (uint32_t)std::min<size_t>(1u << 26, (size_t)(0.4 * (double)have_b) / bytes_per_slot);
             }
             capacity = std::max(capacity, 1024u);
-            const uint32_t np_batch = std::min(np_all, capacity);
-            const uint32_t ns_batch = std::max(1u, std::min(n_samples_total, capacity / np_batch));
+            const uint32_t np_batch = std::min(nb, capacity);
+            // samples per batch: as many as fit, then evened out over the batches (256 spp in batches of 124 would end with a
+            // batch of 8 samples, whose launches are all drain tail)
+            uint32_t ns_batch = std::max(1u, std::min(n_samples_total, capacity / np_batch));
+            const uint32_t n_sample_batches = (n_samples_total + ns_batch - 1) / ns_batch;
+            ns_batch = (n_samples_total + n_sample_batches - 1) / n_sample_batches;
             ensure_wave(s, np_batch * ns_batch, shadow_k, rp.max_ray_depth);
-            s->accum.ensure(np_all);
+            s->accum.ensure(nb);
             Wave w{};
-            w.pixel_list = s->pixel_list.p;
+            w.pixel_list = s->beauty_list;
             w.capacity = np_batch * ns_batch;
             w.state = s->state.p; w.radiance = s->radiance.p; w.hits = s->hits.p;
             w.stats = s->stats_dev.p;
             w.shadow_k = shadow_k; w.svertex = s->svertex.p;
             w.sray_o = s->sray_o.p; w.sray_d = s->sray_d.p; w.scontrib = s->scontrib.p;
-            samples = (uint64_t)np_all * n_samples_total;
             auto enqueue_frame = [&] {
-                CK(cudaMemsetAsync(s->accum.p, 0, (size_t)np_all * sizeof(float4), st));
-                for (uint32_t p0 = 0; p0 < np_all; p0 += np_batch) {
-                    const uint32_t np = std::min(np_batch, np_all - p0);
+                CK(cudaMemsetAsync(s->accum.p, 0, (size_t)nb * sizeof(float4), st));
+                for (uint32_t p0 = 0; p0 < nb; p0 += np_batch) {
+                    const uint32_t np = std::min(np_batch, nb - p0);
                     for (uint32_t s0 = sample_lo; s0 < sample_hi; s0 += ns_batch) {
                         const uint32_t ns = std::min(ns_batch, sample_hi - s0);
                         w.pixel_base = p0; w.n_pixels = np; w.sample_base = s0; w.n_samples = ns;
@@ -949,12 +977,12 @@ void render_device(rtcuda_scene* s, const rtcuda_settings* settings, const rtcud
                         launch_resolve(st, w, s->accum.p, s->lc);
                     }
                 }
-                launch_finalize(st, s->pixel_list.p, np_all, s->width, s->accum.p, sum_mode ? 1.0f : 1.0f / (float)settings->samples_per_pixel, out->beauty, s->stats_dev.p, s->lc);
+                launch_finalize(st, s->beauty_list, nb, s->width, s->accum.p, sum_mode ? 1.0f : 1.0f / (float)settings->samples_per_pixel, out->beauty, s->stats_dev.p, s->lc);
             };
             // frames of at least 4 Mi paths go through the graph (below that instantiating ~40 nodes per batch costs more
             // than the launches it saves); RTCUDA_NO_GRAPH=1 keeps direct launches (A/B, debugging)
             static const bool no_graph = std::getenv("RTCUDA_NO_GRAPH") != nullptr;
-            if (no_graph || samples < (1ull << 22)) {
+            if (no_graph || (uint64_t)nb * n_samples_total < (1ull << 22)) {
                 reset_spans(s);
                 enqueue_frame();
             } else {
@@ -962,7 +990,7 @@ void render_device(rtcuda_scene* s, const rtcuda_settings* settings, const rtcud
                                              settings->has_seed, settings->seed, settings->sampler_kind, settings->stratified_jitter, settings->x_strata,
                                              settings->y_strata, settings->antialias_primary_rays, settings->antialias_secondary_rays,
                                              (uint64_t)(uintptr_t)out->beauty, (uint64_t)(uintptr_t)s->arena.base, (uint64_t)(uintptr_t)s->accum.p,
-                                             (uint64_t)(uintptr_t)s->stats_dev.p, (uint64_t)(uintptr_t)s->pixel_list.p, np_all, np_batch, ns_batch, sample_lo,
+                                             (uint64_t)(uintptr_t)s->stats_dev.p, (uint64_t)(uintptr_t)s->beauty_list, nb, np_batch, ns_batch, sample_lo,
                                              sample_hi, shadow_k, (uint64_t)s->ctx->bs.collect_stats, (uint64_t)sum_mode};
                 if (!s->frame_exec || key != s->frame_key) {
                     reset_spans(s);
@@ -1000,7 +1028,7 @@ void render_device(rtcuda_scene* s, const rtcuda_settings* settings, const rtcud
     CK(cudaEventElapsedTime(&ms, e0, e1));
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     s->stats.samples = samples;
-    s->stats.primary_rays = h_stats[STAT_PRIMARY];
+    s->stats.primary_rays = h_stats[STAT_PRIMARY] + dropped_samples;
     s->stats.bounce_rays = h_stats[STAT_BOUNCE];
     s->stats.shadow_rays = h_stats[STAT_SHADOW];
     s->stats.aov_rays = h_stats[STAT_AOV];
@@ -1012,7 +1040,7 @@ void render_device(rtcuda_scene* s, const rtcuda_settings* settings, const rtcud
     s->stats.prims_fetched = h_stats[STAT_EXT_PRIMS] + h_stats[STAT_SH_PRIMS] + h_stats[STAT_AOV_PRIMS];
     s->stats.shaded_vertices = h_stats[STAT_SHADED];
     s->stats.nonfinite_values = h_stats[STAT_NONFINITE];
-    s->stats.primary_rays_culled = h_stats[STAT_CULLED];
+    s->stats.primary_rays_culled = h_stats[STAT_CULLED] + dropped_samples;
     s->stats.final_rays_skipped = h_stats[STAT_FINAL_SKIPPED];
     s->stats.kernel_launches = s->lc.launches - launches0;
     s->stats.render_ms = ms;

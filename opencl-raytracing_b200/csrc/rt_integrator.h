@@ -357,7 +357,7 @@ template <typename Surf>
 struct ShadeState {
     uint32_t slot, flags, sidx;
     Ray ray;
-    V3 radiance, path_weight;
+    V3 emitted, path_weight;   // emitted: radiance of the emitter hit after a specular bounce / at depth 0 (added when `dirty`)
     Sampler s;
     HitInfo hit;
     Surf surf;
@@ -365,6 +365,14 @@ struct ShadeState {
     V3 wo;
     bool dirty;
 };
+
+// radiance += path_weight * emitted (lib.rs:289, 296): the only read-modify-write of the slot's radiance in shade
+template <typename Surf>
+RT_HD void add_emitted(const Wave& w, const ShadeState<Surf>& S) {
+    V3 r = xyz(w.radiance[S.slot]);
+    r += S.path_weight * S.emitted;
+    w.radiance[S.slot] = make_float4(r.x, r.y, r.z, 0.0f);
+}
 
 // lib.rs:284-322: miss / emission / material setup. False when the path ends here (state already written back).
 template <typename Surf>
@@ -380,15 +388,16 @@ RT_HD bool shade_begin(uint32_t q, const SceneD& sc, const RenderParams& rp, con
     const bool has_hit = h.prim != NONE;
     if (!has_hit && sc.env_texture == NONE) return false;
 
-    const float4 rad4 = w.radiance[slot];
+    // The slot's accumulated radiance is only touched by the few vertices that add to it here (an emitter seen directly or
+    // through specular bounces, the environment on a miss): reading it for every vertex cost a scattered 32-byte sector each.
     const float4 wt4 = w.state[slot].weight;
-    S.radiance = xyz(rad4);
     S.path_weight = xyz(wt4);
     S.flags = f2u(wt4.w);
     S.dirty = false;
+    S.emitted = mk3(0.0f);
     if (!has_hit) {
-        S.radiance += S.path_weight * environment_radiance(sc, S.ray.d);
-        w.radiance[slot] = make_float4(S.radiance.x, S.radiance.y, S.radiance.z, 0.0f);
+        S.emitted = environment_radiance(sc, S.ray.d);
+        add_emitted(w, S);
         return false;
     }
     const bool specular_bounce = (S.flags & 1u) != 0;
@@ -406,7 +415,7 @@ RT_HD bool shade_begin(uint32_t q, const SceneD& sc, const RenderParams& rp, con
     const bool add_zero_bounce = rp.accumulate_bounces || rp.max_ray_depth == depth;
     if (specular_bounce && add_zero_bounce && S.hit.light != NONE) {
         const LightD& l = sc.lights[S.hit.light];
-        if (l.kind == 2) { S.radiance += S.path_weight * mk3(l.b[0], l.b[1], l.b[2]); S.dirty = true; }
+        if (l.kind == 2) { S.emitted = mk3(l.b[0], l.b[1], l.b[2]); S.dirty = true; }
     }
 
     MatCtx mc;
@@ -430,7 +439,7 @@ RT_HD bool shade_begin(uint32_t q, const SceneD& sc, const RenderParams& rp, con
     S.wo = S.fr.to_local(-S.ray.d);
 
     if (depth + 1 > rp.max_ray_depth) {
-        if (S.dirty) w.radiance[slot] = make_float4(S.radiance.x, S.radiance.y, S.radiance.z, 0.0f);
+        if (S.dirty) add_emitted(w, S);
         return false;
     }
     return true;
@@ -529,7 +538,7 @@ RT_HD void shade_vertex(bool active, uint32_t q, const SceneD& sc, const RenderP
         RT_CHECK(vpos < w.capacity && S.slot < w.capacity);
         w.svertex[vpos] = make_uint4(S.slot, first, k, 0u);
     }
-    if (S.dirty) w.radiance[S.slot] = make_float4(S.radiance.x, S.radiance.y, S.radiance.z, 0.0f);
+    if (S.dirty) add_emitted(w, S);
     if (!alive) return;
     const V3 pw = S.path_weight * (bs.f * fabsf(bs.wi.z) / bs.pdf);
     const uint32_t spec = (bs.component & SPECULAR) ? 1u : 0u;

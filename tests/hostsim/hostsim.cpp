@@ -19,6 +19,7 @@ static thread_local std::vector<uint32_t>* g_prim_trace = nullptr;
 #include "../../include/rtcuda.h"
 #include "../../opencl-raytracing_b200/csrc/rt_build.h"
 #include "../../opencl-raytracing_b200/csrc/rt_integrator.h"
+#include "../../opencl-raytracing_b200/csrc/rt_cull.h"
 
 using namespace rt;
 
@@ -374,6 +375,14 @@ int hostsim_render(const rtcuda_scene_desc* d, const rtcuda_settings* st, rtcuda
     return hostsim_render_samples(d, st, out, tile_rank, tile_world, capacity, stats_out, 0, 0);
 }
 
+// rt_cull.h scene_raster_rect for a scene description: 1 and rect = [x0, y0, x1, y1] when pixels outside it can be dropped
+__attribute__((visibility("default")))
+int hostsim_raster_rect(const rtcuda_scene_desc* d, int* rect) {
+    HostScene hs;
+    build(hs, d);
+    return scene_raster_rect(hs.sc, rect) ? 1 : 0;
+}
+
 // sample_hi == 0: the whole frame (mean over all samples). Otherwise samples [sample_lo, sample_hi) only and the beauty plane holds
 // their un-normalised sum — the harness's rtcuda_render_samples_device (sample-range partition across ranks).
 __attribute__((visibility("default")))
@@ -422,6 +431,19 @@ int hostsim_render_samples(const rtcuda_scene_desc* d, const rtcuda_settings* st
     }
     if ((o & RTCUDA_AOV_BEAUTY) && out->beauty && np_all) {
         std::memset(out->beauty, 0, npix * 12);
+        // api.cu build_pixel_list: the beauty pass only takes the pixels whose camera rays can reach the scene bounds (rt_cull.h)
+        int rect[4];
+        if (!std::getenv("HOSTSIM_NO_PIXEL_CULL") && scene_raster_rect(sc, rect)) {
+            std::vector<uint32_t> kept;
+            for (uint32_t packed : pixels) {
+                const int x = (int)(packed & 0xffffu), y = (int)(packed >> 16);
+                if (x >= rect[0] && x <= rect[2] && y >= rect[1] && y <= rect[3]) kept.push_back(packed);
+            }
+            stats[0] += (uint64_t)(pixels.size() - kept.size()) * (sample_hi - sample_lo);   // still primary rays, dropped like raygen's culled ones
+            pixels.swap(kept);
+        }
+        const uint32_t np_all = (uint32_t)pixels.size();
+      if (np_all) {
         if (!capacity) capacity = 1u << 20;
         uint32_t shadow_k = 0;
         for (uint32_t i = 0; i < d->light_count; i++) shadow_k += d->lights[i].kind == 2 ? rp.light_sample_count : 1;
@@ -545,6 +567,7 @@ int hostsim_render_samples(const rtcuda_scene_desc* d, const rtcuda_settings* st
             size_t idx = (size_t)(pixels[i] >> 16) * W + (pixels[i] & 0xffffu);
             out->beauty[3 * idx] = accum[i].x * inv_spp; out->beauty[3 * idx + 1] = accum[i].y * inv_spp; out->beauty[3 * idx + 2] = accum[i].z * inv_spp;
         }
+      }
     }
     stats[4] = ts.nodes; stats[5] = ts.prims; stats[6] = sc.node_count; stats[7] = hs.n_levels;
     if (stats_out) std::memcpy(stats_out, stats, sizeof stats);

@@ -36,6 +36,8 @@ def lib():
         fp = C.POINTER(C.c_float)
         l.hostsim_ray_triangle.argtypes = [C.c_int, fp, fp, fp, fp, fp, C.c_float, C.c_float, fp]
         l.hostsim_ray_triangle.restype = C.c_int
+        l.hostsim_raster_rect.argtypes = [C.POINTER(_ffi.SceneDesc), C.POINTER(C.c_int)]
+        l.hostsim_raster_rect.restype = C.c_int
         _lib = l
     return _lib
 
@@ -59,3 +61,10 @@ def ray_triangle(mode, p0, p1, p2, o, d, t_min=0.0, t_max=float("inf")):
     out = (C.c_float * 3)()
     h = lib().hostsim_ray_triangle(mode, fa(p0), fa(p1), fa(p2), fa(o), fa(d), t_min, t_max, out)
     return bool(h), out[0], out[1], out[2]
+
+
+def raster_rect(scene):
+    """rt_cull.h scene_raster_rect: (x0, y0, x1, y1) inclusive, or None when every pixel is kept"""
+    holder = scene.to_desc()
+    rect = (C.c_int * 4)()
+    return tuple(rect) if lib().hostsim_raster_rect(C.byref(holder.desc), rect) else None

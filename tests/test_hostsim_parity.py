@@ -240,3 +240,47 @@ def test_texture_variants(rc, oracle, hostsim):
     assert len(np.unique(ref.albedo.reshape(-1, 3), axis=0)) > 500       # the walls really are textured
     assert ref.mip_level.max() > 0.5                                     # the trilinear wall reports a mip level
     assert_beauty_parity(out.beauty, ref.beauty)
+
+
+def test_pixels_outside_the_scene_rectangle_are_dropped_exactly(rc, oracle, hostsim, monkeypatch):
+    """rt_cull.h: pixels whose camera rays cannot reach the scene bounds take no path slots (api.cu build_pixel_list).
+    Every pixel outside the rectangle is a miss in the oracle (ids NONE, beauty exactly 0), frames are bit-identical with
+    and without the rule, and cameras / scenes that rule it out keep every pixel."""
+    import math
+    sc = load_scene("cbbunny_area_light_transforms", 192, 108)
+    rect = hostsim.raster_rect(sc)
+    assert rect is not None
+    x0, y0, x1, y1 = rect
+    inside = np.zeros((108, 192), dtype=bool)
+    inside[y0:y1 + 1, x0:x1 + 1] = True
+    assert 0.2 < inside.mean() < 0.45                       # the box covers about a quarter of the 16:9 raster
+    st = rc.RaytracerSettings(outputs=A.BEAUTY | A.DEBUG_IDS, samples_per_pixel=4)
+    ref, ostats = oracle.render(sc, st, num_threads=4)
+    assert (ref.debug_ids[~inside] == 0xffffffff).all() and (ref.beauty[~inside] == 0).all()
+    hit = ref.debug_ids[..., 0] != 0xffffffff
+    ys, xs = np.nonzero(hit)
+    assert x0 <= xs.min() and xs.max() <= x1 and y0 <= ys.min() and ys.max() <= y1
+    assert xs.min() - x0 <= 5 and x1 - xs.max() <= 5        # ... and the rectangle is tight (2 px margin + the 1e-3 growth)
+    a, sa = hostsim.render(sc, st)
+    monkeypatch.setenv("HOSTSIM_NO_PIXEL_CULL", "1")
+    b, sb = hostsim.render(sc, st)
+    assert np.array_equal(a.beauty, b.beauty) and sa["primary_rays"] == sb["primary_rays"] == ostats["primary_rays"]
+    monkeypatch.delenv("HOSTSIM_NO_PIXEL_CULL")
+    # camera inside the box / next to the geometry: the bounds straddle the camera plane -> no rectangle
+    inside_cam = load_scene("cb", 64, 64)
+    inside_cam.camera = rc.Camera.lookat_camera_perspective((0.0, 0.3, 0.0), (0, 0.3, 1.0), (0, 1, 0), False, 0.8, 64, 64)
+    assert hostsim.raster_rect(inside_cam) is None
+    # thin lens and environment light: never
+    assert hostsim.raster_rect(rc.test_scenes.out_of_focus_sphere_scene()) is None
+    assert hostsim.raster_rect(rc.test_scenes.environment_lighting_scene(rc.test_scenes.synthetic_environment_map())) is None
+    # orthographic camera
+    ortho = rc.test_scenes.cube_orthographic_scene()
+    r = hostsim.raster_rect(ortho)
+    st2 = rc.RaytracerSettings(outputs=A.DEBUG_IDS)
+    oref, _ = oracle.render(ortho, st2)
+    if r is not None:
+        ins = np.zeros(oref.debug_ids.shape[:2], dtype=bool)
+        ins[r[1]:r[3] + 1, r[0]:r[2] + 1] = True
+        assert (oref.debug_ids[~ins] == 0xffffffff).all()
+        ys, xs = np.nonzero(oref.debug_ids[..., 0] != 0xffffffff)
+        assert r[0] <= xs.min() and xs.max() <= r[2] and xs.min() - r[0] <= 6

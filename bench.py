@@ -125,6 +125,7 @@ def run_cpu_reference(scene, settings, spp_sample, threads, steps, warmup):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_py
     import copy
+    oracle_py.use_native_build()   # -O3 -march=native, compiled on THIS host (the CPU arm is built for the box it runs on)
     st = copy.copy(settings)
     st.samples_per_pixel = spp_sample
     times, rays = [], 0
@@ -238,14 +239,14 @@ def main():
     for _ in range(args.steps):
         ms, stats = one_step()
         total_ms += ms
-        for k in ("samples", "primary_rays", "bounce_rays", "shadow_rays", "kernel_launches", "extend_launches", "extend_ms",
-                  "shade_ms", "shadow_ms", "other_ms", "render_ms", "reduce_ms"):
+        for k in ("samples", "primary_rays", "bounce_rays", "shadow_rays", "primary_rays_culled", "kernel_launches", "extend_launches", "shade_launches",
+                  "shadow_launches", "extend_ms", "shade_ms", "shadow_ms", "gather_ms", "other_ms", "render_ms", "reduce_ms"):
             agg[k] = agg.get(k, 0) + stats.get(k, 0.0)
     sync_all()
     wall = time.time() - wall0
     clocks.stop_flag = True
     t = torch.tensor([total_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
-    cnt = torch.tensor([agg["samples"], agg["primary_rays"] + agg["bounce_rays"] + agg["shadow_rays"], agg["kernel_launches"]],
+    cnt = torch.tensor([agg["samples"], agg["primary_rays"] + agg["bounce_rays"] + agg["shadow_rays"], agg["kernel_launches"], agg["primary_rays_culled"]],
                        dtype=torch.float64, device=f"cuda:{local_rank}")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -257,7 +258,7 @@ def main():
         dist.all_gather(allr, mine)
         per_rank = [round(float(x.item()), 3) for x in allr]
     job_s = float(t.item()) / 1e3
-    samples, rays, launches = (float(x) for x in cnt.tolist())
+    samples, rays, launches, culled = (float(x) for x in cnt.tolist())
 
     # ---- end to end through the public API with HOST buffers: rc.render(scene, settings) per step =
     # context + scene upload (H2D) + device BVH build + render + D2H of the frame (raytracing_cpu::render also
@@ -279,26 +280,40 @@ def main():
             return out
         e2e_what = "raytracing_cuda.render(scene, settings): rtcuda_init + scene_upload (H2D, device BVH build) + render + D2H frame"
     else:
-        def e2e_call(record):   # every rank: upload + build + its tiles into HBM planes; one NCCL reduce; rank 0: D2H of the frame
+        # N GPUs through the public API = ONE call from ONE process: rc.render(scene, settings, CudaBackendSettings(num_devices=N)).
+        # The library replicates the scene (geometry sliced over the GPUs' PCIe links, forwarded over NVLink), builds the BVH on
+        # every GPU, deals the tiles, and every GPU copies its owned pixels into the caller's host frame. Rank 0 makes the call;
+        # the other torchrun ranks wait at the barrier (their GPUs are driven by rank 0's process during this leg).
+        multi_bs = rc.CudaBackendSettings(num_devices=world, device_ids=list(range(world)), tile_size=tile)
+
+        def e2e_call(record):
+            if rank != 0:
+                return None
             t_call = time.time()
-            out = rc.multi_gpu.render_distributed(sc, st, rank, world, device_id=local_rank, partition=args.partition, tile_size=tile)
+            out = rc.render(sc, st, multi_bs)
             if record:
                 e2e_each.append({"call_ms": 1e3 * (time.time() - t_call)})
             return out
-        e2e_what = ("raytracing_cuda.multi_gpu.render_distributed(scene, settings, rank, world) on every rank: rtcuda_init + scene_upload "
-                    "(H2D, device BVH build) + render of the rank's share + NCCL collective + D2H frame on rank 0")
-    if args.warmup:
-        e2e_call(False)   # one untimed call: the first allocation of a second set of path-state buffers pays the driver's page mapping
+        e2e_what = (f"raytracing_cuda.render(scene, settings, CudaBackendSettings(num_devices={world})) from one process (rank 0): rtcuda_init on {world} GPUs + "
+                    "scene_upload (H2D slices + NVLink forward, device BVH build per GPU) + render of the tile deal + D2H of the owned pixels into the host frame")
     sync_all()
-    e0 = time.time()
-    for _ in range(e2e_steps):
-        e2e_call(True)
+    if world > 1 and rank != 0:
+        # wait on the rendezvous store (host side): an NCCL barrier would park a spinning kernel on this rank's GPU while rank 0's
+        # process renders on it
+        dist.distributed_c10d._get_default_store().wait(["bench_e2e_done"])
+        e2e_s = 0.0
+    else:
+        if args.warmup:
+            e2e_call(False)   # one untimed call: the first allocation of a second set of path-state buffers pays the driver's page mapping
+        torch.cuda.synchronize()
+        e0 = time.time()
+        for _ in range(e2e_steps):
+            e2e_call(True)
+        e2e_s = (time.time() - e0)
+        if world > 1:
+            rc._ffi.load_library().rtcuda_release_cached_memory()   # rank 0's arenas on the other ranks' GPUs
+            dist.distributed_c10d._get_default_store().set("bench_e2e_done", "1")
     sync_all()
-    e2e_s = (time.time() - e0)
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local_rank}")
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_s = float(te.item())
     d2h = int(W * H * 3 * 4)
 
     if rank != 0:
@@ -307,28 +322,62 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (`extend`, closest-hit traversal): algorithmic bytes per launch
-    # = rays * (80 * nodes/ray + 48 * prims/ray + 64) (DESIGN.md "Kernels"); duration = CUDA events around every
-    # extend launch inside the timed region; node / primitive counts from one instrumented (untimed) render.
-    with rc.CudaRenderer(sc, rc.multi_gpu.backend_settings_for_rank(rank, world, local_rank, collect_stats=_ffi.STATS_COUNTERS)) as rs:
+    # ---- roofline of the three hot kernels, the dominant one first (DESIGN.md "Kernels" / SURVEY 8d):
+    #   traversal kernels  bytes = rays * (80 * nodes/ray + 48 * prims/ray + 64)   (N from one instrumented, untimed render)
+    #   shade              bytes = vertices * 160 + 32 * shadow rays emitted (+ texel bytes, not counted)
+    # duration = CUDA events around every launch of the class inside the timed region (rtcuda_stats, the library's own stream).
+    # `bound`: for the L2-resident scenes (C1-C4: BVH <= 3 MB) the traversal kernels are limited by instruction issue, not by HBM
+    # — the algorithmic GB/s below are served by L1 / L2; the ncu counters of the same build (profiles/, per-launch durations
+    # within 5 % of the CUDA-event ones) say how busy the issue slots are and how many of 32 lanes an instruction carries.
+    with rc.CudaRenderer(sc, rc.multi_gpu.backend_settings_for_rank(rank, world, local_rank, collect_stats=_ffi.STATS_COUNTERS, tile_size=tile)) as rs:
         rs.render_device(st, {"beauty": dr.planes_for(rc.AovFlags.BEAUTY)["beauty"].data_ptr()})
         cs = rs.stats()
-    ext_rays = cs["primary_rays"] - cs["primary_rays_culled"] + cs["bounce_rays"]   # rays k_extend actually walked (camera rays that miss the scene bounds never reach it)
-    ext_bytes = 80 * cs["extend_nodes"] + 48 * cs["extend_prims"] + 64 * ext_rays
-    ext_s = agg["extend_ms"] / 1e3 / args.steps
     peak, peak_src = peaks()
-    achieved = ext_bytes / ext_s / 1e9 if ext_s > 0 else None
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "extend_traffic.json")
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
-    roofline = {"kernel": "k_extend (closest-hit BVH8 traversal)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak if achieved else None, "traffic": traffic, "peak_source": peak_src,
-                "bytes_per_ray": ext_bytes / max(1, ext_rays), "nodes_per_ray": cs["extend_nodes"] / max(1, ext_rays),
-                "prims_per_ray": cs["extend_prims"] / max(1, ext_rays), "extend_rays_per_step": ext_rays,
-                "primary_rays_culled_per_step": cs["primary_rays_culled"], "launches_per_step": agg["extend_launches"] / args.steps,
-                "ms_per_launch": 1e3 * ext_s / max(1, agg["extend_launches"] / args.steps),
-                "kernel_share_of_step": {k: agg[k] / agg["render_ms"] for k in ("extend_ms", "shade_ms", "shadow_ms", "other_ms")}}
+    ncu = {}
+    npath = os.path.join(ROOT, "profiles", "ncu_counters.json")   # written by scripts/ncu_counters.py from an `ncu --set full` capture of this build
+    if os.path.exists(npath):
+        ncu = json.load(open(npath)).get(args.workload, {}) if world == 1 else {}
+    ext_rays = cs["primary_rays"] - cs["primary_rays_culled"] + cs["bounce_rays"]   # rays k_extend walked (culled camera rays never reach it)
+    sh_rays = cs["shadow_rays"]
+    steps = args.steps
+
+    def kernel_block(name, what, nbytes, items, item_name, ms_total, launches, extra):
+        sec = ms_total / 1e3 / steps
+        ach = nbytes / sec / 1e9 if sec > 0 else None
+        c = ncu.get(name, {})
+        blk = {"kernel": what, "bound": c.get("bound", "hbm"), "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak if ach else None,
+               "traffic": c.get("dram_bytes_per_launch"), "peak_source": peak_src,
+               "algorithmic_bytes_per_" + item_name: nbytes / max(1, items), item_name + "s_per_step": items,
+               "launches_per_step": launches / steps, "ms_per_step": 1e3 * sec, "ms_per_launch": 1e3 * sec / max(1.0, launches / steps),
+               "share_of_step": ms_total / max(1e-9, agg["render_ms"])}
+        for k in ("issue_active_pct", "lanes_per_inst", "dram_pct_of_peak", "l2_hit_pct", "ncu_ms_per_launch", "ncu_source"):
+            if k in c:
+                blk[k] = c[k]
+        if blk["traffic"] and sec > 0 and launches:
+            blk["dram_gbs"] = blk["traffic"] * (launches / steps) / sec / 1e9
+            blk["dram_frac"] = blk["dram_gbs"] / peak
+        blk.update(extra)
+        return blk
+
+    k_shadow = kernel_block("k_shadow", "k_shadow (any-hit BVH8 traversal of the shadow-ray queue)",
+                            80 * cs["shadow_nodes"] + 48 * cs["shadow_prims"] + 64 * sh_rays, sh_rays, "ray", agg["shadow_ms"], agg["shadow_launches"],
+                            {"nodes_per_ray": cs["shadow_nodes"] / max(1, sh_rays), "prims_per_ray": cs["shadow_prims"] / max(1, sh_rays)})
+    k_shade = kernel_block("k_shade", "k_shade (material + next-event estimation + BSDF sampling)",
+                           160 * cs["shaded_vertices"] + 32 * sh_rays, cs["shaded_vertices"], "vertex", agg["shade_ms"], agg["shade_launches"],
+                           {"shadow_rays_per_vertex": sh_rays / max(1, cs["shaded_vertices"])})
+    k_extend = kernel_block("k_extend", "k_extend (closest-hit BVH8 traversal)",
+                            80 * cs["extend_nodes"] + 48 * cs["extend_prims"] + 64 * ext_rays, ext_rays, "ray", agg["extend_ms"], agg["extend_launches"],
+                            {"nodes_per_ray": cs["extend_nodes"] / max(1, ext_rays), "prims_per_ray": cs["extend_prims"] / max(1, ext_rays),
+                             "primary_rays_culled_per_step": cs["primary_rays_culled"]})
+    blocks = sorted([k_shadow, k_shade, k_extend], key=lambda b: -b["ms_per_step"])
+    roofline = dict(blocks[0])
+    roofline["other_kernels"] = blocks[1:]
+    timed = {k: agg[k] for k in ("extend_ms", "shade_ms", "shadow_ms", "gather_ms", "other_ms")}
+    roofline["kernel_share_of_step"] = {k: v / agg["render_ms"] for k, v in timed.items()}
+    roofline["kernel_share_of_step"]["untimed_ms(resolve, finalize, memsets, gaps)"] = 1.0 - sum(timed.values()) / agg["render_ms"]
+    # whole-step cross-check: every algorithmic byte of the step over the step's time stays below the measured HBM peak only if ... it need not:
+    # the BVH bytes come from L1 / L2. Reported so that the reader can see by how much.
+    roofline["whole_step_algorithmic_gbs"] = sum(b["achieved"] * b["ms_per_step"] for b in blocks if b["achieved"]) / (1e3 * job_s / steps)
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
@@ -338,7 +387,13 @@ def main():
         cpu = {"value": ms, "unit": "Msamples/s", "mrays_per_s": mr, "cores": threads, "kind": "port", "seconds": tcpu,
                "sample": f"full {W}x{H} raster at {cpu_spp} spp (of {spp}), depth {depth}, light samples {ls}"}
 
+    # rays: every sample is one primary ray; `culled` of them end at the scene-bounds test in ray generation (or before: pixels
+    # outside the scene's raster rectangle) and are never traversed — mrays_traced_per_s leaves them out.
     line = {"metric": "Msamples/s", "value": samples / job_s / 1e6, "unit": "Msamples/s", "mrays_per_s": rays / job_s / 1e6,
+            "mrays_traced_per_s": (rays - culled) / job_s / 1e6,
+            "msamples_reaching_the_scene_per_s": (samples - culled) / job_s / 1e6,
+            "north_star_unit_note": "target '>= 2 Gsamples-rays/s': value is SAMPLES/s (camera samples, 74 % of C3's end at the scene-bounds test); "
+                                    "mrays_traced_per_s counts primary + bounce + shadow rays actually walked through the BVH",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * job_s / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": DATA_NOTE, "config": config,

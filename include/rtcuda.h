@@ -38,7 +38,8 @@ extern "C" {
 #define RTCUDA_API __attribute__((visibility("default")))
 #endif
 
-#define RTCUDA_ABI_VERSION 2u
+#define RTCUDA_ABI_VERSION 3u
+#define RTCUDA_MAX_DEVICES 8u
 #define RTCUDA_NONE 0xffffffffu
 
 typedef enum rtcuda_status {
@@ -279,7 +280,16 @@ typedef struct rtcuda_backend_settings {
      * [8, 64]. Smaller tiles balance scenes whose cost is concentrated in part of the frame (C3: the box covers a
      * quarter of the 16:9 raster) at no cost in coherence: inside a tile pixels follow a Morton curve either way. */
     uint32_t tile_size;
-    uint32_t _reserved;
+    /* Multi-GPU inside one context (ABI v3; SURVEY §8b "CudaBackendSettings{device_ids / num_gpus}", the analogue of the CPU
+     * backend's in-process worker pool, crates/raytracing-cpu/src/lib.rs:706-805): num_devices > 1 replicates the scene on
+     * device_ids[0 .. num_devices) (rtcuda_scene_upload uploads and builds on all of them, one host thread per GPU), deals the
+     * image tiles round-robin to them exactly like tile_rank / tile_world (which must then be left 0), and rtcuda_render
+     * returns the complete frame: every GPU copies the pixels it owns straight into the caller's host planes. The device
+     * variants (rtcuda_render_device, rtcuda_render_samples_device) take planes on device_ids[0]; the other GPUs send their
+     * owned pixels there over NVLink (one peer copy of a packed buffer per GPU and frame). 0 or 1: one GPU, device_id.
+     * Every pixel is the same as on one GPU, bit for bit. */
+    uint32_t num_devices;
+    int32_t device_ids[RTCUDA_MAX_DEVICES];
 } rtcuda_backend_settings;
 
 /* RenderOutput (crates/raytracing/src/renderer/mod.rs:49-59). NULL planes are skipped. */
@@ -318,7 +328,7 @@ typedef struct rtcuda_stats {
     double render_ms;                 /* CUDA-event time, inputs resident, excludes D2H */
     double bvh_build_ms;              /* last scene upload */
     double upload_ms;
-    double extend_ms, shade_ms, shadow_ms, other_ms;   /* RTCUDA_STATS_KERNEL_TIMES */
+    double extend_ms, shade_ms, shadow_ms, other_ms;   /* RTCUDA_STATS_KERNEL_TIMES (other: raygen; see gather_ms) */
     uint64_t bvh_node_count, bvh_prim_count;
     /* NaN / Inf channels of the beauty plane of the last render: the device side of the reference's scan
      * (lib.rs:813-854); the binding prints its warnings ("R component of (x, y) is NaN", first 10) when non-zero. */
@@ -333,6 +343,12 @@ typedef struct rtcuda_stats {
     /* 1 when the PLOC tree of the last upload was deeper than the traversal stack covers and the scene was rebuilt as an
      * LBVH (same pixels, usually more node fetches per ray). */
     uint64_t bvh_fallback_lbvh;
+    /* ABI v3 */
+    double gather_ms;                 /* RTCUDA_STATS_KERNEL_TIMES: the shadow-gather launches (shadow_ms is the any-hit kernel alone) */
+    /* Pixels of this context that the beauty pass did not allocate path slots for: none of their camera rays can reach the
+     * scene bounds (raster rectangle of the projected bounds; only without an environment light, pinhole / orthographic
+     * cameras). Their samples are counted in primary_rays and primary_rays_culled like the per-sample culls. */
+    uint64_t pixels_dropped;
 } rtcuda_stats;
 
 typedef struct rtcuda_ctx rtcuda_ctx;
@@ -368,6 +384,14 @@ RTCUDA_API rtcuda_status rtcuda_render_device(rtcuda_scene* scene, const rtcuda_
  * itself adds samples in index order, like render_tile, lib.rs:538-548). Beauty only: AOVs are sample-independent. */
 RTCUDA_API rtcuda_status rtcuda_render_samples_device(rtcuda_scene* scene, const rtcuda_settings* settings,
                                                       uint32_t sample_lo, uint32_t sample_hi, float* beauty_sum);
+
+/* Progressive form of the call above — the hook a viewer needs (crates/viewer/src/render_output_view.rs:84-98 calls `render`
+ * once and shows the result; with this a caller can show a converging image): ADDS the un-normalised radiance sum of
+ * samples [sample_lo, sample_hi) to the device plane `beauty_sum` in place (pixels of other ranks untouched). Starting from
+ * a zeroed plane and calling it for consecutive ranges, `beauty_sum / sample_hi` after each call is the image a render
+ * with sample_hi samples per pixel of the same streams would give (up to the association of the float sum). */
+RTCUDA_API rtcuda_status rtcuda_render_samples_accumulate_device(rtcuda_scene* scene, const rtcuda_settings* settings,
+                                                                 uint32_t sample_lo, uint32_t sample_hi, float* beauty_sum);
 
 /* Replaces raytracing_cpu::render_single_pixel (lib.rs:860-931) in the Range<u32> shape of
  * raytracing_optix::render_single_pixel (crates/raytracing-optix/src/lib.rs:172-234):

@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 NONE = 0xFFFFFFFF
-ABI_VERSION = 2
+ABI_VERSION = 3
+MAX_DEVICES = 8
 
 # enums (values must match rtcuda.h)
 CAMERA_ORTHOGRAPHIC, CAMERA_PINHOLE, CAMERA_THIN_LENS = 0, 1, 2
@@ -106,7 +107,7 @@ class Settings(C.Structure):
 class BackendSettings(C.Structure):
     _fields_ = [("device_id", C.c_int32), ("max_paths_in_flight", C.c_uint32), ("tile_rank", C.c_uint32),
                 ("tile_world", C.c_uint32), ("collect_stats", C.c_uint32), ("flags", C.c_uint32),
-                ("tile_size", C.c_uint32), ("_reserved", C.c_uint32)]
+                ("tile_size", C.c_uint32), ("num_devices", C.c_uint32), ("device_ids", C.c_int32 * 8)]
 
 
 class Outputs(C.Structure):
@@ -129,7 +130,8 @@ class Stats(C.Structure):
                 ("shadow_launches", C.c_uint64), ("render_ms", C.c_double), ("bvh_build_ms", C.c_double),
                 ("upload_ms", C.c_double), ("extend_ms", C.c_double), ("shade_ms", C.c_double),
                 ("shadow_ms", C.c_double), ("other_ms", C.c_double), ("bvh_node_count", C.c_uint64),
-                ("bvh_prim_count", C.c_uint64), ("nonfinite_values", C.c_uint64), ("primary_rays_culled", C.c_uint64), ("final_rays_skipped", C.c_uint64), ("bvh_fallback_lbvh", C.c_uint64)]
+                ("bvh_prim_count", C.c_uint64), ("nonfinite_values", C.c_uint64), ("primary_rays_culled", C.c_uint64), ("final_rays_skipped", C.c_uint64), ("bvh_fallback_lbvh", C.c_uint64),
+                ("gather_ms", C.c_double), ("pixels_dropped", C.c_uint64)]
 
 
 STATS_COUNTERS, STATS_KERNEL_TIMES = 1, 2
@@ -140,7 +142,7 @@ ABI_STRUCTS = [Camera, Shape, Instance, Light, Material, Texture, Image, SceneDe
 
 # every symbol include/rtcuda.h declares
 EXPORTED_SYMBOLS = ["rtcuda_init", "rtcuda_shutdown", "rtcuda_scene_upload", "rtcuda_scene_release", "rtcuda_release_cached_memory", "rtcuda_render",
-                    "rtcuda_render_device", "rtcuda_render_samples_device", "rtcuda_render_pixel", "rtcuda_get_stats", "rtcuda_last_error",
+                    "rtcuda_render_device", "rtcuda_render_samples_device", "rtcuda_render_samples_accumulate_device", "rtcuda_render_pixel", "rtcuda_get_stats", "rtcuda_last_error",
                     "rtcuda_abi_version", "rtcuda_abi_struct_sizes"]
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
@@ -180,6 +182,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.rtcuda_render_device.restype = C.c_int
     lib.rtcuda_render_samples_device.argtypes = [C.c_void_p, C.POINTER(Settings), C.c_uint32, C.c_uint32, C.c_void_p]
     lib.rtcuda_render_samples_device.restype = C.c_int
+    lib.rtcuda_render_samples_accumulate_device.argtypes = [C.c_void_p, C.POINTER(Settings), C.c_uint32, C.c_uint32, C.c_void_p]
+    lib.rtcuda_render_samples_accumulate_device.restype = C.c_int
     lib.rtcuda_render_pixel.argtypes = [C.c_void_p, C.POINTER(Settings), C.c_uint32, C.c_uint32, C.c_uint32,
                                         C.c_uint32, C.POINTER(PixelOutput)]
     lib.rtcuda_render_pixel.restype = C.c_int

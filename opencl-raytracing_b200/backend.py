@@ -29,6 +29,11 @@ class CudaBackendSettings:
     tile_size: int = 0                 # 0 => 64 (the reference's RenderTile grid); a power of two in [8, 64]
     collect_stats: int = 0             # _ffi.STATS_COUNTERS | _ffi.STATS_KERNEL_TIMES (True == counters)
     watertight: bool = False           # Woop's watertight triangle test instead of the reference's Moller-Trumbore
+    # Multi-GPU inside one call (the analogue of CpuBackendSettings::num_threads, lib.rs:446-457): num_devices > 1 replicates the
+    # scene on `device_ids` (default 0 .. num_devices-1), deals the tiles to them and returns the complete frame; every pixel
+    # is the one a single GPU renders.
+    num_devices: int = 0
+    device_ids: Optional[List[int]] = None
 
     def to_c(self) -> _ffi.BackendSettings:
         b = _ffi.BackendSettings()
@@ -36,6 +41,13 @@ class CudaBackendSettings:
         b.tile_rank, b.tile_world, b.collect_stats = self.tile_rank, self.tile_world, int(self.collect_stats)
         b.flags = _ffi.BACKEND_WATERTIGHT if self.watertight else 0
         b.tile_size = self.tile_size
+        ids = list(self.device_ids) if self.device_ids is not None else list(range(max(0, self.num_devices)))
+        n = self.num_devices or (len(ids) if self.device_ids is not None else 0)
+        if n > _ffi.MAX_DEVICES or n > len(ids):
+            raise ValueError(f"num_devices = {n} needs that many device_ids (at most {_ffi.MAX_DEVICES})")
+        b.num_devices = n
+        for i in range(n):
+            b.device_ids[i] = ids[i]
         return b
 
 
@@ -129,6 +141,13 @@ class CudaRenderer:
         s = settings.to_c()
         _ffi.check(self.lib, self.lib.rtcuda_render_samples_device(self._scene, C.byref(s), sample_lo, sample_hi, beauty_sum_ptr),
                    "rtcuda_render_samples_device")
+
+    def render_samples_accumulate_device(self, settings: RaytracerSettings, sample_lo: int, sample_hi: int, beauty_sum_ptr: int) -> None:
+        """Progressive rendering: ADD the un-normalised sum of samples [sample_lo, sample_hi) to the DEVICE plane in place
+        (start from zeros; `plane / sample_hi` is the image so far). See examples/progressive_viewer.py."""
+        s = settings.to_c()
+        _ffi.check(self.lib, self.lib.rtcuda_render_samples_accumulate_device(self._scene, C.byref(s), sample_lo, sample_hi, beauty_sum_ptr),
+                   "rtcuda_render_samples_accumulate_device")
 
     def render_pixel(self, settings: RaytracerSettings, x: int, y: int, sample_lo: int, sample_hi: int) -> List[SinglePixelOutput]:
         n = max(0, sample_hi - sample_lo)

@@ -11,7 +11,10 @@
 #include <cstdio>
 #include <cstring>
 #include <memory>
+#include <condition_variable>
+#include <functional>
 #include <mutex>
+#include <thread>
 #include <stdexcept>
 #include <string>
 #include <type_traits>
@@ -179,6 +182,9 @@ struct rtcuda_ctx {
     int device = 0;
     rtcuda_backend_settings bs{};
     cudaStream_t stream = nullptr;
+    // Multi-device context (backend_settings.num_devices > 1): one single-device context per GPU, subs[r] on device_ids[r]
+    // rendering the tiles of rank r of num_devices. The parent owns no stream of its own; `device` is device_ids[0].
+    std::vector<rtcuda_ctx*> subs;
 };
 
 struct rtcuda_scene {
@@ -201,6 +207,16 @@ struct rtcuda_scene {
     DevBuf<Prim> prims;
     DevBuf<ShadeRec> shade_recs;
     std::vector<rtcuda_light> host_lights;
+    // Multi-device scene: the per-GPU scenes (subs[r] belongs to ctx->subs[r]); the parent holds nothing else of the above.
+    std::vector<rtcuda_scene*> subs;
+    // ... and, in each sub-scene, what the exchange of owned pixels needs (multi_* functions below): the packed planes of this
+    // rank's pixels on its GPU, their pinned host mirror, the host copy of the pixel list; on rank 0 also the other ranks'
+    // pixel lists and a receive buffer per rank (plain cudaMalloc: peer-accessible once peer access is enabled).
+    uint32_t* packed = nullptr; size_t packed_words = 0;
+    uint32_t* h_packed = nullptr; size_t h_packed_words = 0;
+    std::vector<uint32_t> host_pixel_list;
+    std::vector<uint32_t*> peer_list; std::vector<uint32_t*> peer_recv; std::vector<size_t> peer_recv_words;
+    cudaEvent_t sent = nullptr;
     // render state
     DevBuf<uint32_t> pixel_list;
     uint32_t n_my_pixels = 0;
@@ -241,10 +257,47 @@ struct rtcuda_scene {
     ~rtcuda_scene() {
         if (frame_exec) cudaGraphExecDestroy(frame_exec);
         for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
+        if (packed) cudaFree(packed);
+        if (h_packed) cudaFreeHost(h_packed);
+        for (uint32_t* q : peer_list) if (q) cudaFree(q);
+        for (uint32_t* q : peer_recv) if (q) cudaFree(q);
+        if (sent) cudaEventDestroy(sent);
     }
 };
 
 namespace {
+
+// Rendezvous of the per-GPU host threads of a multi-device call. A thread that fails calls fail(): every waiter (now or
+// later) then returns false and unwinds, so one GPU's error cannot leave the others parked.
+struct Rendezvous {
+    std::mutex mu;
+    std::condition_variable cv;
+    int n = 1, waiting = 0;
+    uint64_t phase = 0;
+    bool failed = false;
+    bool wait() {
+        std::unique_lock<std::mutex> g(mu);
+        if (failed) return false;
+        const uint64_t my = phase;
+        if (++waiting == n) { waiting = 0; phase++; cv.notify_all(); return true; }
+        cv.wait(g, [&] { return phase != my || failed; });
+        return !failed;
+    }
+    void fail() {
+        std::lock_guard<std::mutex> g(mu);
+        failed = true;
+        cv.notify_all();
+    }
+};
+
+// How the big geometry arrays reach N GPUs (multi-device upload): the host arrays are cut into N slices, GPU r copies slice r
+// over ITS PCIe link, then forwards it to the other GPUs over NVLink (peer copies) — the host side of the transfer is paid
+// once in total instead of once per GPU (16.8 M triangles: 400 MB of pageable host memory per replica).
+struct GeoShare {
+    int rank = 0, world = 1;
+    std::vector<rtcuda_scene*>* subs = nullptr;
+    Rendezvous* meet = nullptr;
+};
 
 // ---------------------------------------------------------------------------------------------------
 // scene upload
@@ -525,7 +578,7 @@ void build_bvh(rtcuda_scene* s, const std::vector<Instance>& instances, uint32_t
     set_scene_bounds(s->sc, mn, mx, true);
 }
 
-void upload_scene(rtcuda_scene* s, const rtcuda_scene_desc* d) {
+void upload_scene(rtcuda_scene* s, const rtcuda_scene_desc* d, const GeoShare* share = nullptr) {
     cudaStream_t st = s->ctx->stream;
     validate_desc(d);
     for (uint32_t m = 0; m < d->material_count; m++) {
@@ -553,11 +606,14 @@ void upload_scene(rtcuda_scene* s, const rtcuda_scene_desc* d) {
     std::vector<rtcuda_shape> rs(d->shapes, d->shapes + d->shape_count);
     bool own_arrays = false;
     for (const rtcuda_shape& a : rs) own_arrays |= a.kind == RTCUDA_SHAPE_TRIANGLE_MESH && a.vertices != nullptr;
+    struct Piece { int which; size_t dst_off; const void* src; size_t bytes; };   // which: 0 vertices, 1 tris, 2 normals, 3 uvs (byte offsets)
+    std::vector<Piece> pieces;
     if (!own_arrays) {
-        s->vertices.upload(d->vertices, d->vertex_count * 3, st);
-        s->tris.upload(d->tris, d->tri_count * 3, st);
-        s->normals.upload(d->normals, d->normal_count * 3, st);
-        s->uvs.upload(d->uvs, d->uv_count * 2, st);
+        s->vertices.alloc(d->vertex_count * 3); s->tris.alloc(d->tri_count * 3); s->normals.alloc(d->normal_count * 3); s->uvs.alloc(d->uv_count * 2);
+        pieces.push_back({0, 0, d->vertices, d->vertex_count * 12});
+        pieces.push_back({1, 0, d->tris, d->tri_count * 12});
+        pieces.push_back({2, 0, d->normals, d->normal_count * 12});
+        pieces.push_back({3, 0, d->uvs, d->uv_count * 8});
     } else {
         uint64_t nv = 0, nt = 0, nn = 0, nuv = 0;
         for (rtcuda_shape& a : rs) {
@@ -573,10 +629,42 @@ void upload_scene(rtcuda_scene* s, const rtcuda_scene_desc* d) {
         s->vertices.alloc(nv * 3); s->tris.alloc(nt * 3); s->normals.alloc(nn * 3); s->uvs.alloc(nuv * 2);
         for (const rtcuda_shape& a : rs) {
             if (a.kind != RTCUDA_SHAPE_TRIANGLE_MESH) continue;
-            if (a.vertex_count) CK(cudaMemcpyAsync(s->vertices.p + (size_t)a.vertex_offset * 3, a.vertices, (size_t)a.vertex_count * 12, cudaMemcpyHostToDevice, st));
-            if (a.tri_count) CK(cudaMemcpyAsync(s->tris.p + (size_t)a.tri_offset * 3, a.tris, (size_t)a.tri_count * 12, cudaMemcpyHostToDevice, st));
-            if (a.normals && a.vertex_count) CK(cudaMemcpyAsync(s->normals.p + (size_t)a.normal_offset * 3, a.normals, (size_t)a.vertex_count * 12, cudaMemcpyHostToDevice, st));
-            if (a.uvs && a.vertex_count) CK(cudaMemcpyAsync(s->uvs.p + (size_t)a.uv_offset * 2, a.uvs, (size_t)a.vertex_count * 8, cudaMemcpyHostToDevice, st));
+            pieces.push_back({0, (size_t)a.vertex_offset * 12, a.vertices, (size_t)a.vertex_count * 12});
+            pieces.push_back({1, (size_t)a.tri_offset * 12, a.tris, (size_t)a.tri_count * 12});
+            if (a.normals) pieces.push_back({2, (size_t)a.normal_offset * 12, a.normals, (size_t)a.vertex_count * 12});
+            if (a.uvs) pieces.push_back({3, (size_t)a.uv_offset * 8, a.uvs, (size_t)a.vertex_count * 8});
+        }
+    }
+    {
+        auto base_of = [](rtcuda_scene* q, int which) -> uint8_t* {
+            return which == 0 ? (uint8_t*)q->vertices.p : which == 1 ? (uint8_t*)q->tris.p : which == 2 ? (uint8_t*)q->normals.p : (uint8_t*)q->uvs.p;
+        };
+        const bool shared = share && share->world > 1;
+        if (shared) {   // every GPU's arrays must exist before anybody writes into them
+            CK(cudaStreamSynchronize(st));
+            if (!share->meet->wait()) throw RtError{RTCUDA_ERR_CUDA, "another device failed during the upload"};
+        }
+        constexpr size_t SHARE_MIN = 4u << 20;   // smaller arrays: every GPU reads the host copy itself
+        for (const Piece& pc : pieces) {
+            if (!pc.bytes) continue;
+            if (!shared || pc.bytes < SHARE_MIN) {
+                CK(cudaMemcpyAsync(base_of(s, pc.which) + pc.dst_off, pc.src, pc.bytes, cudaMemcpyHostToDevice, st));
+                continue;
+            }
+            const size_t world = (size_t)share->world, slice = ((pc.bytes + world - 1) / world + 255) & ~(size_t)255;
+            const size_t lo = std::min(pc.bytes, slice * (size_t)share->rank), hi = std::min(pc.bytes, lo + slice);
+            if (hi == lo) continue;
+            uint8_t* mine = base_of(s, pc.which) + pc.dst_off + lo;
+            CK(cudaMemcpyAsync(mine, (const uint8_t*)pc.src + lo, hi - lo, cudaMemcpyHostToDevice, st));
+            for (int q = 0; q < share->world; q++) {
+                if (q == share->rank) continue;
+                rtcuda_scene* other = (*share->subs)[q];
+                CK(cudaMemcpyPeerAsync(base_of(other, pc.which) + pc.dst_off + lo, other->ctx->device, mine, s->ctx->device, hi - lo, st));
+            }
+        }
+        if (shared) {   // all slices have arrived everywhere
+            CK(cudaStreamSynchronize(st));
+            if (!share->meet->wait()) throw RtError{RTCUDA_ERR_CUDA, "another device failed during the upload"};
         }
     }
     {   // triangle indices must stay inside their mesh: checked on the device, one flag read back
@@ -744,6 +832,7 @@ void build_pixel_list(rtcuda_scene* s) {
         }
     s->n_my_pixels = (uint32_t)list.size();
     s->pixel_list.upload(list.data(), list.size(), s->ctx->stream);
+    if (s->ctx->bs.tile_world > 1) s->host_pixel_list = list;   // the multi-device exchange scatters by it
     s->beauty_list = s->pixel_list.p;
     s->n_beauty_pixels = s->n_my_pixels;
     int rect[4];
@@ -814,7 +903,7 @@ void ensure_wave(rtcuda_scene* s, uint32_t capacity, uint32_t shadow_k, uint32_t
     s->arena_capacity = capacity; s->arena_shadow_k = k; s->arena_depth = max_depth;
 }
 
-enum { CLS_EXTEND = 0, CLS_SHADE = 1, CLS_SHADOW = 2, CLS_OTHER = 3, CLS_COUNT = 4 };
+enum { CLS_EXTEND = 0, CLS_SHADE = 1, CLS_SHADOW = 2, CLS_OTHER = 3, CLS_GATHER = 4, CLS_COUNT = 5 };
 
 // The event pool and the span list are shared by direct launches and by the captured frame (whose event-record nodes keep
 // pointing at the pool's events): starting a new span list outside a capture drops the cached frame graph.
@@ -869,13 +958,17 @@ void run_batch(rtcuda_scene* s, const RenderParams& rp, Wave w, uint32_t n_paths
         w.n_in = rays + depth; w.n_out = rays + depth + 1; w.n_shadow = shadows + depth;
         { SpanGuard g(s, CLS_EXTEND, timing); launch_extend(st, s->sc, w, n_paths, depth == 0 ? s->sc.camera.near_clip : 0.0001f, fetch_ext + depth, collect, s->lc); }
         { SpanGuard g(s, CLS_SHADE, timing); launch_shade(st, s->sc, rp, w, n_paths, s->lc); }
-        if (depth < max_depth && w.shadow_k) { SpanGuard g(s, CLS_SHADOW, timing); launch_shadow(st, s->sc, w, (uint32_t)std::min<uint64_t>(0xffffffffull, (uint64_t)n_paths * std::max(1u, w.shadow_k)), fetch_sh + depth, collect, s->lc); }
+        if (depth < max_depth && w.shadow_k) {
+            { SpanGuard g(s, CLS_SHADOW, timing); launch_shadow(st, s->sc, w, (uint32_t)std::min<uint64_t>(0xffffffffull, (uint64_t)n_paths * std::max(1u, w.shadow_k)), fetch_sh + depth, collect, s->lc); }
+            { SpanGuard g(s, CLS_GATHER, timing); launch_shadow_gather(st, w, n_paths, s->lc); }
+        }
     }
 }
 
 // sample_hi == 0: the whole frame (all samples, mean). Otherwise samples [sample_lo, sample_hi) only and the beauty plane
 // receives their un-normalised sum (rtcuda_render_samples_device).
-void render_device(rtcuda_scene* s, const rtcuda_settings* settings, const rtcuda_outputs* out, uint32_t sample_lo = 0, uint32_t sample_hi = 0) {
+void render_device(rtcuda_scene* s, const rtcuda_settings* settings, const rtcuda_outputs* out, uint32_t sample_lo = 0, uint32_t sample_hi = 0,
+                   bool accumulate = false) {
     cudaStream_t st = s->ctx->stream;
     REQUIRE(out->width == s->width && out->height == s->height, "output size must equal the camera raster size");
     REQUIRE(settings->samples_per_pixel >= 1, "samples_per_pixel must be >= 1");
@@ -924,7 +1017,7 @@ void render_device(rtcuda_scene* s, const rtcuda_settings* settings, const rtcud
         samples = (uint64_t)np_all * n_samples_total;
         dropped_samples = (uint64_t)(np_all - s->n_beauty_pixels) * n_samples_total;   // every one a camera ray that misses the scene bounds
         const uint32_t nb = s->n_beauty_pixels;   // owned pixels whose rays can reach the scene bounds (build_pixel_list)
-        if (nb != npix_img) CK(cudaMemsetAsync(out->beauty, 0, npix_img * 12, st));
+        if (nb != npix_img && !accumulate) CK(cudaMemsetAsync(out->beauty, 0, npix_img * 12, st));   // (accumulate: the plane holds the running sum)
         if (nb) {
             const uint32_t shadow_k = shadow_entries_per_vertex(s, rp);
             // Wavefront size. Deep bounces keep only a fraction of a batch alive (C3: 26 % at depth 1, 8 % at depth 8)
@@ -977,7 +1070,7 @@ void render_device(rtcuda_scene* s, const rtcuda_settings* settings, const rtcud
                         launch_resolve(st, w, s->accum.p, s->lc);
                     }
                 }
-                launch_finalize(st, s->beauty_list, nb, s->width, s->accum.p, sum_mode ? 1.0f : 1.0f / (float)settings->samples_per_pixel, out->beauty, s->stats_dev.p, s->lc);
+                launch_finalize(st, s->beauty_list, nb, s->width, s->accum.p, sum_mode ? 1.0f : 1.0f / (float)settings->samples_per_pixel, out->beauty, s->stats_dev.p, accumulate, s->lc);
             };
             // frames of at least 4 Mi paths go through the graph (below that instantiating ~40 nodes per batch costs more
             // than the launches it saves); RTCUDA_NO_GRAPH=1 keeps direct launches (A/B, debugging)
@@ -991,7 +1084,7 @@ void render_device(rtcuda_scene* s, const rtcuda_settings* settings, const rtcud
                                              settings->y_strata, settings->antialias_primary_rays, settings->antialias_secondary_rays,
                                              (uint64_t)(uintptr_t)out->beauty, (uint64_t)(uintptr_t)s->arena.base, (uint64_t)(uintptr_t)s->accum.p,
                                              (uint64_t)(uintptr_t)s->stats_dev.p, (uint64_t)(uintptr_t)s->beauty_list, nb, np_batch, ns_batch, sample_lo,
-                                             sample_hi, shadow_k, (uint64_t)s->ctx->bs.collect_stats, (uint64_t)sum_mode};
+                                             sample_hi, shadow_k, (uint64_t)s->ctx->bs.collect_stats, (uint64_t)sum_mode, (uint64_t)accumulate};
                 if (!s->frame_exec || key != s->frame_key) {
                     reset_spans(s);
                     const unsigned long long l0 = s->lc.launches;
@@ -1041,11 +1134,12 @@ void render_device(rtcuda_scene* s, const rtcuda_settings* settings, const rtcud
     s->stats.shaded_vertices = h_stats[STAT_SHADED];
     s->stats.nonfinite_values = h_stats[STAT_NONFINITE];
     s->stats.primary_rays_culled = h_stats[STAT_CULLED] + dropped_samples;
+    s->stats.pixels_dropped = (o & RTCUDA_AOV_BEAUTY) && out->beauty ? np_all - s->n_beauty_pixels : 0;
     s->stats.final_rays_skipped = h_stats[STAT_FINAL_SKIPPED];
     s->stats.kernel_launches = s->lc.launches - launches0;
     s->stats.render_ms = ms;
-    double cls_ms[CLS_COUNT] = {0, 0, 0, 0};
-    uint64_t cls_n[CLS_COUNT] = {0, 0, 0, 0};
+    double cls_ms[CLS_COUNT] = {0, 0, 0, 0, 0};
+    uint64_t cls_n[CLS_COUNT] = {0, 0, 0, 0, 0};
     for (const rtcuda_scene::Span& sp : s->spans) {
         float t = 0;
         CK(cudaEventElapsedTime(&t, s->ev_pool[sp.e0], s->ev_pool[sp.e1]));
@@ -1054,6 +1148,7 @@ void render_device(rtcuda_scene* s, const rtcuda_settings* settings, const rtcud
     }
     s->stats.extend_ms = cls_ms[CLS_EXTEND]; s->stats.shade_ms = cls_ms[CLS_SHADE]; s->stats.shadow_ms = cls_ms[CLS_SHADOW];
     s->stats.other_ms = cls_ms[CLS_OTHER];
+    s->stats.gather_ms = cls_ms[CLS_GATHER];
     s->stats.extend_launches = cls_n[CLS_EXTEND]; s->stats.shade_launches = cls_n[CLS_SHADE]; s->stats.shadow_launches = cls_n[CLS_SHADOW];
 }
 
@@ -1121,6 +1216,248 @@ void render_pixel(rtcuda_scene* s, const rtcuda_settings* settings, uint32_t x, 
     CK(cudaStreamSynchronize(st));
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// multi-device contexts (backend_settings.num_devices > 1): the scene replicated on every GPU, tiles dealt round-robin,
+// one host thread per GPU per call — the in-process analogue of the CPU backend's worker pool (lib.rs:706-805)
+// ---------------------------------------------------------------------------------------------------
+void enter(rtcuda_scene* sub) {
+    CK(cudaSetDevice(sub->ctx->device));
+    tls_stream = sub->ctx->stream;
+}
+
+// f(r) on one thread per GPU; the first error (by rank) is rethrown on the caller's thread after all have finished
+template <typename F>
+void for_each_device(size_t n, F&& f) {
+    std::vector<RtError> errs(n, RtError{RTCUDA_OK, ""});
+    std::vector<std::thread> threads;
+    threads.reserve(n);
+    for (size_t r = 0; r < n; r++)
+        threads.emplace_back([&, r] {
+            try { f(r); }
+            catch (const RtError& e) { errs[r] = e; }
+            catch (const std::bad_alloc&) { errs[r] = RtError{RTCUDA_ERR_OUT_OF_MEMORY, "host allocation failed"}; }
+            catch (const std::exception& e) { errs[r] = RtError{RTCUDA_ERR_CUDA, e.what()}; }
+        });
+    for (std::thread& t : threads) t.join();
+    for (size_t r = 0; r < n; r++)
+        if (errs[r].status != RTCUDA_OK) throw RtError{errs[r].status, "device " + std::to_string(r) + ": " + errs[r].msg};
+}
+
+void multi_upload(rtcuda_ctx* ctx, const rtcuda_scene_desc* desc, rtcuda_scene* parent) {
+    const size_t n = ctx->subs.size();
+    parent->width = desc->camera.raster_width;
+    parent->height = desc->camera.raster_height;
+    parent->subs.assign(n, nullptr);
+    for (size_t r = 0; r < n; r++) {
+        parent->subs[r] = new rtcuda_scene();
+        parent->subs[r]->ctx = ctx->subs[r];
+    }
+    rtcuda_scene* first = parent->subs[0];
+    first->peer_list.assign(n, nullptr);
+    first->peer_recv.assign(n, nullptr);
+    first->peer_recv_words.assign(n, 0);
+    Rendezvous meet;
+    meet.n = (int)n;
+    for_each_device(n, [&](size_t r) {
+        try {
+            enter(parent->subs[r]);
+            GeoShare share{(int)r, (int)n, &parent->subs, &meet};
+            upload_scene(parent->subs[r], desc, &share);
+            CK(cudaEventCreateWithFlags(&parent->subs[r]->sent, cudaEventDisableTiming));
+        } catch (...) {
+            meet.fail();
+            throw;
+        }
+    });
+}
+
+void multi_release(rtcuda_scene* parent) {
+    for (rtcuda_scene* sub : parent->subs) {
+        if (!sub) continue;
+        cudaSetDevice(sub->ctx->device);
+        tls_stream = sub->ctx->stream;
+        cudaStreamSynchronize(tls_stream);
+        delete sub;
+        cudaStreamSynchronize(tls_stream);
+    }
+    parent->subs.clear();
+}
+
+struct PlaneSlot { uint32_t ch; void* ptr; };
+constexpr int N_PLANES = 7;
+void planes_of(const rtcuda_outputs& o, uint32_t outputs, PlaneSlot out[N_PLANES]) {
+    out[0] = {3, (outputs & RTCUDA_AOV_BEAUTY) ? (void*)o.beauty : nullptr};
+    out[1] = {3, (outputs & RTCUDA_AOV_NORMALS) ? (void*)o.normals : nullptr};
+    out[2] = {3, (outputs & RTCUDA_AOV_ALBEDO) ? (void*)o.albedo : nullptr};
+    out[3] = {2, (outputs & RTCUDA_AOV_UV_COORDS) ? (void*)o.uv : nullptr};
+    out[4] = {1, (outputs & RTCUDA_AOV_MIP_LEVEL) ? (void*)o.mip_level : nullptr};
+    out[5] = {2, (outputs & RTCUDA_AOV_DEBUG_IDS) ? (void*)o.debug_ids : nullptr};
+    out[6] = {1, (outputs & RTCUDA_AOV_DEBUG_DEPTH) ? (void*)o.debug_depth : nullptr};
+}
+
+// this GPU's staging planes for the requested outputs (the planes render_host uses)
+rtcuda_outputs staging_planes(rtcuda_scene* s, uint32_t o, const rtcuda_outputs& like) {
+    const size_t n = (size_t)s->width * s->height;
+    rtcuda_outputs dev{};
+    dev.width = s->width; dev.height = s->height;
+    dev.beauty = stage_plane(s->d_beauty, (o & RTCUDA_AOV_BEAUTY) && like.beauty, n * 3);
+    dev.normals = stage_plane(s->d_normals, (o & RTCUDA_AOV_NORMALS) && like.normals, n * 3);
+    dev.albedo = stage_plane(s->d_albedo, (o & RTCUDA_AOV_ALBEDO) && like.albedo, n * 3);
+    dev.uv = stage_plane(s->d_uv, (o & RTCUDA_AOV_UV_COORDS) && like.uv, n * 2);
+    dev.mip_level = stage_plane(s->d_mip, (o & RTCUDA_AOV_MIP_LEVEL) && like.mip_level, n);
+    dev.debug_ids = stage_plane(s->d_ids, (o & RTCUDA_AOV_DEBUG_IDS) && like.debug_ids, n * 2);
+    dev.debug_depth = stage_plane(s->d_depth, (o & RTCUDA_AOV_DEBUG_DEPTH) && like.debug_depth, n);
+    return dev;
+}
+
+// Gather this GPU's owned pixels of every requested plane into its packed buffer (plane after plane); returns the words used.
+size_t pack_owned(rtcuda_scene* sub, const PlaneSlot planes[N_PLANES]) {
+    cudaStream_t st = sub->ctx->stream;
+    const uint32_t np = sub->n_my_pixels;
+    size_t words = 0;
+    for (int i = 0; i < N_PLANES; i++) if (planes[i].ptr) words += (size_t)np * planes[i].ch;
+    if (words > sub->packed_words) {
+        CK(cudaStreamSynchronize(st));
+        if (sub->packed) cudaFree(sub->packed);
+        sub->packed = nullptr; sub->packed_words = 0;
+        CK(cudaMalloc((void**)&sub->packed, words * 4));
+        sub->packed_words = words;
+    }
+    size_t off = 0;
+    for (int i = 0; i < N_PLANES; i++) {
+        if (!planes[i].ptr) continue;
+        launch_pack_plane(st, 0, sub->pixel_list.p, np, sub->width, planes[i].ch, (uint32_t*)planes[i].ptr, sub->packed + off, sub->lc);
+        off += (size_t)np * planes[i].ch;
+    }
+    return words;
+}
+
+// rtcuda_render on a multi-device scene: every GPU renders its tiles and copies the pixels it owns straight into the caller's
+// host planes (its own PCIe link, its own host thread): no GPU-to-GPU hop, no second pass over the frame on the host.
+void multi_render_host(rtcuda_scene* parent, const rtcuda_settings* settings, rtcuda_outputs* out) {
+    REQUIRE(out->width == parent->width && out->height == parent->height, "output size must equal the camera raster size");
+    const uint32_t o = settings->outputs;
+    for_each_device(parent->subs.size(), [&](size_t r) {
+        rtcuda_scene* sub = parent->subs[r];
+        enter(sub);
+        cudaStream_t st = sub->ctx->stream;
+        rtcuda_outputs dev = staging_planes(sub, o, *out);
+        render_device(sub, settings, &dev);
+        PlaneSlot dp[N_PLANES], hp[N_PLANES];
+        planes_of(dev, o, dp);
+        planes_of(*out, o, hp);
+        const size_t words = pack_owned(sub, dp);
+        if (!words) return;
+        if (words > sub->h_packed_words) {
+            if (sub->h_packed) cudaFreeHost(sub->h_packed);
+            sub->h_packed = nullptr; sub->h_packed_words = 0;
+            CK(cudaMallocHost((void**)&sub->h_packed, words * 4));
+            sub->h_packed_words = words;
+        }
+        CK(cudaMemcpyAsync(sub->h_packed, sub->packed, words * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        const uint32_t np = sub->n_my_pixels, W = sub->width;
+        const uint32_t* list = sub->host_pixel_list.data();
+        size_t off = 0;
+        for (int i = 0; i < N_PLANES; i++) {
+            if (!dp[i].ptr) continue;
+            const uint32_t ch = dp[i].ch;
+            uint32_t* dst = (uint32_t*)hp[i].ptr;
+            const uint32_t* src = sub->h_packed + off;
+            for (uint32_t k = 0; k < np; k++) {
+                const uint32_t p = list[k];
+                uint32_t* d = dst + ((size_t)(p >> 16) * W + (p & 0xffffu)) * ch;
+                for (uint32_t c = 0; c < ch; c++) d[c] = src[(size_t)k * ch + c];
+            }
+            off += (size_t)np * ch;
+        }
+    });
+}
+
+// Device-plane variants on a multi-device scene: the planes live on device_ids[0]. GPU 0 renders its tiles into them; every
+// other GPU packs the pixels it owns and sends them with ONE peer copy (NVLink) into a receive buffer on GPU 0, which
+// scatters (or, for progressive sums, adds) them into the planes.
+void multi_render_device(rtcuda_scene* parent, const rtcuda_settings* settings, const rtcuda_outputs* out, uint32_t sample_lo, uint32_t sample_hi,
+                         bool accumulate) {
+    REQUIRE(out->width == parent->width && out->height == parent->height, "output size must equal the camera raster size");
+    const uint32_t o = settings->outputs;
+    rtcuda_scene* first = parent->subs[0];
+    const size_t n = parent->subs.size();
+    std::vector<size_t> sent_words(n, 0);
+    for_each_device(n, [&](size_t r) {
+        rtcuda_scene* sub = parent->subs[r];
+        enter(sub);
+        cudaStream_t st = sub->ctx->stream;
+        if (r == 0) {
+            render_device(sub, settings, out, sample_lo, sample_hi, accumulate);
+            return;
+        }
+        rtcuda_outputs dev = staging_planes(sub, o, *out);
+        render_device(sub, settings, &dev, sample_lo, sample_hi, false);
+        PlaneSlot dp[N_PLANES];
+        planes_of(dev, o, dp);
+        const size_t words = pack_owned(sub, dp);
+        sent_words[r] = words;
+        if (!words) return;
+        if (words > first->peer_recv_words[r]) {   // receive buffer of rank r on GPU 0 (slot r is only ever touched by this thread)
+            CK(cudaStreamSynchronize(st));
+            CK(cudaSetDevice(first->ctx->device));
+            if (first->peer_recv[r]) cudaFree(first->peer_recv[r]);
+            first->peer_recv[r] = nullptr; first->peer_recv_words[r] = 0;
+            const cudaError_t e = cudaMalloc((void**)&first->peer_recv[r], words * 4);
+            cudaSetDevice(sub->ctx->device);
+            CK(e);
+            first->peer_recv_words[r] = words;
+        }
+        CK(cudaMemcpyPeerAsync(first->peer_recv[r], first->ctx->device, sub->packed, sub->ctx->device, words * 4, st));
+        CK(cudaEventRecord(sub->sent, st));
+        CK(cudaStreamSynchronize(st));
+    });
+    enter(first);
+    cudaStream_t st0 = first->ctx->stream;
+    PlaneSlot up[N_PLANES];
+    planes_of(*out, o, up);
+    for (size_t r = 1; r < n; r++) {
+        rtcuda_scene* sub = parent->subs[r];
+        if (!sent_words[r]) continue;
+        if (!first->peer_list[r]) {   // rank r's pixel list, once, on GPU 0
+            CK(cudaMalloc((void**)&first->peer_list[r], std::max<size_t>(1, sub->host_pixel_list.size()) * 4));
+            CK(cudaMemcpyAsync(first->peer_list[r], sub->host_pixel_list.data(), sub->host_pixel_list.size() * 4, cudaMemcpyHostToDevice, st0));
+        }
+        CK(cudaStreamWaitEvent(st0, sub->sent, 0));
+        size_t off = 0;
+        for (int i = 0; i < N_PLANES; i++) {
+            if (!up[i].ptr) continue;
+            launch_pack_plane(st0, accumulate && i == 0 ? 2 : 1, first->peer_list[r], sub->n_my_pixels, first->width, up[i].ch, (uint32_t*)up[i].ptr,
+                              first->peer_recv[r] + off, first->lc);
+            off += (size_t)sub->n_my_pixels * up[i].ch;
+        }
+    }
+    CK(cudaStreamSynchronize(st0));
+}
+
+// rtcuda_get_stats of a multi-device scene: ray / fetch / launch counters summed over the GPUs, times = the slowest GPU
+rtcuda_stats multi_stats(const rtcuda_scene* parent) {
+    rtcuda_stats t{};
+    bool first = true;
+    for (const rtcuda_scene* sub : parent->subs) {
+        const rtcuda_stats& a = sub->stats;
+        t.samples += a.samples; t.primary_rays += a.primary_rays; t.bounce_rays += a.bounce_rays; t.shadow_rays += a.shadow_rays; t.aov_rays += a.aov_rays;
+        t.nodes_fetched += a.nodes_fetched; t.prims_fetched += a.prims_fetched; t.extend_nodes += a.extend_nodes; t.extend_prims += a.extend_prims;
+        t.shadow_nodes += a.shadow_nodes; t.shadow_prims += a.shadow_prims; t.shaded_vertices += a.shaded_vertices;
+        t.kernel_launches += a.kernel_launches; t.extend_launches += a.extend_launches; t.shade_launches += a.shade_launches; t.shadow_launches += a.shadow_launches;
+        t.nonfinite_values += a.nonfinite_values; t.primary_rays_culled += a.primary_rays_culled; t.final_rays_skipped += a.final_rays_skipped;
+        t.bvh_fallback_lbvh = std::max(t.bvh_fallback_lbvh, a.bvh_fallback_lbvh);
+        t.render_ms = std::max(t.render_ms, a.render_ms); t.bvh_build_ms = std::max(t.bvh_build_ms, a.bvh_build_ms); t.upload_ms = std::max(t.upload_ms, a.upload_ms);
+        t.extend_ms = std::max(t.extend_ms, a.extend_ms); t.shade_ms = std::max(t.shade_ms, a.shade_ms); t.shadow_ms = std::max(t.shadow_ms, a.shadow_ms);
+        t.other_ms = std::max(t.other_ms, a.other_ms); t.gather_ms = std::max(t.gather_ms, a.gather_ms);
+        t.pixels_dropped += a.pixels_dropped;
+        if (first) { t.bvh_node_count = a.bvh_node_count; t.bvh_prim_count = a.bvh_prim_count; first = false; }
+    }
+    return t;
+}
+
 template <typename F>
 rtcuda_status guarded(F&& f) {
     try {
@@ -1143,6 +1480,35 @@ rtcuda_status guarded(F&& f) {
 
 extern "C" {
 
+namespace {
+// One single-device context (the per-GPU part of rtcuda_init).
+rtcuda_ctx* make_device_ctx(const rtcuda_backend_settings& bs, int device_count) {
+    REQUIRE(bs.device_id >= 0 && bs.device_id < device_count, "device_id out of range");
+    REQUIRE(bs.tile_world <= 1 || bs.tile_rank < bs.tile_world, "tile_rank >= tile_world");
+    REQUIRE(bs.tile_size == 0 || (bs.tile_size >= 8 && bs.tile_size <= 64 && (bs.tile_size & (bs.tile_size - 1)) == 0),
+            "tile_size must be 0 or a power of two in [8, 64]");
+    auto ctx = std::make_unique<rtcuda_ctx>();
+    ctx->device = bs.device_id;
+    ctx->bs = bs;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    cudaMemPool_t pool;
+    CK(cudaDeviceGetDefaultMemPool(&pool, ctx->device));
+    uint64_t keep = UINT64_MAX;   // freed blocks stay in the pool until rtcuda_release_cached_memory
+    CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    return ctx.release();
+}
+void destroy_ctx(rtcuda_ctx* ctx) {
+    if (!ctx) return;
+    for (rtcuda_ctx* sub : ctx->subs) destroy_ctx(sub);
+    if (ctx->stream) {
+        cudaSetDevice(ctx->device);
+        cudaStreamDestroy(ctx->stream);
+    }
+    delete ctx;
+}
+}  // namespace
+
 RTCUDA_API rtcuda_status rtcuda_init(const rtcuda_backend_settings* settings, rtcuda_ctx** out_ctx) {
     return guarded([&] {
         REQUIRE(settings && out_ctx, "null argument");
@@ -1150,38 +1516,77 @@ RTCUDA_API rtcuda_status rtcuda_init(const rtcuda_backend_settings* settings, rt
         int count = 0;
         cudaError_t e = cudaGetDeviceCount(&count);
         if (e != cudaSuccess || count == 0) throw RtError{RTCUDA_ERR_NO_DEVICE, "no CUDA device: the cuda backend has no CPU fallback"};
-        REQUIRE(settings->device_id >= 0 && settings->device_id < count, "device_id out of range");
-        REQUIRE(settings->tile_world <= 1 || settings->tile_rank < settings->tile_world, "tile_rank >= tile_world");
-        REQUIRE(settings->tile_size == 0 || (settings->tile_size >= 8 && settings->tile_size <= 64 && (settings->tile_size & (settings->tile_size - 1)) == 0),
-                "tile_size must be 0 or a power of two in [8, 64]");
-        auto ctx = std::make_unique<rtcuda_ctx>();
-        ctx->device = settings->device_id;
-        ctx->bs = *settings;
-        CK(cudaSetDevice(ctx->device));
-        CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-        cudaMemPool_t pool;
-        CK(cudaDeviceGetDefaultMemPool(&pool, ctx->device));
-        uint64_t keep = UINT64_MAX;   // freed blocks stay in the pool until rtcuda_release_cached_memory
-        CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-        *out_ctx = ctx.release();
+        if (settings->num_devices <= 1) {
+            rtcuda_backend_settings bs = *settings;
+            if (bs.num_devices == 1) bs.device_id = bs.device_ids[0];
+            bs.num_devices = 0;
+            *out_ctx = make_device_ctx(bs, count);
+            return;
+        }
+        // multi-device: one sub-context per GPU, rank r of num_devices in the tile deal
+        const uint32_t n = settings->num_devices;
+        REQUIRE(n <= RTCUDA_MAX_DEVICES, "num_devices > RTCUDA_MAX_DEVICES");
+        REQUIRE(settings->tile_world <= 1, "tile_rank / tile_world cannot be combined with num_devices > 1");
+        for (uint32_t i = 0; i < n; i++) {
+            // (entries may repeat: several ranks then share a GPU — no use in production, but it lets a one-GPU box run this path)
+            REQUIRE(settings->device_ids[i] >= 0 && settings->device_ids[i] < count, "device_ids entry out of range");
+        }
+        std::unique_ptr<rtcuda_ctx, void (*)(rtcuda_ctx*)> parent(new rtcuda_ctx(), destroy_ctx);
+        parent->device = settings->device_ids[0];
+        parent->bs = *settings;
+        for (uint32_t i = 0; i < n; i++) {
+            rtcuda_backend_settings bs = *settings;
+            bs.device_id = settings->device_ids[i];
+            bs.num_devices = 0;
+            bs.tile_rank = i;
+            bs.tile_world = n;
+            parent->subs.push_back(make_device_ctx(bs, count));
+        }
+        // NVLink peer access in both directions between every pair (geometry slices are forwarded all-to-all, owned pixels go to
+        // GPU 0), for plain allocations and for the stream-ordered pools the scene arrays come from
+        for (uint32_t i = 0; i < n; i++) {
+            CK(cudaSetDevice(settings->device_ids[i]));
+            cudaMemPool_t pool;
+            CK(cudaDeviceGetDefaultMemPool(&pool, settings->device_ids[i]));
+            for (uint32_t j = 0; j < n; j++) {
+                if (settings->device_ids[i] == settings->device_ids[j]) continue;
+                int can = 0;
+                CK(cudaDeviceCanAccessPeer(&can, settings->device_ids[i], settings->device_ids[j]));
+                if (!can) continue;   // copies between the two then go through the host (still correct)
+                const cudaError_t pe = cudaDeviceEnablePeerAccess(settings->device_ids[j], 0);
+                if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) CK(pe);
+                cudaGetLastError();
+                cudaMemAccessDesc desc{};
+                desc.location.type = cudaMemLocationTypeDevice;
+                desc.location.id = settings->device_ids[j];
+                desc.flags = cudaMemAccessFlagsProtReadWrite;
+                CK(cudaMemPoolSetAccess(pool, &desc, 1));   // device j may access device i's pool memory
+            }
+        }
+        *out_ctx = parent.release();
     });
 }
 
-RTCUDA_API void rtcuda_shutdown(rtcuda_ctx* ctx) {
-    if (!ctx) return;
-    cudaSetDevice(ctx->device);
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
-    delete ctx;
-}
+RTCUDA_API void rtcuda_shutdown(rtcuda_ctx* ctx) { destroy_ctx(ctx); }
 
 RTCUDA_API rtcuda_status rtcuda_scene_upload(rtcuda_ctx* ctx, const rtcuda_scene_desc* desc, rtcuda_scene** out_scene) {
     return guarded([&] {
         REQUIRE(ctx && desc && out_scene, "null argument");
         *out_scene = nullptr;
-        CK(cudaSetDevice(ctx->device));
-        tls_stream = ctx->stream;
         auto s = std::make_unique<rtcuda_scene>();
         s->ctx = ctx;
+        if (!ctx->subs.empty()) {
+            try {
+                multi_upload(ctx, desc, s.get());
+            } catch (...) {
+                multi_release(s.get());
+                throw;
+            }
+            *out_scene = s.release();
+            return;
+        }
+        CK(cudaSetDevice(ctx->device));
+        tls_stream = ctx->stream;
         upload_scene(s.get(), desc);
         *out_scene = s.release();
     });
@@ -1189,16 +1594,27 @@ RTCUDA_API rtcuda_status rtcuda_scene_upload(rtcuda_ctx* ctx, const rtcuda_scene
 
 RTCUDA_API void rtcuda_release_cached_memory(void) {
     g_arena_cache.release_all();
-    int dev = 0;
-    cudaMemPool_t pool;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    int cur = 0, count = 0;
+    if (cudaGetDevice(&cur) != cudaSuccess || cudaGetDeviceCount(&count) != cudaSuccess) return;
+    for (int dev = 0; dev < count; dev++) {   // every device this process may have used
+        cudaMemPool_t pool;
+        if (cudaSetDevice(dev) != cudaSuccess || cudaDeviceGetDefaultMemPool(&pool, dev) != cudaSuccess) continue;
+        uint64_t reserved = 0;
+        if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) != cudaSuccess || reserved == 0) continue;
         cudaDeviceSynchronize();
         cudaMemPoolTrimTo(pool, 0);
     }
+    cudaSetDevice(cur);
+    cudaGetLastError();
 }
 
 RTCUDA_API void rtcuda_scene_release(rtcuda_scene* scene) {
     if (!scene) return;
+    if (!scene->subs.empty()) {
+        multi_release(scene);
+        delete scene;
+        return;
+    }
     cudaSetDevice(scene->ctx->device);
     tls_stream = scene->ctx->stream;
     cudaStreamSynchronize(tls_stream);
@@ -1209,6 +1625,7 @@ RTCUDA_API void rtcuda_scene_release(rtcuda_scene* scene) {
 RTCUDA_API rtcuda_status rtcuda_render(rtcuda_scene* scene, const rtcuda_settings* settings, rtcuda_outputs* outputs) {
     return guarded([&] {
         REQUIRE(scene && settings && outputs, "null argument");
+        if (!scene->subs.empty()) { multi_render_host(scene, settings, outputs); return; }
         CK(cudaSetDevice(scene->ctx->device));
         tls_stream = scene->ctx->stream;
         render_host(scene, settings, outputs);
@@ -1218,42 +1635,56 @@ RTCUDA_API rtcuda_status rtcuda_render(rtcuda_scene* scene, const rtcuda_setting
 RTCUDA_API rtcuda_status rtcuda_render_device(rtcuda_scene* scene, const rtcuda_settings* settings, rtcuda_outputs* device_outputs) {
     return guarded([&] {
         REQUIRE(scene && settings && device_outputs, "null argument");
+        if (!scene->subs.empty()) { multi_render_device(scene, settings, device_outputs, 0, 0, false); return; }
         CK(cudaSetDevice(scene->ctx->device));
         tls_stream = scene->ctx->stream;
         render_device(scene, settings, device_outputs);
     });
 }
 
-RTCUDA_API rtcuda_status rtcuda_render_samples_device(rtcuda_scene* scene, const rtcuda_settings* settings, uint32_t sample_lo,
-                                                      uint32_t sample_hi, float* beauty_sum) {
+namespace {
+rtcuda_status render_samples(rtcuda_scene* scene, const rtcuda_settings* settings, uint32_t sample_lo, uint32_t sample_hi, float* beauty_sum, bool accumulate) {
     return guarded([&] {
         REQUIRE(scene && settings && beauty_sum, "null argument");
         REQUIRE(sample_hi != 0, "empty sample range");
-        CK(cudaSetDevice(scene->ctx->device));
-        tls_stream = scene->ctx->stream;
         rtcuda_settings st = *settings;
         st.outputs = RTCUDA_AOV_BEAUTY;
         rtcuda_outputs o{};
         o.width = scene->width; o.height = scene->height;
         o.beauty = beauty_sum;
-        render_device(scene, &st, &o, sample_lo, sample_hi);
+        if (!scene->subs.empty()) { multi_render_device(scene, &st, &o, sample_lo, sample_hi, accumulate); return; }
+        CK(cudaSetDevice(scene->ctx->device));
+        tls_stream = scene->ctx->stream;
+        render_device(scene, &st, &o, sample_lo, sample_hi, accumulate);
     });
+}
+}  // namespace
+
+RTCUDA_API rtcuda_status rtcuda_render_samples_device(rtcuda_scene* scene, const rtcuda_settings* settings, uint32_t sample_lo,
+                                                      uint32_t sample_hi, float* beauty_sum) {
+    return render_samples(scene, settings, sample_lo, sample_hi, beauty_sum, false);
+}
+
+RTCUDA_API rtcuda_status rtcuda_render_samples_accumulate_device(rtcuda_scene* scene, const rtcuda_settings* settings, uint32_t sample_lo,
+                                                                 uint32_t sample_hi, float* beauty_sum) {
+    return render_samples(scene, settings, sample_lo, sample_hi, beauty_sum, true);
 }
 
 RTCUDA_API rtcuda_status rtcuda_render_pixel(rtcuda_scene* scene, const rtcuda_settings* settings, uint32_t x, uint32_t y,
                                              uint32_t sample_lo, uint32_t sample_hi, rtcuda_pixel_output* out) {
     return guarded([&] {
         REQUIRE(scene && settings && (out || sample_hi == sample_lo), "null argument");
-        CK(cudaSetDevice(scene->ctx->device));
-        tls_stream = scene->ctx->stream;
-        render_pixel(scene, settings, x, y, sample_lo, sample_hi, out);
+        rtcuda_scene* one = scene->subs.empty() ? scene : scene->subs[0];   // a pixel's samples do not depend on the tile deal
+        CK(cudaSetDevice(one->ctx->device));
+        tls_stream = one->ctx->stream;
+        render_pixel(one, settings, x, y, sample_lo, sample_hi, out);
     });
 }
 
 RTCUDA_API rtcuda_status rtcuda_get_stats(const rtcuda_scene* scene, rtcuda_stats* out) {
     return guarded([&] {
         REQUIRE(scene && out, "null argument");
-        *out = scene->stats;
+        *out = scene->subs.empty() ? scene->stats : multi_stats(scene);
     });
 }
 

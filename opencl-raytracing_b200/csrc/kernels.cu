@@ -302,6 +302,7 @@ __global__ void __launch_bounds__(BLOCK) k_resolve(const __grid_constant__ Wave 
 
 // Pixel mean + the NaN / Inf scan of the beauty plane (lib.rs:813-854: every channel is classified): the count of
 // non-finite channels goes to the stats block; the caller side prints the reference's warnings from it.
+template <bool ACCUMULATE>
 __global__ void __launch_bounds__(BLOCK) k_finalize(const uint32_t* pixel_list, uint32_t n, uint32_t width, const float4* accum,
                                                      float inv_spp, float* beauty, unsigned long long* stats) {
     const uint32_t i = blockIdx.x * BLOCK + threadIdx.x;
@@ -310,7 +311,8 @@ __global__ void __launch_bounds__(BLOCK) k_finalize(const uint32_t* pixel_list, 
         const uint32_t packed = pixel_list[i];
         const size_t idx = (size_t)(packed >> 16) * width + (packed & 0xffffu);
         const float4 a = accum[i];
-        const float r = a.x * inv_spp, g = a.y * inv_spp, b = a.z * inv_spp;  // `radiance /= spp` is a multiply by the reciprocal (vec3.rs:122-126)
+        float r = a.x * inv_spp, g = a.y * inv_spp, b = a.z * inv_spp;  // `radiance /= spp` is a multiply by the reciprocal (vec3.rs:122-126)
+        if (ACCUMULATE) { r += beauty[3 * idx]; g += beauty[3 * idx + 1]; b += beauty[3 * idx + 2]; }   // progressive: add this range's sum to the plane
         beauty[3 * idx] = r;
         beauty[3 * idx + 1] = g;
         beauty[3 * idx + 2] = b;
@@ -324,12 +326,11 @@ void launch_raygen(cudaStream_t st, const SceneD& sc, const RenderParams& rp, co
     lc.launches++;
 }
 static uint32_t persistent_grid(const void* kernel, uint32_t n_max) {
-    static int sm_count = 0;
-    if (!sm_count) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-    }
+    static int sm_counts[64] = {0};   // per device: a process may drive several GPUs (multi-device contexts)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int& sm_count = sm_counts[dev & 63];
+    if (!sm_count) cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, BLOCK, 0);
     const uint32_t resident = (uint32_t)sm_count * (uint32_t)(per_sm > 0 ? per_sm : 1);
@@ -349,16 +350,43 @@ void launch_shade(cudaStream_t st, const SceneD& sc, const RenderParams& rp, con
 void launch_shadow(cudaStream_t st, const SceneD& sc, const Wave& w, uint32_t n_max, uint32_t* fetch_counter, bool stats, LaunchCounter& lc) {
     if (stats) k_shadow<true><<<persistent_grid((const void*)k_shadow<true>, n_max), BLOCK, 0, st>>>(sc, w, fetch_counter);
     else k_shadow<false><<<persistent_grid((const void*)k_shadow<false>, n_max), BLOCK, 0, st>>>(sc, w, fetch_counter);
+    lc.launches++;
+}
+void launch_shadow_gather(cudaStream_t st, const Wave& w, uint32_t n_max, LaunchCounter& lc) {
     k_shadow_gather<<<persistent_grid((const void*)k_shadow_gather, n_max), BLOCK, 0, st>>>(w);
-    lc.launches += 2;
+    lc.launches++;
 }
 void launch_resolve(cudaStream_t st, const Wave& w, float4* accum, LaunchCounter& lc) {
     k_resolve<<<grid_for(w.n_pixels), BLOCK, 0, st>>>(w, accum);
     lc.launches++;
 }
 void launch_finalize(cudaStream_t st, const uint32_t* pixel_list, uint32_t n_pixels, uint32_t width, const float4* accum, float inv_spp,
-                     float* beauty, unsigned long long* stats, LaunchCounter& lc) {
-    k_finalize<<<grid_for(n_pixels), BLOCK, 0, st>>>(pixel_list, n_pixels, width, accum, inv_spp, beauty, stats);
+                     float* beauty, unsigned long long* stats, bool accumulate, LaunchCounter& lc) {
+    if (accumulate) k_finalize<true><<<grid_for(n_pixels), BLOCK, 0, st>>>(pixel_list, n_pixels, width, accum, inv_spp, beauty, stats);
+    else k_finalize<false><<<grid_for(n_pixels), BLOCK, 0, st>>>(pixel_list, n_pixels, width, accum, inv_spp, beauty, stats);
+    lc.launches++;
+}
+
+// Multi-device exchange of owned pixels (api.cu multi_*): a plane of `ch` 32-bit channels per pixel <-> the packed run of the
+// pixels of one rank's list. PACK reads the plane; UNPACK writes (or, for progressive sums, adds floats to) it.
+template <int MODE>   // 0 pack, 1 unpack, 2 unpack-add (float)
+__global__ void __launch_bounds__(BLOCK) k_pack_plane(const uint32_t* pixel_list, uint32_t n, uint32_t width, uint32_t ch, uint32_t* plane, uint32_t* packed) {
+    const uint32_t i = blockIdx.x * BLOCK + threadIdx.x;
+    if (i >= n * ch) return;
+    const uint32_t pix = i / ch, c = i - pix * ch;
+    const uint32_t p = pixel_list[pix];
+    const size_t at = ((size_t)(p >> 16) * width + (p & 0xffffu)) * ch + c;
+    if (MODE == 0) packed[i] = plane[at];
+    else if (MODE == 1) plane[at] = packed[i];
+    else plane[at] = __float_as_uint(__uint_as_float(plane[at]) + __uint_as_float(packed[i]));
+}
+void launch_pack_plane(cudaStream_t st, int mode, const uint32_t* pixel_list, uint32_t n, uint32_t width, uint32_t ch, uint32_t* plane, uint32_t* packed,
+                       LaunchCounter& lc) {
+    if (!n) return;
+    const uint32_t grid = grid_for(n * ch);
+    if (mode == 0) k_pack_plane<0><<<grid, BLOCK, 0, st>>>(pixel_list, n, width, ch, plane, packed);
+    else if (mode == 1) k_pack_plane<1><<<grid, BLOCK, 0, st>>>(pixel_list, n, width, ch, plane, packed);
+    else k_pack_plane<2><<<grid, BLOCK, 0, st>>>(pixel_list, n, width, ch, plane, packed);
     lc.launches++;
 }
 

@@ -13,9 +13,13 @@ void launch_extend(cudaStream_t st, const SceneD& sc, const Wave& w, uint32_t n_
                    LaunchCounter& lc);
 void launch_shade(cudaStream_t st, const SceneD& sc, const RenderParams& rp, const Wave& w, uint32_t n_max, LaunchCounter& lc);
 void launch_shadow(cudaStream_t st, const SceneD& sc, const Wave& w, uint32_t n_max, uint32_t* fetch_counter, bool stats, LaunchCounter& lc);
+void launch_shadow_gather(cudaStream_t st, const Wave& w, uint32_t n_max, LaunchCounter& lc);
 void launch_resolve(cudaStream_t st, const Wave& w, float4* accum, LaunchCounter& lc);
 void launch_finalize(cudaStream_t st, const uint32_t* pixel_list, uint32_t n_pixels, uint32_t width, const float4* accum,
-                     float inv_spp, float* beauty, unsigned long long* stats, LaunchCounter& lc);
+                     float inv_spp, float* beauty, unsigned long long* stats, bool accumulate, LaunchCounter& lc);
+// multi-device exchange: mode 0 pack plane -> packed, 1 unpack packed -> plane, 2 unpack adding floats (planes of `ch` 32-bit channels)
+void launch_pack_plane(cudaStream_t st, int mode, const uint32_t* pixel_list, uint32_t n, uint32_t width, uint32_t ch, uint32_t* plane,
+                       uint32_t* packed, LaunchCounter& lc);
 void launch_aov(cudaStream_t st, const SceneD& sc, const RenderParams& rp, const uint32_t* pixel_list, uint32_t n_pixels,
                 const AovPlanes& planes, unsigned long long* stats, bool collect, LaunchCounter& lc);
 // single-pixel diagnostics (render_single_pixel): one thread per sample index

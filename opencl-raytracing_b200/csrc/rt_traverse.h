@@ -139,8 +139,12 @@ RT_HD uint32_t byte_of(uint32_t w) {
 // are tested: equal-t ties go to the larger (geom_id, prim_id) (the reference resolves them by its own BVH2 leaf
 // order, "later hit overwrites", geometry.rs:335 / accel.rs:159-171, which no other tree can reproduce), so
 // frames stay bit-reproducible although lanes pick up rays dynamically and the builder packs primitives with atomics.
+#ifndef RT_ANYHIT_ORDERED
+#define RT_ANYHIT_ORDERED 0   // 1: any-hit walks keep the octant order too (A/B switch)
+#endif
 template <bool ANY_HIT, bool STATS>
 struct Traversal {
+    static constexpr bool UNORDERED = ANY_HIT && !RT_ANYHIT_ORDERED;
     V3 o, d, idir;
     float t_min, closest;
     uint32_t octinv;
@@ -187,7 +191,7 @@ struct Traversal {
         if (ngroup.y & 0xff000000u) stack[sp++] = ngroup;
         // closest-hit walks pop the children of a node front to back (hit-mask position = slot ^ octinv); an any-hit walk
         // has no use for the order: positions are the slots themselves, and the per-node octant permutation is not computed
-        const uint32_t slot = ANY_HIT ? (uint32_t)bit - 24u : ((uint32_t)bit - 24u) ^ octinv;
+        const uint32_t slot = UNORDERED ? (uint32_t)bit - 24u : ((uint32_t)bit - 24u) ^ octinv;
         const uint32_t rel = (uint32_t)popc32(hits & ~(0xffffffffu << slot) & 0xffu);
         RT_CHECK(ngroup.x + rel < sc.node_count);
         const Node8* node = sc.nodes + (ngroup.x + rel);
@@ -223,7 +227,7 @@ struct Traversal {
         uint32_t hitmask = 0;
         {
             const uint32_t inner4 = (meta_lo & (meta_lo << 1)) & 0x10101010u;   // bit 4 set <=> (meta & 0x18) == 0x18
-            const uint32_t index4 = ANY_HIT ? (meta_lo & 0x1f1f1f1fu) : (meta_lo ^ (octinv4 & ((inner4 >> 4) * 0x07u))) & 0x1f1f1f1fu;
+            const uint32_t index4 = UNORDERED ? (meta_lo & 0x1f1f1f1fu) : (meta_lo ^ (octinv4 & ((inner4 >> 4) * 0x07u))) & 0x1f1f1f1fu;
             const uint32_t bits4 = (meta_lo >> 5) & 0x07070707u;
             child<0>(bits4, index4, nearx0, farx0, neary0, fary0, nearz0, farz0, a15, cn, af, cf, tf_cap, hitmask);
             child<1>(bits4, index4, nearx0, farx0, neary0, fary0, nearz0, farz0, a15, cn, af, cf, tf_cap, hitmask);
@@ -232,7 +236,7 @@ struct Traversal {
         }
         {
             const uint32_t inner4 = (meta_hi & (meta_hi << 1)) & 0x10101010u;
-            const uint32_t index4 = ANY_HIT ? (meta_hi & 0x1f1f1f1fu) : (meta_hi ^ (octinv4 & ((inner4 >> 4) * 0x07u))) & 0x1f1f1f1fu;
+            const uint32_t index4 = UNORDERED ? (meta_hi & 0x1f1f1f1fu) : (meta_hi ^ (octinv4 & ((inner4 >> 4) * 0x07u))) & 0x1f1f1f1fu;
             const uint32_t bits4 = (meta_hi >> 5) & 0x07070707u;
             child<0>(bits4, index4, nearx1, farx1, neary1, fary1, nearz1, farz1, a15, cn, af, cf, tf_cap, hitmask);
             child<1>(bits4, index4, nearx1, farx1, neary1, fary1, nearz1, farz1, a15, cn, af, cf, tf_cap, hitmask);

@@ -122,8 +122,8 @@ class DistributedRenderer:
         for name, flag, ch in PLANES:
             if outputs & flag:
                 key = (name, ch)
-                if key not in self._planes:
-                    self._planes[key] = torch.zeros((self.height, self.width, ch), dtype=torch.float32, device=self.device)
+                if key not in self._planes:   # (the library zero-fills the pixels of other ranks itself)
+                    self._planes[key] = torch.empty((self.height, self.width, ch), dtype=torch.float32, device=self.device)
                 planes[name] = self._planes[key]
         return planes
 
@@ -131,6 +131,10 @@ class DistributedRenderer:
         """This rank's share of the frame in HBM planes. partition="samples": the beauty plane holds this rank's sample
         range already multiplied by 1 / spp (so that the reduce yields the mean); AOVs come from rank 0 alone."""
         planes = self.planes_for(AovFlags(settings.outputs))
+        # The library renders on its own non-blocking stream: whatever torch still has in flight on these planes (the previous
+        # frame's index_select / gather reads, the allocation of a fresh plane) must be done before the library writes them;
+        # the library itself synchronises its stream before it returns, so torch may read the planes right after.
+        self.torch.cuda.current_stream(self.device).synchronize()
         if self.partition == "samples" and self.world > 1:
             lo, hi = sample_range_for_rank(settings.samples_per_pixel, self.rank, self.world)
             if "beauty" in planes:

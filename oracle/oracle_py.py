@@ -35,14 +35,39 @@ def build(force: bool = False) -> str:
 
 
 _lib = None
+_lib_path = LIB_PATH
+
+
+def use_native_build() -> str:
+    """The CPU-baseline build (bench.py): the same oracle.cpp compiled `-O3 -march=native` ON THE HOST IT RUNS ON
+    (BASELINE.md / SURVEY 8d), still -ffp-contract=off so its pixels are the portable build's. Kept apart from liboracle.so,
+    which is built -O2 for any x86-64 host because the prebuilt file travels from the build container to the GPU box."""
+    global _lib, _lib_path
+    import hashlib
+    import platform
+    cpu = ""
+    try:
+        cpu = next(l for l in open("/proc/cpuinfo") if l.startswith("model name"))
+    except Exception:
+        cpu = platform.processor()
+    tag = hashlib.sha1((cpu + platform.machine()).encode()).hexdigest()[:10]
+    path = os.path.join(_HERE, f"liboracle_native_{tag}.so")
+    src = os.path.join(_HERE, "oracle.cpp")
+    hdr = os.path.join(os.path.dirname(_HERE), "include", "rtcuda.h")
+    if not os.path.exists(path) or os.path.getmtime(path) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["g++", "-O3", "-march=native", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-pthread",
+                               "-shared", "-o", path, src])
+    if path != _lib_path:
+        _lib, _lib_path = None, path
+    return path
 
 
 def lib() -> C.CDLL:
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        if _lib_path == LIB_PATH and not os.path.exists(LIB_PATH):
             build()
-        l = C.CDLL(LIB_PATH)
+        l = C.CDLL(_lib_path)
         l.oracle_render.argtypes = [C.POINTER(_ffi.SceneDesc), C.POINTER(_ffi.Settings), C.POINTER(_ffi.Outputs), C.c_uint32,
                                     C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(OracleStats)]
         l.oracle_render.restype = C.c_int

@@ -501,3 +501,83 @@ def test_general_surface_kernel_batched(rc, oracle, name):
     la, lb = luminance(out.beauty), luminance(ref.beauty)
     assert abs(np.nanmean(la) - np.nanmean(lb)) <= 2e-3 * abs(np.nanmean(lb))
     print(f"\n[parity] {name} 16 spp: {rep}")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Multi-GPU behind the C ABI (backend_settings.num_devices): one process, one call, the complete frame
+# ---------------------------------------------------------------------------------------------------------------------
+def _device_ids(n):
+    import torch
+    have = torch.cuda.device_count()
+    return [i % have for i in range(n)]      # on a one-GPU box the ranks share the GPU: same code path, same pixels
+
+
+@pytest.mark.parametrize("n,tile", [(2, 0), (3, 16), (8, 16)])
+def test_multi_device_render_is_bit_identical(rc, n, tile):
+    """rc.render(scene, settings, CudaBackendSettings(num_devices=N)): tiles dealt to N sub-contexts inside the library, every
+    GPU copies its owned pixels into the caller's host planes — every plane equals the single-GPU frame bit for bit"""
+    sc = load_scene("cb_texture", 400, 225)
+    st = rc.RaytracerSettings(outputs=dbg() | A.BEAUTY, samples_per_pixel=4)
+    one, s1 = gpu_render(rc, sc, st)
+    many, sn = gpu_render(rc, sc, st, num_devices=n, device_ids=_device_ids(n), tile_size=tile, collect_stats=1)
+    for plane in ("beauty", "normals", "albedo", "uv", "mip_level", "debug_ids", "debug_depth"):
+        assert np.array_equal(getattr(one, plane), getattr(many, plane)), plane
+    assert sn["samples"] == s1["samples"] and sn["primary_rays"] == s1["primary_rays"] and sn["shadow_rays"] == s1["shadow_rays"]
+    assert sn["bounce_rays"] == s1["bounce_rays"] and sn["nodes_fetched"] > 0
+
+
+def test_multi_device_device_planes_and_progressive_sums(rc):
+    """rtcuda_render_device / rtcuda_render_samples_device / ..._accumulate_device on a multi-device scene: planes on
+    device_ids[0], owned pixels of the other GPUs arrive by peer copy; progressive accumulation converges to the frame"""
+    import torch
+    sc = load_scene("cb", 256, 192)
+    st = rc.RaytracerSettings(outputs=A.BEAUTY | A.NORMALS, samples_per_pixel=12, light_sample_count=2)
+    full, _ = gpu_render(rc, sc, st)
+    ids = _device_ids(4)
+    with rc.CudaRenderer(sc, rc.CudaBackendSettings(num_devices=4, device_ids=ids, tile_size=16)) as r:
+        dev = f"cuda:{ids[0]}"
+        beauty = torch.full((192, 256, 3), 7.0, dtype=torch.float32, device=dev)
+        normals = torch.full((192, 256, 3), 7.0, dtype=torch.float32, device=dev)
+        torch.cuda.synchronize()
+        r.render_device(st, {"beauty": beauty.data_ptr(), "normals": normals.data_ptr()})
+        assert np.array_equal(beauty.cpu().numpy(), full.beauty) and np.array_equal(normals.cpu().numpy(), full.normals)
+        r.render_samples_device(st, 0, 12, beauty.data_ptr())
+        inv = torch.tensor(1.0 / 12, dtype=torch.float32)
+        assert np.array_equal((beauty.cpu() * inv).numpy(), full.beauty)
+        acc = torch.zeros_like(beauty)
+        torch.cuda.synchronize()
+        for lo, hi in ((0, 4), (4, 5), (5, 12)):
+            r.render_samples_accumulate_device(st, lo, hi, acc.data_ptr())
+        np.testing.assert_allclose((acc.cpu() * inv).numpy(), full.beauty, rtol=2e-6, atol=1e-7)
+        assert r.render_pixel(st, 100, 100, 0, 2)[0].sample_index == 0
+    with pytest.raises(rc._ffi.RtCudaError):
+        rc.CudaRenderer(sc, rc.CudaBackendSettings(num_devices=2, device_ids=[0, 99]))
+    with pytest.raises(rc._ffi.RtCudaError):
+        rc.CudaRenderer(sc, rc.CudaBackendSettings(num_devices=2, device_ids=_device_ids(2), tile_world=2, tile_rank=1))
+
+
+def test_progressive_accumulation_single_device(rc):
+    """the viewer hook: consecutive sample ranges added in place; plane / hi is the image so far (examples/progressive_viewer.py)"""
+    import torch
+    sc = load_scene("cbbunny_area_light_transforms", 320, 180)
+    st = rc.RaytracerSettings(samples_per_pixel=16)
+    with rc.CudaRenderer(sc) as r:
+        full = r.render(st).beauty
+        acc = torch.zeros((180, 320, 3), dtype=torch.float32, device="cuda:0")
+        torch.cuda.synchronize()
+        for lo, hi in ((0, 1), (1, 2), (2, 4), (4, 8), (8, 16)):
+            r.render_samples_accumulate_device(st, lo, hi, acc.data_ptr())
+            img = (acc / hi).cpu().numpy()
+            assert np.isfinite(img).all()
+        np.testing.assert_allclose(img, full, rtol=3e-6, atol=1e-7)
+
+
+def test_multi_device_large_mesh_upload_is_shared(rc):
+    """geometry above the sharing threshold travels once over PCIe (one slice per GPU) and is forwarded between the GPUs:
+    the replicas are identical to a single-GPU upload (same frame)"""
+    base = load_scene("cb", 256, 256)
+    sc = rc.test_scenes.synthetic_mesh_scene(base, 1024, 512)       # 12 MB of indices, 6 MB of vertices and normals
+    st = rc.RaytracerSettings(outputs=A.BEAUTY | A.DEBUG_IDS, samples_per_pixel=2, light_sample_count=1)
+    one, _ = gpu_render(rc, sc, st)
+    many, _ = gpu_render(rc, sc, st, num_devices=3, device_ids=_device_ids(3))
+    assert np.array_equal(one.beauty, many.beauty) and np.array_equal(one.debug_ids, many.debug_ids)

@@ -903,6 +903,7 @@ void ensure_wave(rtcuda_scene* s, uint32_t capacity, uint32_t shadow_k, uint32_t
     s->arena_capacity = capacity; s->arena_shadow_k = k; s->arena_depth = max_depth;
 }
 
+constexpr size_t MAX_BATCH = (size_t)1 << 28;   // path slots per wavefront batch (see render_device)
 enum { CLS_EXTEND = 0, CLS_SHADE = 1, CLS_SHADOW = 2, CLS_OTHER = 3, CLS_GATHER = 4, CLS_COUNT = 5 };
 
 // The event pool and the span list are shared by direct launches and by the captured frame (whose event-record nodes keep
@@ -1020,10 +1021,11 @@ void render_device(rtcuda_scene* s, const rtcuda_settings* settings, const rtcud
         if (nb != npix_img && !accumulate) CK(cudaMemsetAsync(out->beauty, 0, npix_img * 12, st));   // (accumulate: the plane holds the running sum)
         if (nb) {
             const uint32_t shadow_k = shadow_entries_per_vertex(s, rp);
-            // Wavefront size. Deep bounces keep only a fraction of a batch alive (C3: 26 % at depth 1, 8 % at depth 8)
-            // and every launch of a persistent kernel ends with a drain tail, so batches are sized for the 180 GB of
-            // HBM3e, not for L2: 64 Mi paths by default (~17 GB of path state with 4 light samples per vertex), capped
-            // to 40 % of the free device memory.
+            // Wavefront size. Deep bounces keep only a fraction of a batch alive (C3: 15 % fewer per bounce, 30 % left at
+            // depth 8) and every launch of a persistent kernel ends with a drain tail, so batches are sized for the 180 GB
+            // of HBM3e, not for L2: up to 256 Mi paths (336 B of path state each with 4 light samples per vertex), capped
+            // to 40 % of the free device memory. C3's 143 M live paths are ONE batch of 111 launches (48 GB); with 64 Mi-path
+            // batches the same frame took 327 launches and 3.4 % longer (profiles/r3a_ab.log).
             uint32_t capacity = s->ctx->bs.max_paths_in_flight;
             if (!capacity)
                 if (const char* env = std::getenv("RTCUDA_MAX_PATHS")) capacity = (uint32_t)std::strtoul(env, nullptr, 0);  // tuning aid
@@ -1032,7 +1034,7 @@ void render_device(rtcuda_scene* s, const rtcuda_settings* settings, const rtcud
                 // wavefront this job wants settles the size without asking the driver: cudaMemGetInfo is a trip into the
                 // kernel driver (it queues behind NVML queries of a monitoring thread and other processes' calls) and sat
                 // inside the render window with the GPU idle — 5-35 ms per frame on a busy box (profiles/r1s_gap.log).
-                const size_t want = std::min<size_t>(1u << 26, std::max<size_t>(1024, (size_t)nb * n_samples_total));
+                const size_t want = std::min<size_t>(MAX_BATCH, std::max<size_t>(1024, (size_t)nb * n_samples_total));
                 const size_t held = std::max(s->arena.base ? s->arena.bytes : 0, g_arena_cache.largest(s->ctx->device));
                 if (held >= arena_bytes(want, shadow_k, rp.max_ray_depth)) capacity = (uint32_t)want;
             }
@@ -1041,8 +1043,9 @@ void render_device(rtcuda_scene* s, const rtcuda_settings* settings, const rtcud
                 size_t free_b = 0, total_b = 0;
                 CK(cudaMemGetInfo(&free_b, &total_b));
                 const size_t have_b = free_b + s->wave_bytes();
-                capacity = (uint32_t)std::min<size_t>(1u << 26, (size_t)(0.4 * (double)have_b) / bytes_per_slot);
+                capacity = (uint32_t)std::min<size_t>(std::min<size_t>(MAX_BATCH, std::max<size_t>(1024, (size_t)nb * n_samples_total)), (size_t)(0.4 * (double)have_b) / bytes_per_slot);
             }
+            capacity = std::min(capacity, (uint32_t)(0xffffffffull / std::max(1u, shadow_k)));   // shadow-ray queue positions are 32-bit
             capacity = std::max(capacity, 1024u);
             const uint32_t np_batch = std::min(nb, capacity);
             // samples per batch: as many as fit, then evened out over the batches (256 spp in batches of 124 would end with a

@@ -579,6 +579,27 @@ struct AovPlanes {  // device planes, row-major y*W+x; null = not requested
 };
 struct FirstHit { bool hit; V2 uv; V3 normal, albedo; bool has_mip; float mip; uint32_t geom, prim; float t; };
 
+// The traversal intersects world-space triangles (one transform per triangle at build time instead of one per ray and
+// instance); the reference intersects in OBJECT space: the ray goes through the instance's inverse transform and
+// Moller-Trumbore runs on the mesh's own vertices (intersect_shape, geometry.rs:92-136; t is shared between the spaces).
+// Both are the same hit to rounding, but on small triangles the barycentrics differ in the 4th decimal (a 5 mm triangle
+// seen from 4 m resolves its hit point to ~1e-6, i.e. ~2e-4 of its edge) — visible in the uv AOV of meshes without uvs, where
+// uv IS the barycentrics. The first-hit AOV pass (one ray per pixel) therefore repeats the test of the WINNING triangle the
+// reference's way and reports those (t, u, v): same operations in the same order, un-fused in this translation unit.
+RT_HD void refine_triangle_hit_in_object_space(const SceneD& sc, const Ray& ray, Hit& h) {
+    if (sc.watertight) return;
+    const Prim* pr = sc.prims + h.prim;
+    if (f2u(ldg(&pr->c).w) != 0u) return;   // spheres are intersected in object space already
+    const uint32_t geom = f2u(ldg(&pr->a).w), prim_id = f2u(ldg(&pr->b).w);
+    const Instance& inst = sc.instances[geom];
+    const uint32_t* t3 = sc.tris + 3 * (size_t)(inst.tri_offset + prim_id);
+    const V3 p0 = load3(sc.vertices, inst.vertex_offset + ldg(t3)), p1 = load3(sc.vertices, inst.vertex_offset + ldg(t3 + 1)),
+             p2 = load3(sc.vertices, inst.vertex_offset + ldg(t3 + 2));
+    const V3 oo = apply_point(inst.w2o, ray.o), od = apply_vector(inst.w2o, ray.d);
+    float t, u, v;
+    if (triangle_t(p0, p1, p2, oo, od, sc.camera.near_clip, sc.camera.far_clip, t, u, v)) { h.t = t; h.u = u; h.v = v; }
+}
+
 template <bool STATS>
 RT_HD FirstHit first_hit(const SceneD& sc, const RenderParams& rp, uint32_t px, uint32_t py, uint32_t sidx, TraverseStats* stats) {
     Sampler s;
@@ -592,6 +613,7 @@ RT_HD FirstHit first_hit(const SceneD& sc, const RenderParams& rp, uint32_t px, 
     r.geom = NONE; r.prim = NONE; r.t = 0.0f;
     Hit h;
     if (!traverse<false, STATS>(sc, ray.o, ray.d, sc.camera.near_clip, sc.camera.far_clip, h, stats)) return r;
+    refine_triangle_hit_in_object_space(sc, ray, h);
     HitInfo hit;
     reconstruct_hit(sc, ray.o, ray.d, h, true, hit);
     MatCtx mc = matctx_from_differentials(hit, ray, rd);

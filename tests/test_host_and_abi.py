@@ -210,3 +210,31 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["workload"].startswith("C2")
+
+
+def test_integration_patch_applies(tmp_path):
+    """integration/reference.patch is a real diff against the reference tree: it applies cleanly to copies of the files it
+    names (only where /root/reference exists: the GPU box does not have it), and the Rust crate only calls entry points and
+    constants that include/rtcuda.h declares"""
+    import re
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    patch = os.path.join(root, "integration", "reference.patch")
+    text = open(patch).read()
+    files = re.findall(r"^\+\+\+ b/(\S+)", text, flags=re.M)
+    assert len(files) == 6 and "crates/cli/src/main.rs" in files and "visual-testing/src/rttest/runner.py" in files
+    header = open(os.path.join(root, "include", "rtcuda.h")).read()
+    rust = open(os.path.join(root, "integration", "crates", "raytracing-cuda", "src", "lib.rs")).read()
+    for name in set(re.findall(r"ffi::(rtcuda_\w+|RTCUDA_\w+)", rust)):
+        base = re.sub(r"^rtcuda_(\w+?_kind|image_format|status)_(RTCUDA_\w+)$", r"\2", name)   # bindgen's name for a C enum constant
+        assert re.search(r"\b" + re.escape(base) + r"\b", header), f"{name} is not in rtcuda.h"
+    if not os.path.isdir("/root/reference"):
+        pytest.skip("reference tree absent")
+    for f in files:
+        dst = tmp_path / f
+        dst.parent.mkdir(parents=True, exist_ok=True)
+        shutil.copy(os.path.join("/root/reference", f), dst)
+        os.chmod(dst, 0o644)
+    r = subprocess.run(["patch", "-p1", "--dry-run", "-i", patch], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr

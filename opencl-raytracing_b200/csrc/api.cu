@@ -480,7 +480,11 @@ void build_bvh(rtcuda_scene* s, const std::vector<Instance>& instances, uint32_t
     counters.alloc(4);
     queue_a.alloc(n); queue_b.alloc(n);
     s->nodes.alloc(n);   // every wide node consumes at least one binary internal node
-    s->prims.alloc(n);
+    // primitive slots: 3 per leaf child of the wide tree (rt_scene.h Node8), at most 3 per primitive; unfilled slots keep the
+    // 0xff pattern (PRIM_HOLE)
+    const size_t prim_slots = RT_FIXED_SLOTS ? 3 * (size_t)n : (size_t)n;
+    REQUIRE(prim_slots < 0xffffffffull, "too many primitives");
+    s->prims.alloc(prim_slots);
     const size_t temp_bytes = sort_temp_bytes(n);
     sort_temp.alloc(temp_bytes);
 
@@ -495,7 +499,7 @@ void build_bvh(rtcuda_scene* s, const std::vector<Instance>& instances, uint32_t
     b.keys = keys.p; b.vals = vals.p; b.keys_sorted = keys_sorted.p; b.vals_sorted = vals_sorted.p;
     b.left = left.p; b.right = right.p; b.parent = parent.p; b.count = count.p;
     b.node_lo = node_lo.p; b.node_hi = node_hi.p; b.visit = visit.p;
-    b.nodes = s->nodes.p; b.prims = s->prims.p; b.counters = counters.p;
+    b.nodes = s->nodes.p; b.prims = s->prims.p; b.counters = counters.p; b.prim_capacity = (uint32_t)prim_slots;
 
     launch_prim_setup(st, b, s->lc);
     launch_morton(st, b, s->lc);
@@ -532,6 +536,7 @@ void build_bvh(rtcuda_scene* s, const std::vector<Instance>& instances, uint32_t
     }
 
     // collapse, one launch per wide level
+    CK(cudaMemsetAsync(s->prims.p, 0xff, prim_slots * sizeof(Prim), st));
     WorkItem root{0u, 0u};
     CK(cudaMemcpyAsync(queue_a.p, &root, sizeof root, cudaMemcpyHostToDevice, st));
     h_counters[0] = 0u; h_counters[1] = 1u; h_counters[2] = 0u; h_counters[3] = 0u;  // next-level size, wide nodes (root allocated), packed prims
@@ -561,7 +566,8 @@ void build_bvh(rtcuda_scene* s, const std::vector<Instance>& instances, uint32_t
     use_lbvh = true;
     s->stats.bvh_fallback_lbvh = 1;
   }
-    if (h_counters[2] != n) throw RtError{RTCUDA_ERR_CUDA, "BVH build lost primitives"};
+    if (h_counters[3] != n || h_counters[2] > prim_slots) throw RtError{RTCUDA_ERR_CUDA, "BVH build lost primitives"};
+    s->sc.prim_count = h_counters[2];   // primitive SLOTS (holes included): what shade records and bounds checks range over
     s->sc.node_count = h_counters[1];
     s->stats.bvh_node_count = h_counters[1];
     s->stats.bvh_prim_count = n;
@@ -780,7 +786,7 @@ void upload_scene(rtcuda_scene* s, const rtcuda_scene_desc* d, const GeoShare* s
     sc.prims = s->prims.p;
     sc.shade_recs = nullptr;
     if (n_prims) {
-        s->shade_recs.alloc(n_prims);
+        s->shade_recs.alloc(sc.prim_count);
         launch_shade_recs(st, sc, s->shade_recs.p, s->lc);
         sc.shade_recs = s->shade_recs.p;
     }

@@ -59,7 +59,8 @@ struct BuildCtx {
     Prim* prims;
     const WorkItem* queue_in;
     WorkItem* queue_out;
-    uint32_t* counters;         // [0] next-level size, [1] wide node count, [2] packed prim count
+    uint32_t* counters;         // [0] next-level size, [1] wide node count, [2] primitive slots handed out, [3] primitives placed
+    uint32_t prim_capacity;     // slots allocated behind `prims` (writes beyond are dropped; the driver checks [2])
     // PLOC state
     const uint32_t* cl_in;      // current clusters (binary node ids) in Morton order
     uint32_t* cl_out;
@@ -325,7 +326,21 @@ RT_HD void collapse_body(uint32_t item_idx, const BuildCtx& b) {
     int child_in[8];
     for (int s = 0; s < 8; s++) child_in[s] = -1;
     for (int c = 0; c < nc; c++) slot_of[c] = -1;
-    for (int round = 0; round < nc; round++) {
+#if RT_FIXED_SLOTS
+    // Leaf children take the lowest slots (their primitives live at prim_base + 3 * slot: a contiguous run of 3 * n_leaves
+    // primitive slots per node, see below); the octant order only matters for the children a ray descends into, and those
+    // share the remaining slots by the greedy rule. Nodes with only inner children (the upper tree) are unaffected.
+    int n_leaf_children = 0;
+    for (int c = 0; c < nc; c++)
+        if (ch[c] >= first_leaf || b.count[ch[c]] <= LEAF_MAX) {
+            slot_of[c] = n_leaf_children;
+            child_in[n_leaf_children++] = c;
+        }
+    const int n_greedy = nc - n_leaf_children;
+#else
+    const int n_greedy = nc;
+#endif
+    for (int round = 0; round < n_greedy; round++) {
         float best = -RT_INF;
         int bc = -1, bs = -1;
         for (int c = 0; c < nc; c++) {
@@ -369,11 +384,20 @@ RT_HD void collapse_body(uint32_t item_idx, const BuildCtx& b) {
         if (cnt <= LEAF_MAX) n_leaf_prims += cnt; else n_internal++;
     }
     const uint32_t child_base = n_internal ? atomic_add_u32(&b.counters[1], n_internal) : 0u;
+#if RT_FIXED_SLOTS
+    // 3 primitive slots per leaf child, at prim_base + 3 * slot (leaf children are slots 0 .. n_leaves-1): a hit on child s
+    // sets the fixed bits 3s..3s+2 of the ray's primitive mask and the node's `valid` word clears the slots a leaf does not
+    // fill — no per-child decoding in the traversal (rt_traverse.h). Unfilled slots stay holes in the primitive array.
+    const uint32_t prim_base = n_leaf_children ? atomic_add_u32(&b.counters[2], 3u * (uint32_t)n_leaf_children) : 0u;
+    if (n_leaf_prims) atomic_add_u32(&b.counters[3], n_leaf_prims);
+#else
     const uint32_t prim_base = n_leaf_prims ? atomic_add_u32(&b.counters[2], n_leaf_prims) : 0u;
+    if (n_leaf_prims) atomic_add_u32(&b.counters[3], n_leaf_prims);
+#endif
     const uint32_t q_base = n_internal ? atomic_add_u32(&b.counters[0], n_internal) : 0u;
 
     uint32_t meta[8], q[6][8];
-    uint32_t imask = 0, k_internal = 0, k_prim = 0;
+    uint32_t imask = 0, k_internal = 0, k_prim = 0, valid = 0;
     for (int s = 0; s < 8; s++) {
         meta[s] = 0;
         for (int a = 0; a < 6; a++) q[a][s] = 0;
@@ -394,13 +418,21 @@ RT_HD void collapse_body(uint32_t item_idx, const BuildCtx& b) {
             q[3 + a][s] = (uint32_t)qh;
         }
         if (cnt <= LEAF_MAX) {
+#if RT_FIXED_SLOTS
+            k_prim = 3u * (uint32_t)s;
+            valid |= ((1u << cnt) - 1u) << k_prim;
+#else
             meta[s] = (((1u << cnt) - 1u) << 5) | k_prim;
+#endif
             uint32_t walk[4];  // the <= LEAF_MAX leaves of this subtree, left to right
             int wsp = 0;
             walk[wsp++] = nd;
             while (wsp) {
                 const uint32_t x = walk[--wsp];
-                if (x >= first_leaf) b.prims[prim_base + k_prim++] = b.prims_unsorted[b.vals_sorted[x - first_leaf]];
+                if (x >= first_leaf) {
+                    if (prim_base + k_prim < b.prim_capacity) b.prims[prim_base + k_prim] = b.prims_unsorted[b.vals_sorted[x - first_leaf]];
+                    k_prim++;
+                }
                 else { walk[wsp++] = b.right[x]; walk[wsp++] = b.left[x]; }
             }
         } else {
@@ -417,7 +449,11 @@ RT_HD void collapse_body(uint32_t item_idx, const BuildCtx& b) {
     auto pack4 = [](const uint32_t* v) { return v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24); };
     Node8 nd8;
     nd8.n0 = make_float4(lo.x, lo.y, lo.z, u2f(ebits[0] | (ebits[1] << 8) | (ebits[2] << 16) | (imask << 24)));
+#if RT_FIXED_SLOTS
+    nd8.n1 = make_float4(u2f(child_base), u2f(prim_base), u2f(valid | (imask << 24)), u2f(0u));
+#else
     nd8.n1 = make_float4(u2f(child_base), u2f(prim_base), u2f(pack4(meta)), u2f(pack4(meta + 4)));
+#endif
     nd8.n2 = make_float4(u2f(pack4(q[0])), u2f(pack4(q[0] + 4)), u2f(pack4(q[1])), u2f(pack4(q[1] + 4)));
     nd8.n3 = make_float4(u2f(pack4(q[2])), u2f(pack4(q[2] + 4)), u2f(pack4(q[3])), u2f(pack4(q[3] + 4)));
     nd8.n4 = make_float4(u2f(pack4(q[4])), u2f(pack4(q[4] + 4)), u2f(pack4(q[5])), u2f(pack4(q[5] + 4)));

@@ -10,6 +10,10 @@
 #pragma once
 #include "rt_common.h"
 
+#ifndef RT_FIXED_SLOTS
+#define RT_FIXED_SLOTS 1   // 0: the dense primitive packing + per-child meta bytes of round 1 (A/B switch)
+#endif
+
 namespace rt {
 
 // 48-byte traversal primitive. Triangle: world-space vertices, ids in the w lanes.
@@ -91,12 +95,16 @@ struct ShadeRec {
     float4 uv2_mat;    // uv2.xy | material | area light
 };
 enum { REC_FLAT = 1u, REC_UV = 2u, REC_SPHERE = 4u };
+constexpr uint32_t PRIM_HOLE = 0xffffffffu;   // Prim::c.w of an unfilled primitive slot (the array is memset to 0xff before the build)
 
 // 80-byte compressed 8-wide node (DESIGN.md "BVH8 node"): five 128-bit loads.
 //   n0 = origin.xyz | ex | ey<<8 | ez<<16 | imask<<24
-//   n1 = child_base | prim_base | meta[0..3] | meta[4..7]
+//   n1 = child_base | prim_base | valid | -
 //   n2 = qlo_x[0..7] qlo_y[0..7]   n3 = qlo_z[0..7] qhi_x[0..7]   n4 = qhi_y[0..7] qhi_z[0..7]
-// meta[i]: 0 = empty; internal child: (1<<5) | (24+i); leaf child: (unary count: 1,3,7)<<5 | prim offset.
+// valid: bit 24+s = child s is an inner node (the imask again); bits 3s..3s+2 = unary primitive count (1, 3, 7) of leaf child s,
+// whose primitives are prims[prim_base + 3s + k]. Leaf children occupy the lowest slots, so a node owns 3 * n_leaves consecutive
+// primitive slots; slots a leaf does not fill are holes (PRIM_HOLE) that no ray ever reads.
+// (RT_FIXED_SLOTS=0, the round-1 layout: n1.zw = 8 meta bytes, 0 = empty; inner: (1<<5) | (24+i); leaf: unary count << 5 | prim offset.)
 struct Node8 { float4 n0, n1, n2, n3, n4; };
 
 struct SceneD {
@@ -158,9 +166,14 @@ RT_HD V2 load2(const float* p, uint32_t i) { return mk2(ldg(p + 2 * (size_t)i), 
 RT_HD void shade_rec_body(uint32_t i, const SceneD& sc, ShadeRec* out) {
     const Prim& pr = sc.prims[i];
     const uint32_t geom = f2u(pr.a.w), prim_id = f2u(pr.b.w), kind = f2u(pr.c.w);
-    const Instance& inst = sc.instances[geom];
+    const Instance& inst = sc.instances[kind == 0xffffffffu ? 0u : geom];
     ShadeRec r;
     uint32_t flags = 0;
+    if (kind == PRIM_HOLE) {   // unfilled slot: never referenced by a hit
+        r.n0_geom = r.n1_prim = r.n2_flags = r.uv01 = r.uv2_mat = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        out[i] = r;
+        return;
+    }
     V3 n0 = mk3(0.0f), n1 = mk3(0.0f), n2 = mk3(0.0f);
     V2 uv0 = mk2(0, 0), uv1 = mk2(1, 0), uv2 = mk2(0, 1);
     if (kind != 0) flags = REC_SPHERE;

@@ -172,6 +172,20 @@ struct Traversal {
     RT_HD bool has_nodes() const { return (ngroup.y & 0xff000000u) != 0u; }
     RT_HD bool can_stash() const { return sp < TRAVERSE_STACK - 2; }
 
+#if RT_FIXED_SLOTS
+    // child slot S (plane bytes I = S & 3 of the half's words): slab test; a hit sets the child's FIXED bits of the hit mask —
+    // its inner-node bit 24 + S and its three primitive bits 3S..3S+2 — with one immediate; node_step then clears what the
+    // node's `valid` word does not back (empty slots, leaves with fewer than three primitives, the wrong kind of child).
+    template <int S>
+    RT_HD void child_fixed(uint32_t nx_w, uint32_t fx_w, uint32_t ny_w, uint32_t fy_w, uint32_t nz_w, uint32_t fz_w,
+                           V3 an, V3 cn, V3 af, V3 cf, float tf_cap, uint32_t& hitmask) const {
+        constexpr int I = S & 3;
+        const float tn = fmaxf(fmaxf(qfloat<I>(nx_w) * an.x + cn.x, qfloat<I>(ny_w) * an.y + cn.y), fmaxf(qfloat<I>(nz_w) * an.z + cn.z, t_min));
+        const float tf = fminf(fminf(qfloat<I>(fx_w) * af.x + cf.x, qfloat<I>(fy_w) * af.y + cf.y), fminf(qfloat<I>(fz_w) * af.z + cf.z, tf_cap));
+        if (tn <= tf) hitmask |= (7u << (3 * S)) | (1u << (24 + S));
+    }
+#endif
+
     // child I of a 4-child half: slab test against the near / far plane words of the three axes
     template <int I>
     RT_HD void child(uint32_t bits4, uint32_t index4, uint32_t nx_w, uint32_t fx_w, uint32_t ny_w, uint32_t fy_w, uint32_t nz_w, uint32_t fz_w,
@@ -221,6 +235,31 @@ struct Traversal {
         const uint32_t nearx0 = nx ? hix0 : lox0, nearx1 = nx ? hix1 : lox1, farx0 = nx ? lox0 : hix0, farx1 = nx ? lox1 : hix1;
         const uint32_t neary0 = ny ? hiy0 : loy0, neary1 = ny ? hiy1 : loy1, fary0 = ny ? loy0 : hiy0, fary1 = ny ? loy1 : hiy1;
         const uint32_t nearz0 = nz ? hiz0 : loz0, nearz1 = nz ? hiz1 : loz1, farz0 = nz ? loz0 : hiz0, farz1 = nz ? loz1 : hiz1;
+#if RT_FIXED_SLOTS
+        uint32_t hitmask = 0;
+        child_fixed<0>(nearx0, farx0, neary0, fary0, nearz0, farz0, a15, cn, af, cf, tf_cap, hitmask);
+        child_fixed<1>(nearx0, farx0, neary0, fary0, nearz0, farz0, a15, cn, af, cf, tf_cap, hitmask);
+        child_fixed<2>(nearx0, farx0, neary0, fary0, nearz0, farz0, a15, cn, af, cf, tf_cap, hitmask);
+        child_fixed<3>(nearx0, farx0, neary0, fary0, nearz0, farz0, a15, cn, af, cf, tf_cap, hitmask);
+        child_fixed<4>(nearx1, farx1, neary1, fary1, nearz1, farz1, a15, cn, af, cf, tf_cap, hitmask);
+        child_fixed<5>(nearx1, farx1, neary1, fary1, nearz1, farz1, a15, cn, af, cf, tf_cap, hitmask);
+        child_fixed<6>(nearx1, farx1, neary1, fary1, nearz1, farz1, a15, cn, af, cf, tf_cap, hitmask);
+        child_fixed<7>(nearx1, farx1, neary1, fary1, nearz1, farz1, a15, cn, af, cf, tf_cap, hitmask);
+        hitmask &= meta_lo;   // the node's `valid` word
+        if (!UNORDERED) {
+            // closest-hit walks pop inner children front to back: move the bit of slot s to position s ^ octinv (three
+            // conditional swaps of the top byte: neighbours, pairs, nibbles)
+            uint32_t top = hitmask >> 24;
+            const uint32_t t1 = ((top & 0x55u) << 1) | ((top >> 1) & 0x55u);
+            top = (octinv & 1u) ? t1 : top;
+            const uint32_t t2 = ((top & 0x33u) << 2) | ((top >> 2) & 0x33u);
+            top = (octinv & 2u) ? t2 : top;
+            const uint32_t t4 = ((top & 0x0fu) << 4) | (top >> 4);
+            top = (octinv & 4u) ? t4 : top;
+            hitmask = (hitmask & 0x00ffffffu) | (top << 24);
+        }
+        (void)meta_hi;
+#else
         // four children at a time: hit-mask bit position (24 + slot ^ octinv for inner children, the primitive offset for
         // leaves) and the bits to set there (1 for inner, unary primitive count for leaves; 0 for an empty child)
         const uint32_t octinv4 = octinv * 0x01010101u;
@@ -243,6 +282,7 @@ struct Traversal {
             child<2>(bits4, index4, nearx1, farx1, neary1, fary1, nearz1, farz1, a15, cn, af, cf, tf_cap, hitmask);
             child<3>(bits4, index4, nearx1, farx1, neary1, fary1, nearz1, farz1, a15, cn, af, cf, tf_cap, hitmask);
         }
+#endif
         ngroup.x = f2u(n1.x);
         ngroup.y = (hitmask & 0xff000000u) | imask;
         tgroup.x = f2u(n1.y);

@@ -155,7 +155,10 @@ void build(HostScene& hs, const rtcuda_scene_desc* d) {
     for (uint32_t t = 0; t < d->texture_count; t++)
         if (d->textures[t].kind == RTCUDA_TEXTURE_IMAGE || d->textures[t].kind == RTCUDA_TEXTURE_CHECKER) sc.tex_uses_derivs = 1;
     sc.prim_count = n_prims; sc.node_count = 0;
-    hs.nodes.resize(std::max(1u, n_prims)); hs.prims.resize(std::max(1u, n_prims));
+    const uint32_t prim_slots = RT_FIXED_SLOTS ? 3u * n_prims : n_prims;   // api.cu build_bvh
+    Prim hole;
+    std::memset(&hole, 0xff, sizeof hole);
+    hs.nodes.resize(std::max(1u, n_prims)); hs.prims.assign(std::max(1u, prim_slots), hole);
     sc.nodes = hs.nodes.data(); sc.prims = hs.prims.data();
     if (!n_prims) return;
 
@@ -174,7 +177,7 @@ void build(HostScene& hs, const rtcuda_scene_desc* d) {
     b.keys = keys.data(); b.vals = vals.data(); b.keys_sorted = keys_sorted.data(); b.vals_sorted = vals_sorted.data();
     b.left = left.data(); b.right = right.data(); b.parent = parent.data(); b.count = count.data();
     b.node_lo = node_lo.data(); b.node_hi = node_hi.data(); b.visit = visit.data();
-    b.nodes = hs.nodes.data(); b.prims = hs.prims.data(); b.counters = counters;
+    b.nodes = hs.nodes.data(); b.prims = hs.prims.data(); b.counters = counters; b.prim_capacity = prim_slots;
     for (uint32_t i = 0; i < n; i++) prim_setup_body(i, b);
     for (uint32_t i = 0; i < n; i++) morton_body(i, b);
     std::vector<uint32_t> order(n);
@@ -219,7 +222,7 @@ void build(HostScene& hs, const rtcuda_scene_desc* d) {
         hs.n_levels++;
     }
     sc.node_count = counters[1];
-    if (std::getenv("HOSTSIM_NODESTATS")) {
+    if (std::getenv("HOSTSIM_NODESTATS") && !RT_FIXED_SLOTS) {
         uint32_t hist[9] = {0}, inner = 0, leafc = 0, prims = 0, hi_empty = 0;
         for (uint32_t i = 0; i < counters[1]; i++) {
             const Node8& nd = hs.nodes[i];
@@ -243,10 +246,11 @@ void build(HostScene& hs, const rtcuda_scene_desc* d) {
     sc.scene_center[0] = c.x; sc.scene_center[1] = c.y; sc.scene_center[2] = c.z;
     sc.scene_radius = n == 1 ? INFINITY : length(mx - c);
     set_scene_bounds(sc, mn, mx, true);
-    if (counters[2] != n) sc.node_count = 0xdeadbeef;  // lost primitives: surfaced through the stats
+    sc.prim_count = counters[2];   // primitive slots (holes included with RT_FIXED_SLOTS)
+    if (counters[3] != n || counters[2] > prim_slots) sc.node_count = 0xdeadbeef;  // lost primitives: surfaced through the stats
     else if (!std::getenv("HOSTSIM_NO_SHADE_RECS")) {
-        hs.shade_recs.resize(n);
-        for (uint32_t i = 0; i < n; i++) shade_rec_body(i, sc, hs.shade_recs.data());
+        hs.shade_recs.resize(sc.prim_count);
+        for (uint32_t i = 0; i < sc.prim_count; i++) shade_rec_body(i, sc, hs.shade_recs.data());
         sc.shade_recs = hs.shade_recs.data();
     }
 }

@@ -360,7 +360,8 @@ void validate_desc(const rtcuda_scene_desc* d) {
         const rtcuda_texture& t = d->textures[i];
         REQUIRE(t.kind <= RTCUDA_TEXTURE_MIX, "unknown texture kind");
         if (t.kind == RTCUDA_TEXTURE_IMAGE) REQUIRE(t.image < d->image_count && t.filter <= 2 && t.wrap <= 2, "image texture out of range");
-        // Scale / Mix may only refer to earlier textures: bounded nesting, no cycles
+        // Scale / Mix operands: any texture of the scene; cycles and nesting beyond what the device evaluator unrolls
+        // (TEXTURE_NEST) are refused by texture_depth at upload
         if (t.kind == RTCUDA_TEXTURE_SCALE) REQUIRE(tex_ok(t.a) && tex_ok(t.b), "scale texture operand out of range");
         if (t.kind == RTCUDA_TEXTURE_MIX) REQUIRE(tex_ok(t.a) && tex_ok(t.b) && tex_ok(t.c), "mix texture operand out of range");
     }
@@ -368,6 +369,7 @@ void validate_desc(const rtcuda_scene_desc* d) {
         const rtcuda_image& im = d->images[i];
         REQUIRE(im.channels >= 1 && im.channels <= 4 && im.format <= RTCUDA_IMAGE_F32 && im.width && im.height, "bad image header");
         REQUIRE(im.byte_offset + (uint64_t)im.width * im.height * im.channels * bytes_per_sample(im.format) <= d->image_byte_count, "image bytes out of range");
+        REQUIRE(im.byte_offset % bytes_per_sample(im.format) == 0, "image byte_offset must be aligned to the sample size (u16: 2, f32: 4)");
     }
     REQUIRE(d->environment_light_texture == RTCUDA_NONE || tex_ok(d->environment_light_texture), "environment texture out of range");
 }
@@ -594,6 +596,8 @@ void upload_scene(rtcuda_scene* s, const rtcuda_scene_desc* d, const GeoShare* s
             if (t != RTCUDA_NONE && t < d->texture_count && texture_depth(d, t, 0) > (uint32_t)TEXTURE_NEST)
                 throw RtError{RTCUDA_ERR_UNSUPPORTED, "texture nesting deeper than the device evaluator supports"};
     }
+    if (d->environment_light_texture != RTCUDA_NONE && texture_depth(d, d->environment_light_texture, 0) > (uint32_t)TEXTURE_NEST)
+        throw RtError{RTCUDA_ERR_UNSUPPORTED, "environment texture nesting deeper than the device evaluator supports"};
     cudaEvent_t e0, e1, e2;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&e2));
     CK(cudaEventRecord(e0, st));
@@ -1553,12 +1557,18 @@ RTCUDA_API rtcuda_status rtcuda_init(const rtcuda_backend_settings* settings, rt
         }
         // NVLink peer access in both directions between every pair (geometry slices are forwarded all-to-all, owned pixels go to
         // GPU 0), for plain allocations and for the stream-ordered pools the scene arrays come from
+        static std::mutex peer_mu;
+        static uint64_t peer_done[64] = {0};   // per process: pairs already set up (the calls below cost milliseconds each)
+        std::lock_guard<std::mutex> peer_lock(peer_mu);
         for (uint32_t i = 0; i < n; i++) {
             CK(cudaSetDevice(settings->device_ids[i]));
             cudaMemPool_t pool;
             CK(cudaDeviceGetDefaultMemPool(&pool, settings->device_ids[i]));
             for (uint32_t j = 0; j < n; j++) {
                 if (settings->device_ids[i] == settings->device_ids[j]) continue;
+                const int di = settings->device_ids[i] & 63, dj = settings->device_ids[j] & 63;
+                if (peer_done[di] & (1ull << dj)) continue;
+                peer_done[di] |= 1ull << dj;
                 int can = 0;
                 CK(cudaDeviceCanAccessPeer(&can, settings->device_ids[i], settings->device_ids[j]));
                 if (!can) continue;   // copies between the two then go through the host (still correct)

@@ -371,6 +371,8 @@ class SceneDescHolder:
                 mt = np.ascontiguousarray(m.tris, dtype=np.uint32).reshape(-1, 3)
                 mn = np.ascontiguousarray(m.normals, dtype=f32).reshape(-1, 3) if m.normals is not None and len(m.normals) else None
                 mu = np.ascontiguousarray(m.uvs, dtype=f32).reshape(-1, 2) if m.uvs is not None and len(m.uvs) else None
+                if (mn is not None and len(mn) != len(mv)) or (mu is not None and len(mu) != len(mv)):   # the library copies vertex_count entries of each
+                    raise ValueError(f"shape {i}: normals / uvs must have one entry per vertex ({len(mv)})")
                 nv += len(mv)
                 nt += len(mt)
                 if mn is not None:
@@ -746,7 +748,10 @@ def scene_from_gltf_file(path: str, raster_height: int = HEIGHT, raster_width: O
 # triangles dropped.
 # --------------------------------------------------------------------------------------------
 def mesh_from_ply_bytes(data: bytes, swap_handedness: bool = False) -> Mesh:
-    end = data.index(b"end_header\n") + len(b"end_header\n")
+    marker = data.find(b"end_header")
+    if marker < 0:
+        raise ValueError("not a PLY file: no end_header")
+    end = data.index(b"\n", marker) + 1                  # tolerant of CRLF line ends ("end_header\r\n")
     header = data[:end].decode("ascii").splitlines()
     fmt = "ascii"
     elements = []
@@ -800,19 +805,33 @@ def mesh_from_ply_bytes(data: bytes, swap_handedness: bool = False) -> Mesh:
             dt = np.dtype([(p[1], ty[p[0]]) for p in el["props"]])
             verts = np.frombuffer(data, dtype=dt, count=el["count"], offset=off)
             off += dt.itemsize * el["count"]
-        elif el["name"] == "face":
-            p = el["props"][0]
-            cdt, idt = np.dtype(ty[p[1]]), np.dtype(ty[p[2]])
-            faces = []
+        else:   # face, or any other element: walk its properties so that offsets stay right; only the first list of `face` is kept
+            is_face = el["name"] == "face"
+            if is_face:
+                faces = []
+            fixed = all(p[0] != "list" for p in el["props"])
+            if fixed and not is_face:
+                off += sum(np.dtype(ty[p[0]]).itemsize for p in el["props"]) * el["count"]
+                continue
             for _ in range(el["count"]):
-                n = int(np.frombuffer(data, dtype=cdt, count=1, offset=off)[0])
-                off += cdt.itemsize
-                faces.append(np.frombuffer(data, dtype=idt, count=n, offset=off).astype(np.uint32))
-                off += idt.itemsize * n
+                first_list = True
+                for p in el["props"]:
+                    if p[0] == "list":
+                        cdt, idt = np.dtype(ty[p[1]]), np.dtype(ty[p[2]])
+                        n = int(np.frombuffer(data, dtype=cdt, count=1, offset=off)[0])
+                        off += cdt.itemsize
+                        if is_face and first_list:
+                            faces.append(np.frombuffer(data, dtype=idt, count=n, offset=off).astype(np.uint32))
+                            first_list = False
+                        off += idt.itemsize * n
+                    else:
+                        off += np.dtype(ty[p[0]]).itemsize
     names = verts.dtype.names
     v = np.stack([verts["x"], verts["y"], verts["z"]], axis=1).astype(f32)
     normals = np.stack([verts["nx"], verts["ny"], verts["nz"]], axis=1).astype(f32) if "nx" in names else None
-    uvs = np.stack([verts["u"], verts["v"]], axis=1).astype(f32) if "u" in names else None
+    un = "u" if "u" in names else ("s" if "s" in names else None)      # mesh.rs:37-38 accepts (s, t) as well as (u, v)
+    vn = "v" if "v" in names else ("t" if "t" in names else None)
+    uvs = np.stack([verts[un], verts[vn]], axis=1).astype(f32) if un and vn else None
     tris = []
     for idx in faces:
         for i in range(1, len(idx) - 1):

@@ -238,3 +238,22 @@ def test_integration_patch_applies(tmp_path):
         os.chmod(dst, 0o644)
     r = subprocess.run(["patch", "-p1", "--dry-run", "-i", patch], cwd=tmp_path, capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_ply_importer_variants(rc):
+    """Mesh::from_ply_reader conventions (mesh.rs:25-170): (s, t) texture coordinates as well as (u, v), CRLF headers, extra
+    elements and trailing face properties in binary files"""
+    import struct
+    hdr = ("ply\r\nformat binary_little_endian 1.0\r\nelement vertex 4\r\nproperty float x\r\nproperty float y\r\nproperty float z\r\n"
+           "property float s\r\nproperty float t\r\nelement edge 2\r\nproperty int a\r\nproperty int b\r\n"
+           "element face 2\r\nproperty list uchar int vertex_indices\r\nproperty uchar flags\r\nend_header\r\n").encode()
+    verts = [(0, 0, 0, 0, 0), (1, 0, 0, 1, 0), (1, 1, 0, 1, 1), (0, 1, 0, 0, 1)]
+    body = b"".join(struct.pack("<5f", *v) for v in verts) + struct.pack("<4i", 0, 1, 1, 2)
+    body += struct.pack("<B3iB", 3, 0, 1, 2, 9) + struct.pack("<B3iB", 3, 0, 2, 3, 9)
+    m = rc.scene.mesh_from_ply_bytes(hdr + body)
+    assert m.vertices.shape == (4, 3) and m.tris.tolist() == [[0, 1, 2], [0, 2, 3]]
+    assert m.uvs is not None and m.uvs.tolist() == [[0, 0], [1, 0], [1, 1], [0, 1]]
+    bad = rc.test_scenes.cube_scene()
+    bad.shapes[0].shape.normals = bad.shapes[0].shape.normals[:-1]
+    with pytest.raises(ValueError, match="one entry per vertex"):
+        bad.to_desc(own_arrays=True)

@@ -587,7 +587,6 @@ struct FirstHit { bool hit; V2 uv; V3 normal, albedo; bool has_mip; float mip; u
 // uv IS the barycentrics. The first-hit AOV pass (one ray per pixel) therefore repeats the test of the WINNING triangle the
 // reference's way and reports those (t, u, v): same operations in the same order, un-fused in this translation unit.
 RT_HD void refine_triangle_hit_in_object_space(const SceneD& sc, const Ray& ray, Hit& h) {
-    if (sc.watertight) return;
     const Prim* pr = sc.prims + h.prim;
     if (f2u(ldg(&pr->c).w) != 0u) return;   // spheres are intersected in object space already
     const uint32_t geom = f2u(ldg(&pr->a).w), prim_id = f2u(ldg(&pr->b).w);
@@ -597,7 +596,9 @@ RT_HD void refine_triangle_hit_in_object_space(const SceneD& sc, const Ray& ray,
              p2 = load3(sc.vertices, inst.vertex_offset + ldg(t3 + 2));
     const V3 oo = apply_point(inst.w2o, ray.o), od = apply_vector(inst.w2o, ray.d);
     float t, u, v;
-    if (triangle_t(p0, p1, p2, oo, od, sc.camera.near_clip, sc.camera.far_clip, t, u, v)) { h.t = t; h.u = u; h.v = v; }
+    const bool ok = sc.watertight ? triangle_watertight(p0, p1, p2, oo, od, sc.camera.near_clip, sc.camera.far_clip, t, u, v)
+                                  : triangle_t(p0, p1, p2, oo, od, sc.camera.near_clip, sc.camera.far_clip, t, u, v);
+    if (ok) { h.t = t; h.u = u; h.v = v; }
 }
 
 template <bool STATS>

@@ -247,6 +247,7 @@ void build(HostScene& hs, const rtcuda_scene_desc* d) {
     sc.scene_radius = n == 1 ? INFINITY : length(mx - c);
     set_scene_bounds(sc, mn, mx, true);
     sc.prim_count = counters[2];   // primitive slots (holes included with RT_FIXED_SLOTS)
+    if (std::getenv("HOSTSIM_NODESTATS")) std::fprintf(stderr, "wide nodes %u, primitives %u in %u slots (%.3f slots per primitive)\n", counters[1], counters[3], counters[2], (double)counters[2] / counters[3]);
     if (counters[3] != n || counters[2] > prim_slots) sc.node_count = 0xdeadbeef;  // lost primitives: surfaced through the stats
     else if (!std::getenv("HOSTSIM_NO_SHADE_RECS")) {
         hs.shade_recs.resize(sc.prim_count);

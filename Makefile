@@ -14,9 +14,10 @@ oracle_ref:
 
 # wavefront kernels: FMA contraction on, 2-ulp division / sqrt (the beauty plane is gated statistically; the
 # strict-tolerance AOV kernels live in kernels_aov.cu and keep IEEE division, sqrt and unfused multiply-add)
+FASTDIV ?= -prec-div=false -prec-sqrt=false
 build/kernels.o: $(CSRC)/kernels.cu $(HDRS)
 	@mkdir -p build
-	$(NVCC) $(NVCCFLAGS) -prec-div=false -prec-sqrt=false -c $< -o $@
+	$(NVCC) $(NVCCFLAGS) $(FASTDIV) -c $< -o $@
 
 build/kernels_aov.o: $(CSRC)/kernels_aov.cu $(HDRS)
 	@mkdir -p build

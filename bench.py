@@ -28,6 +28,10 @@ WORKLOADS = {
     # BASELINE config C5: 16,777,216-triangle displaced UV-sphere (4096 x 2048 quads, seed 42) inside the cb.glb box, 4K
     "C5": ("cb", 3840, 2160, 256, 8, 1),
     "C5s": ("cb", 1920, 1080, 32, 8, 1),     # same mesh, 1080p / 32 spp (quick check of the HBM-bound regime)
+    # the general shade kernel (k_shade<Surface>: every non-Diffuse material): the reference's builtin Cornell box with a
+    # rough-conductor / rough-dielectric sphere (test_scenes/mod.rs), 1000x1000, 64 spp, point light
+    "CM": ("builtin:rough_metal", 1000, 1000, 64, 8, 4),
+    "CD": ("builtin:rough_dielectric", 1000, 1000, 64, 8, 4),
 }
 SYNTHETIC = {"C5": (4096, 2048), "C5s": (4096, 2048)}
 # Tile edge of the multi-GPU deal: BASELINE names 64x64 tiles for C5; the other frames concentrate their cost in part of the
@@ -42,6 +46,15 @@ DATA_NOTE = "scene fixture (reference asset; C5: procedural mesh generated in-pr
 def load_workload(name, synthetic_tris=0):
     import raytracing_cuda as rc
     fixture, w, h, spp, depth, ls = WORKLOADS[name]
+    if fixture.startswith("builtin:"):
+        import math
+        import numpy as np
+        t = [t for t in rc.test_scenes.all_test_scenes() if t.name == fixture.split(":")[1]][0]
+        sc = t.scene_func()
+        sc.camera = rc.Camera.lookat_camera_perspective((0.0, 1.0 + 3.4, 0.4), (0, 0, 0.75), (0, 0, 1), False,
+                                                        float(np.float32(37.8) * np.float32(math.pi / 180)), w, h)   # cornell_box()'s camera
+        st = rc.RaytracerSettings(samples_per_pixel=spp, max_ray_depth=depth, light_sample_count=ls)
+        return sc, st
     sc = rc.Scene.load_npz(os.path.join(ROOT, "tests", "golden", "scenes", fixture + ".npz"))
     if name in SYNTHETIC:
         sc = rc.test_scenes.synthetic_mesh_scene(sc, *SYNTHETIC[name])
@@ -155,7 +168,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     fixture, W, H, spp, depth, ls = WORKLOADS[args.workload]
-    what = f"{fixture}.glb" + (f" + synthetic displaced UV-sphere {SYNTHETIC[args.workload][0]}x{SYNTHETIC[args.workload][1]} quads (seed 42)"
+    what = (f"{fixture}.glb" if not fixture.startswith("builtin:") else f"builtin scene '{fixture.split(':')[1]}'") + (f" + synthetic displaced UV-sphere {SYNTHETIC[args.workload][0]}x{SYNTHETIC[args.workload][1]} quads (seed 42)"
                                if args.workload in SYNTHETIC else "")
     tile = args.tile_size or TILE_SIZE.get(args.workload, 16)
     part = (f"{tile}x{tile} tiles round-robin" if args.partition == "tiles" else "sample ranges of every pixel")

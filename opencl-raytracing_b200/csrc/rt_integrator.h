@@ -127,7 +127,7 @@ struct HitInfo {  // accel.rs:13-25 (+ ids for the debug planes)
 RT_HD void reconstruct_hit(const SceneD& sc, V3 o, V3 d, const Hit& h, bool need_derivs, HitInfo& out) {
     if (!need_derivs && sc.shade_recs) {   // the gathered record (rt_scene.h ShadeRec): same values, two load levels instead of five
         const ShadeRec* r = sc.shade_recs + h.prim;
-        const float4 a = ldg(&r->n0_geom), b = ldg(&r->n1_prim), c = ldg(&r->n2_flags), e = ldg(&r->uv2_mat);
+        const float4 a = ldg(&r->n0_geom), b = ldg(&r->n1_prim), c = ldg(&r->n2_flags);
         const uint32_t flags = f2u(c.w);
         if (!(flags & REC_SPHERE)) {
             const uint32_t geom = f2u(a.w);
@@ -135,13 +135,13 @@ RT_HD void reconstruct_hit(const SceneD& sc, V3 o, V3 d, const Hit& h, bool need
             out.t = h.t;
             out.geom_id = geom;
             out.prim_id = f2u(b.w);
-            out.material = f2u(e.z);
-            out.light = f2u(e.w);
+            out.material = inst.material;     // (the record's copies are the instance's values: one scattered load less for
+            out.light = inst.area_light;      //  meshes without uvs, whose fourth and fifth record words are never read)
             const float u = h.u, v = h.v, w = 1.0f - u - v;
             const V3 n_obj = (flags & REC_FLAT) ? xyz(a) : unit(w * xyz(a) + u * xyz(b) + v * xyz(c));
             V2 uv0 = mk2(0, 0), uv1 = mk2(1, 0), uv2 = mk2(0, 1);
             if (flags & REC_UV) {
-                const float4 q = ldg(&r->uv01);
+                const float4 q = ldg(&r->uv01), e = ldg(&r->uv2_mat);
                 uv0 = mk2(q.x, q.y); uv1 = mk2(q.z, q.w); uv2 = mk2(e.x, e.y);
             }
             out.uv = w * uv0 + u * uv1 + v * uv2;

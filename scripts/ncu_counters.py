@@ -27,8 +27,12 @@ UNIT_SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "nsecond": 
 def main():
     workload, rep = sys.argv[1], sys.argv[2]
     out_path = sys.argv[3] if len(sys.argv) > 3 else os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "ncu_counters.json")
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    # either an .ncu-rep, or the text of `ncu -i <rep> --page raw --csv` made on the GPU box (reports of many launches exceed what
+    # a GPU session may bring back)
+    raw = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
+    while rows and "Kernel Name" not in rows[0]:
+        rows.pop(0)
     hdr, units = rows[0], rows[1]
     idx = {h: i for i, h in enumerate(hdr)}
 

@@ -183,6 +183,13 @@ __global__ void __launch_bounds__(BLOCK, std::is_same<Surf, DiffuseSurface>::val
 #endif
     const uint32_t n = *w.n_in;
     const unsigned lane = threadIdx.x & 31u;
+#if RT_NEE_SMEM > 0
+    // staging columns of the next-event entries (rt_integrator.h StagePtr): NEE_SMEM entries x 3 fields per thread, 48 KB per block
+    __shared__ float4 s_stage[3 * NEE_SMEM * BLOCK];
+    const StagePtr stage_col{s_stage + threadIdx.x, (uint32_t)BLOCK, NEE_SMEM};
+#else
+    const StagePtr stage_col{nullptr, 0u, 0u};
+#endif
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&w.stats[STAT_SHADED], (unsigned long long)n);
     for (uint32_t base = blockIdx.x * BLOCK; base < n; base += gridDim.x * BLOCK) {
         const uint32_t q = base + threadIdx.x;
@@ -237,7 +244,7 @@ __global__ void __launch_bounds__(BLOCK, std::is_same<Surf, DiffuseSurface>::val
             vpos = (uint32_t)b1 + (uint32_t)__popc(mv & lt);
 #endif
             first = (uint32_t)(b1 >> 32) + (incl - k);
-        });
+        }, stage_col);
     }
 }
 

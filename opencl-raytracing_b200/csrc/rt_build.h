@@ -400,6 +400,7 @@ RT_HD void collapse_body(uint32_t item_idx, const BuildCtx& b) {
     uint32_t imask = 0, k_internal = 0, k_prim = 0, valid = 0;
     for (int s = 0; s < 8; s++) {
         meta[s] = 0;
+        (void)meta[s];
         for (int a = 0; a < 6; a++) q[a][s] = 0;
         int c = child_in[s];
         if (c < 0) continue;

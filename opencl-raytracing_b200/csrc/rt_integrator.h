@@ -452,11 +452,21 @@ RT_HD bool shade_begin(uint32_t q, const SceneD& sc, const RenderParams& rp, con
 #define RT_NEE_STAGE 8
 #endif
 constexpr uint32_t NEE_STAGE = RT_NEE_STAGE;
-struct NeeStage { float4 o[NEE_STAGE], d[NEE_STAGE], c[NEE_STAGE]; };
+struct NeeStage { float4 e[3 * NEE_STAGE]; };   // entry k: origin | t_max, direction, contribution at e[3k .. 3k+2]
+// Where nee_pass<1> parks the entries: field f of entry k lives at p[(3k + f) * stride]. The kernels hand every thread a
+// column of a SHARED-memory array (stride = block size, up to NEE_SMEM entries: the default 4 light samples of one area
+// light); thread-local memory (stride 1) serves larger counts and the CPU harness. Staged entries in thread-local memory
+// were 40 % of k_shade's local-memory sectors, and local memory was most of what the kernel wrote to DRAM (ncu, round 2:
+// 10.1 GB written against 6.5 GB of queue / state stores in the depth-0 launch of a 34 M-vertex batch).
+#ifndef RT_NEE_SMEM
+#define RT_NEE_SMEM 4
+#endif
+constexpr uint32_t NEE_SMEM = RT_NEE_SMEM;
+struct StagePtr { float4* p; uint32_t stride, capacity; };
 
 template <int MODE, typename Surf>
 RT_HD uint32_t nee_pass(const SceneD& sc, const RenderParams& rp, const Wave& w, const ShadeState<Surf>& S, Sampler& s, uint32_t first, uint32_t limit,
-                        NeeStage* stage) {
+                        StagePtr stage) {
     uint32_t k = 0;
     for (uint32_t li = 0; li < sc.light_count; li++) {
         const LightD& light = sc.lights[li];
@@ -479,7 +489,7 @@ RT_HD uint32_t nee_pass(const SceneD& sc, const RenderParams& rp, const Wave& w,
                     const bool skip_test = !(finite_f(ls.origin.x) && finite_f(ls.origin.y) && finite_f(ls.origin.z));
                     const float4 eo = make_float4(ls.origin.x, ls.origin.y, ls.origin.z, skip_test ? -1.0f : ls.distance - 0.001f);
                     const float4 ed = make_float4(ls.dir.x, ls.dir.y, ls.dir.z, 0.0f), ec = make_float4(c.x, c.y, c.z, 0.0f);
-                    if (MODE == 1) { stage->o[k] = eo; stage->d[k] = ed; stage->c[k] = ec; }
+                    if (MODE == 1) { float4* e = stage.p + (size_t)(3u * k) * stage.stride; e[0] = eo; e[stage.stride] = ed; e[2u * stage.stride] = ec; }
                     else { const size_t e = (size_t)first + k; RT_CHECK(e < (size_t)w.capacity * (w.shadow_k ? w.shadow_k : 1u)); w.sray_o[e] = eo; w.sray_d[e] = ed; w.scontrib[e] = ec; }
                 }
                 k++;
@@ -498,22 +508,24 @@ RT_HD uint32_t nee_pass(const SceneD& sc, const RenderParams& rp, const Wave& w,
 
 // alloc(continue_path, has_nee_vertex, n_shadow_rays, final_ray_skipped, &ray_pos, &vertex_pos, &first_shadow_ray)
 template <typename Surf, typename Alloc>
-RT_HD void shade_vertex(bool active, uint32_t q, const SceneD& sc, const RenderParams& rp, const Wave& w, Alloc&& alloc) {
+RT_HD void shade_vertex(bool active, uint32_t q, const SceneD& sc, const RenderParams& rp, const Wave& w, Alloc&& alloc, StagePtr shared_stage = StagePtr{nullptr, 0u, 0u}) {
     ShadeState<Surf> S;
     Sampler s2;
     BsdfSample bs;
-    NeeStage stage;
+    NeeStage local_stage;
     uint32_t k = 0;
     bool alive = false, final_skipped = false;
-    // few light samples per vertex (the usual case): one evaluation, entries staged in thread-local memory until their
-    // queue position is known; otherwise count first and evaluate again when writing
+    // few light samples per vertex (the usual case): one evaluation, entries staged (shared memory when the kernel offers a
+    // column that holds them, else thread-local memory) until their queue position is known; otherwise count first and
+    // evaluate again when writing
     const bool staged = w.shadow_k <= NEE_STAGE;
+    const StagePtr stage = (shared_stage.p && w.shadow_k <= shared_stage.capacity) ? shared_stage : StagePtr{local_stage.e, 1u, NEE_STAGE};
     if (active) active = shade_begin(q, sc, rp, w, S);
     if (active) {
         s2 = S.s;
         const bool add_direct = rp.accumulate_bounces || rp.max_ray_depth == w.depth + 1;
         const bool nee = !surface_is_delta(S.surf) && add_direct;
-        if (nee) k = staged ? nee_pass<1>(sc, rp, w, S, s2, 0u, NEE_STAGE, &stage) : nee_pass<0>(sc, rp, w, S, s2, 0u, 0u, nullptr);
+        if (nee) k = staged ? nee_pass<1>(sc, rp, w, S, s2, 0u, NEE_STAGE, stage) : nee_pass<0>(sc, rp, w, S, s2, 0u, 0u, stage);
         alive = surface_sample(S.surf, S.wo, s2, bs) == S_VALID;
         if (alive && (is_zero(bs.f) || bs.pdf == 0.0f)) alive = false;
         // The ray of the last depth can only add emitted light after a specular bounce, or the environment on a miss
@@ -532,9 +544,10 @@ RT_HD void shade_vertex(bool active, uint32_t q, const SceneD& sc, const RenderP
             for (uint32_t j = 0; j < k; j++) {
                 const size_t e = (size_t)first + j;
                 RT_CHECK(e < (size_t)w.capacity * (w.shadow_k ? w.shadow_k : 1u));
-                w.sray_o[e] = stage.o[j]; w.sray_d[e] = stage.d[j]; w.scontrib[e] = stage.c[j];
+                const float4* se = stage.p + (size_t)(3u * j) * stage.stride;
+                w.sray_o[e] = se[0]; w.sray_d[e] = se[stage.stride]; w.scontrib[e] = se[2u * stage.stride];
             }
-        else nee_pass<2>(sc, rp, w, S, S.s, first, k, nullptr);
+        else nee_pass<2>(sc, rp, w, S, S.s, first, k, stage);
         RT_CHECK(vpos < w.capacity && S.slot < w.capacity);
         w.svertex[vpos] = make_uint4(S.slot, first, k, 0u);
     }

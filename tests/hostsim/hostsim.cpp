@@ -222,7 +222,7 @@ void build(HostScene& hs, const rtcuda_scene_desc* d) {
         hs.n_levels++;
     }
     sc.node_count = counters[1];
-    if (std::getenv("HOSTSIM_NODESTATS") && !RT_FIXED_SLOTS) {
+    if (!RT_FIXED_SLOTS && std::getenv("HOSTSIM_NODESTATS") != nullptr) {
         uint32_t hist[9] = {0}, inner = 0, leafc = 0, prims = 0, hi_empty = 0;
         for (uint32_t i = 0; i < counters[1]; i++) {
             const Node8& nd = hs.nodes[i];

@@ -26,6 +26,13 @@ UNIT_SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "nsecond": 
 
 def main():
     workload, rep = sys.argv[1], sys.argv[2]
+    # the capture runs the workload's frame at a reduced spp (one batch either way): every launch then carries spp_bench / spp_profiled
+    # times fewer items, and the per-launch figures bench.py compares with (DRAM bytes, duration) are scaled by that ratio
+    scale = 1.0
+    for a in list(sys.argv[3:]):
+        if a.startswith("--scale="):
+            scale = float(a.split("=")[1])
+            sys.argv.remove(a)
     out_path = sys.argv[3] if len(sys.argv) > 3 else os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "ncu_counters.json")
     # either an .ncu-rep, or the text of `ncu -i <rep> --page raw --csv` made on the GPU box (reports of many launches exceed what
     # a GPU session may bring back)
@@ -61,8 +68,8 @@ def main():
             return sum(v * wi for v, wi in vals) / (sum(wi for _, wi in vals) or 1.0) if vals else None
         dram = sum((val(r, "rd") or 0.0) + (val(r, "wr") or 0.0) for r in rs) / len(rs)
         issue, dram_pct = avg("issue"), avg("dram_pct")
-        result[k] = {"launches_captured": len(rs), "ncu_ms_per_launch": tot / len(rs), "issue_active_pct": issue, "lanes_per_inst": avg("lanes"),
-                     "dram_bytes_per_launch": dram, "dram_pct_of_peak": dram_pct, "l2_hit_pct": avg("l2hit"), "l1_hit_pct": avg("l1hit"),
+        result[k] = {"launches_captured": len(rs), "ncu_ms_per_launch": scale * tot / len(rs), "issue_active_pct": issue, "lanes_per_inst": avg("lanes"),
+                     "dram_bytes_per_launch": scale * dram, "per_launch_scale": scale, "dram_pct_of_peak": dram_pct, "l2_hit_pct": avg("l2hit"), "l1_hit_pct": avg("l1hit"),
                      "achieved_occupancy_pct": avg("occ"), "registers": avg("regs"), "warp_instructions_per_launch": sum(val(r, "warp_inst") or 0 for r in rs) / len(rs),
                      "bound": "hbm" if (dram_pct or 0) > (issue or 0) else "issue", "ncu_source": os.path.basename(rep)}
     allc = json.load(open(out_path)) if os.path.exists(out_path) else {}

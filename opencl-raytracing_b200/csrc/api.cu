@@ -6,6 +6,7 @@
 // Error handling: status codes + rtcuda_last_error() instead of the exit() of the OptiX precedent
 // (crates/raytracing-optix/csrc/host/util.hpp:7-27).
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <cmath>
 #include <cstdio>
@@ -54,6 +55,20 @@ struct RtError {
 // scene and the BVH build and frees them again, and cudaMalloc / cudaFree serialise on the driver and get slow once tens
 // of GB are mapped in the process.
 static thread_local cudaStream_t tls_stream = nullptr;
+
+// RTCUDA_TRACE=1: host-side wall-clock marks of the phases of a call, per thread, on stderr (diagnostic of the end-to-end path)
+struct Trace {
+    static bool on() { static const bool v = std::getenv("RTCUDA_TRACE") != nullptr; return v; }
+    std::chrono::steady_clock::time_point t0;
+    const char* what; int rank;
+    Trace(const char* w, int r = 0) : t0(std::chrono::steady_clock::now()), what(w), rank(r) {}
+    void mark(const char* phase) {
+        if (!on()) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[rtcuda trace] %s r%d %-18s %8.3f ms\n", what, rank, phase, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
 
 template <typename T>
 struct DevBuf {
@@ -252,6 +267,7 @@ struct rtcuda_scene {
     DevBuf<LightD> lights;
     DevBuf<LightTri> light_tris;
     DevBuf<MaterialD> materials;
+    DevBuf<float4> mat_const;
     DevBuf<TextureD> textures;
     DevBuf<ImageD> images;
     DevBuf<MipChain> mips;
@@ -640,6 +656,7 @@ void build_bvh(rtcuda_scene* s, const std::vector<Instance>& instances, uint32_t
 
 void upload_scene(rtcuda_scene* s, const rtcuda_scene_desc* d, const GeoShare* share = nullptr) {
     cudaStream_t st = s->ctx->stream;
+    Trace tr("upload", share ? share->rank : 0);
     validate_desc(d);
     for (uint32_t m = 0; m < d->material_count; m++) {
         const rtcuda_material& mm = d->materials[m];
@@ -729,6 +746,7 @@ void upload_scene(rtcuda_scene* s, const rtcuda_scene_desc* d, const GeoShare* s
             if (!share->meet->wait()) throw RtError{RTCUDA_ERR_CUDA, "another device failed during the upload"};
         }
     }
+    tr.mark("geometry");
     {   // triangle indices must stay inside their mesh: checked on the device, one flag read back
         DevBuf<uint32_t> bad;
         bad.alloc(1);
@@ -819,10 +837,19 @@ void upload_scene(rtcuda_scene* s, const rtcuda_scene_desc* d, const GeoShare* s
     s->light_tris.alloc(n_light_tris);
     for (uint32_t i = 0; i < d->light_count; i++)
         if (lights[i].kind == RTCUDA_LIGHT_DIFFUSE_AREA)
-            launch_light_tris(st, s->shapes.p, lights[i].shape, shapes[lights[i].shape].tri_count, s->vertices.p, s->tris.p,
+            launch_light_tris(st, s->shapes.p, lights[i].shape, shapes[lights[i].shape].tri_count, s->vertices.p, s->tris.p, s->normals.p,
                               s->light_tris.p + lights[i].tri_table, s->lc);
+    // constant albedo per material (SceneD::mat_const)
+    std::vector<float4> mat_const(d->material_count, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+    for (uint32_t i = 0; i < d->material_count; i++) {
+        const uint32_t t = d->materials[i].albedo;
+        if (t != RTCUDA_NONE && t < d->texture_count && d->textures[t].kind == RTCUDA_TEXTURE_CONSTANT)
+            mat_const[i] = make_float4(d->textures[t].value[0], d->textures[t].value[1], d->textures[t].value[2], 1.0f);
+    }
+    s->mat_const.upload(mat_const.data(), mat_const.size(), st);
     CK(cudaStreamSynchronize(st));  // host vectors die at scope end
     CK(cudaEventRecord(e1, st));
+    tr.mark("tables+mips");
 
     SceneD& sc = s->sc;
     sc.instances = s->instances.p; sc.shapes = s->shapes.p; sc.lights = s->lights.p; sc.light_tris = s->light_tris.p; sc.materials = s->materials.p;
@@ -830,6 +857,14 @@ void upload_scene(rtcuda_scene* s, const rtcuda_scene_desc* d, const GeoShare* s
     sc.vertices = s->vertices.p; sc.tris = s->tris.p; sc.normals = s->normals.p; sc.uvs = s->uvs.p;
     sc.instance_count = d->instance_count; sc.light_count = d->light_count; sc.material_count = d->material_count;
     sc.texture_count = d->texture_count; sc.env_texture = d->environment_light_texture;
+    sc.mat_const = d->material_count ? s->mat_const.p : nullptr;
+    sc.use_light0 = 0;
+    if (d->light_count) {   // light 0 rides in the kernel parameter block (SceneD::light0)
+        sc.light0 = lights[0];
+        sc.light0_tri_count = lights[0].kind == RTCUDA_LIGHT_DIFFUSE_AREA ? shapes[lights[0].shape].tri_count : 0u;
+        sc.light0_has_normals = lights[0].kind == RTCUDA_LIGHT_DIFFUSE_AREA && shapes[lights[0].shape].normal_offset != NONE ? 1u : 0u;
+        sc.use_light0 = std::getenv("RTCUDA_NO_LIGHT0") ? 0u : 1u;   // (the variable is an A/B aid)
+    }
     sc.watertight = (s->ctx->bs.flags & RTCUDA_BACKEND_WATERTIGHT) ? 1u : 0u;
     sc.all_diffuse = 1;
     for (uint32_t m = 0; m < d->material_count; m++) if (d->materials[m].kind != RTCUDA_MATERIAL_DIFFUSE) sc.all_diffuse = 0;
@@ -848,6 +883,7 @@ void upload_scene(rtcuda_scene* s, const rtcuda_scene_desc* d, const GeoShare* s
     }
     CK(cudaEventRecord(e2, st));
     CK(cudaStreamSynchronize(st));
+    tr.mark("bvh");
     float ms_up = 0, ms_build = 0;
     CK(cudaEventElapsedTime(&ms_up, e0, e1));
     CK(cudaEventElapsedTime(&ms_build, e1, e2));
@@ -1042,7 +1078,9 @@ void render_device(rtcuda_scene* s, const rtcuda_settings* settings, const rtcud
     const uint32_t n_samples_total = sample_hi - sample_lo;
     const RenderParams rp = make_params(settings);
     const bool collect = (s->ctx->bs.collect_stats & RTCUDA_STATS_COUNTERS) != 0;
+    Trace tr("render_device", (int)s->ctx->bs.tile_rank);
     if (!s->pixel_list.p) build_pixel_list(s);
+    tr.mark("pixel list");
     const uint32_t np_all = s->n_my_pixels;
     const size_t npix_img = (size_t)s->width * s->height;
     s->stats_dev.ensure(STAT_TOTAL);
@@ -1115,8 +1153,10 @@ void render_device(rtcuda_scene* s, const rtcuda_settings* settings, const rtcud
             uint32_t ns_batch = std::max(1u, std::min(n_samples_total, capacity / np_batch));
             const uint32_t n_sample_batches = (n_samples_total + ns_batch - 1) / ns_batch;
             ns_batch = (n_samples_total + n_sample_batches - 1) / n_sample_batches;
+            tr.mark("sizing");
             ensure_wave(s, np_batch * ns_batch, shadow_k, rp.max_ray_depth);
             s->accum.ensure(nb);
+            tr.mark("arena");
             Wave w{};
             w.pixel_list = s->beauty_list;
             w.capacity = np_batch * ns_batch;
@@ -1179,9 +1219,11 @@ void render_device(rtcuda_scene* s, const rtcuda_settings* settings, const rtcud
         }
     }
     CK(cudaEventRecord(e1, st));
+    tr.mark("enqueue");
     unsigned long long h_stats[STAT_TOTAL];
     CK(cudaMemcpyAsync(h_stats, s->stats_dev.p, sizeof h_stats, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    tr.mark("gpu");
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, e0, e1));
     cudaEventDestroy(e0); cudaEventDestroy(e1);
@@ -1424,8 +1466,11 @@ void multi_render_host(rtcuda_scene* parent, const rtcuda_settings* settings, rt
         rtcuda_scene* sub = parent->subs[r];
         enter(sub);
         cudaStream_t st = sub->ctx->stream;
+        Trace tr("render_host", (int)r);
         rtcuda_outputs dev = staging_planes(sub, o, *out);
+        tr.mark("staging planes");
         render_device(sub, settings, &dev);
+        tr.mark("render_device");
         PlaneSlot dp[N_PLANES], hp[N_PLANES];
         planes_of(dev, o, dp);
         planes_of(*out, o, hp);
@@ -1441,6 +1486,7 @@ void multi_render_host(rtcuda_scene* parent, const rtcuda_settings* settings, rt
         }
         CK(cudaMemcpyAsync(sub->h_packed, sub->packed, words * 4, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
+        tr.mark("pack + d2h");
         const uint32_t np = sub->n_my_pixels, W = sub->width;
         const uint32_t* list = sub->host_pixel_list.data();
         size_t off = 0;
@@ -1456,6 +1502,7 @@ void multi_render_host(rtcuda_scene* parent, const rtcuda_settings* settings, rt
             }
             off += (size_t)np * ch;
         }
+        tr.mark("host scatter");
     });
 }
 

@@ -26,6 +26,18 @@ constexpr int BLOCK = 256;
 
 static inline uint32_t grid_for(uint32_t n, int block = BLOCK) { return n ? (n + block - 1) / block : 1; }
 
+// L2 prefetch of a line a later iteration reads (no register, no scoreboard entry)
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// Queue entries the persistent traversal kernels prefetch ahead of their fetch counter, in units of the rays the grid holds
+// in flight (0 = off)
+#ifndef RT_REFILL_PREFETCH
+#define RT_REFILL_PREFETCH 1
+#endif
+// k_shade: prefetch of the next chunk's slot-indexed state and primitive record (0 = off)
+#ifndef RT_SHADE_PREFETCH
+#define RT_SHADE_PREFETCH 0
+#endif
+
 // ---------------------------------------------------------------------------------------------------
 // queue compaction: one global atomic per block per queue
 // ---------------------------------------------------------------------------------------------------
@@ -147,6 +159,12 @@ __global__ void __launch_bounds__(BLOCK, 4) k_extend(const __grid_constant__ Sce
             base = __shfl_sync(FULL, base, leader);
             if (!have) {
                 const uint32_t mine = base + (uint32_t)__popc(need & lt);
+#if RT_REFILL_PREFETCH
+                {
+                    const uint32_t ahead = mine + (uint32_t)RT_REFILL_PREFETCH * gridDim.x * BLOCK;
+                    if (ahead < n) { prefetch_l2(w.ray_o_in + ahead); prefetch_l2(w.ray_d_in + ahead); }
+                }
+#endif
                 if (mine < n) {
                     q = mine;
                     const float4 o4 = w.ray_o_in[q], d4 = w.ray_d_in[q];
@@ -191,8 +209,30 @@ __global__ void __launch_bounds__(BLOCK, std::is_same<Surf, DiffuseSurface>::val
     const StagePtr stage_col{nullptr, 0u, 0u};
 #endif
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&w.stats[STAT_SHADED], (unsigned long long)n);
+#if RT_SHADE_PREFETCH
+    // Software pipeline over the chunks of this block: a vertex costs two dependent DRAM round trips before any arithmetic
+    // (queue entry -> slot / primitive -> path state / primitive record). The slot and primitive of the NEXT chunk's entry are
+    // loaded one iteration early (two registers), their state and record lines are prefetched into L2 at the top of this
+    // iteration, and the entry after that is prefetched as lines.
+    const uint32_t stride = gridDim.x * BLOCK;
+    uint32_t slot_next = NONE, prim_next = NONE;
+    {
+        const uint32_t q1 = blockIdx.x * BLOCK + threadIdx.x + stride;
+        if (q1 < n) { slot_next = f2u(w.ray_d_in[q1].w); prim_next = f2u(w.hits[q1].y); }
+    }
+#endif
     for (uint32_t base = blockIdx.x * BLOCK; base < n; base += gridDim.x * BLOCK) {
         const uint32_t q = base + threadIdx.x;
+#if RT_SHADE_PREFETCH
+        if (slot_next != NONE) prefetch_l2(w.state + slot_next);
+        if (prim_next != NONE && sc.shade_recs) prefetch_l2(sc.shade_recs + prim_next);
+        if (q + stride < n) prefetch_l2(w.ray_o_in + q + stride);
+        {
+            const uint32_t q2 = q + 2u * stride;
+            slot_next = NONE; prim_next = NONE;
+            if (q2 < n) { slot_next = f2u(w.ray_d_in[q2].w); prim_next = f2u(w.hits[q2].y); }
+        }
+#endif
         shade_vertex<Surf>(q < n, q, sc, rp, w, [&](bool cont, bool has_vertex, uint32_t k, bool final_skipped, uint32_t& rpos, uint32_t& vpos, uint32_t& first) {
             const unsigned FULL = 0xffffffffu;
             const unsigned mc = __ballot_sync(FULL, cont), mv = __ballot_sync(FULL, has_vertex);
@@ -273,6 +313,12 @@ __global__ void __launch_bounds__(BLOCK, SHADOW_BLOCKS) k_shadow(const __grid_co
             base = __shfl_sync(FULL, base, leader);
             if (!have) {
                 const uint32_t mine = base + (uint32_t)__popc(need & lt);
+#if RT_REFILL_PREFETCH
+                {
+                    const uint32_t ahead = mine + (uint32_t)RT_REFILL_PREFETCH * gridDim.x * BLOCK;
+                    if (ahead < n) { prefetch_l2(w.sray_o + ahead); prefetch_l2(w.sray_d + ahead); }
+                }
+#endif
                 if (mine < n) {
                     q = mine;
                     const float4 o4 = w.sray_o[q], d4 = w.sray_d[q];
@@ -475,14 +521,14 @@ void launch_sort(cudaStream_t st, void* temp, size_t temp_bytes, const uint64_t*
 }
 
 __global__ void __launch_bounds__(BLOCK) k_light_tris(const ShapeD* shapes, uint32_t shape, uint32_t tri_count, const float* vertices,
-                                                       const uint32_t* tris, LightTri* out) {
+                                                       const uint32_t* tris, const float* normals, LightTri* out) {
     const uint32_t i = blockIdx.x * BLOCK + threadIdx.x;
-    if (i < tri_count) light_tri_body(i, shapes[shape], vertices, tris, out);
+    if (i < tri_count) light_tri_body(i, shapes[shape], vertices, tris, normals, out);
 }
 void launch_light_tris(cudaStream_t st, const ShapeD* shapes, uint32_t shape, uint32_t tri_count, const float* vertices, const uint32_t* tris,
-                       LightTri* out, LaunchCounter& lc) {
+                       const float* normals, LightTri* out, LaunchCounter& lc) {
     if (!tri_count) return;
-    k_light_tris<<<grid_for(tri_count), BLOCK, 0, st>>>(shapes, shape, tri_count, vertices, tris, out);
+    k_light_tris<<<grid_for(tri_count), BLOCK, 0, st>>>(shapes, shape, tri_count, vertices, tris, normals, out);
     lc.launches++;
 }
 

@@ -45,7 +45,7 @@ void launch_ploc_round(cudaStream_t st, const BuildCtx& b, void* scan_temp, size
 // emitter triangle table (rt_scene.h LightTri)
 void launch_check_indices(cudaStream_t st, const uint32_t* idx, size_t n, uint32_t vertex_count, uint32_t* bad, LaunchCounter& lc);
 void launch_light_tris(cudaStream_t st, const ShapeD* shapes, uint32_t shape, uint32_t tri_count, const float* vertices, const uint32_t* tris,
-                       LightTri* out, LaunchCounter& lc);
+                       const float* normals, LightTri* out, LaunchCounter& lc);
 
 // shading records (rt_scene.h ShadeRec), one per packed primitive
 void launch_shade_recs(cudaStream_t st, const SceneD& sc, ShadeRec* out, LaunchCounter& lc);

@@ -535,6 +535,16 @@ RT_HD int surface_sample(const DiffuseSurface& s, V3, Sampler& smp, BsdfSample& 
     return validate_sample(out);
 }
 RT_HD void get_surface(const SceneD& sc, const MaterialD& m, const MatCtx& c, DiffuseSurface& out) { out.albedo = xyz(tex(sc, m.albedo, c)); }
+// Diffuse material by index: a constant albedo comes from the per-material table (one load instead of the dependent
+// material -> texture -> value chain); the value is the one tex() returns for a constant texture
+RT_HD void get_surface_of(const SceneD& sc, uint32_t material, const MatCtx& c, DiffuseSurface& out) {
+    if (sc.mat_const) {
+        const float4 mc = ldg(sc.mat_const + material);
+        if (mc.w != 0.0f) { out.albedo = xyz(mc); return; }
+    }
+    get_surface(sc, sc.materials[material], c, out);
+}
+RT_HD void get_surface_of(const SceneD& sc, uint32_t material, const MatCtx& c, Surface& out) { get_surface(sc, sc.materials[material], c, out); }
 
 RT_HD bool get_mip_level(const SceneD& sc, const MaterialD& m, const MatCtx& c, float& level) {  // materials.rs:957-968
     if (m.kind != 0) return false;

@@ -147,6 +147,23 @@ RT_HD V3 apply_vector(const M4& a, V3 v) {
     return mk3(a.m[0] * v.x + a.m[1] * v.y + a.m[2] * v.z, a.m[4] * v.x + a.m[5] * v.y + a.m[6] * v.z,
                a.m[8] * v.x + a.m[9] * v.y + a.m[10] * v.z);
 }
+// rows 0..2 of a matrix that lives in device memory at a 16-byte aligned address (Instance arrays), as three 128-bit loads
+RT_HD void load_rows3(const M4& a, float4& r0, float4& r1, float4& r2) {
+#if defined(__CUDA_ARCH__)
+    const float4* p = reinterpret_cast<const float4*>(a.m);
+    r0 = __ldg(p); r1 = __ldg(p + 1); r2 = __ldg(p + 2);
+#else
+    r0 = make_float4(a.m[0], a.m[1], a.m[2], a.m[3]); r1 = make_float4(a.m[4], a.m[5], a.m[6], a.m[7]); r2 = make_float4(a.m[8], a.m[9], a.m[10], a.m[11]);
+#endif
+}
+// four consecutive 32-bit fields at a 16-byte aligned device address
+RT_HD uint4 load_u4(const uint32_t* p) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(reinterpret_cast<const uint4*>(p));
+#else
+    return make_uint4(p[0], p[1], p[2], p[3]);
+#endif
+}
 RT_HD V3 apply_vector_transposed(const M4& a, V3 v) {
     return mk3(a.m[0] * v.x + a.m[4] * v.y + a.m[8] * v.z, a.m[1] * v.x + a.m[5] * v.y + a.m[9] * v.z,
                a.m[2] * v.x + a.m[6] * v.y + a.m[10] * v.z);

@@ -132,11 +132,15 @@ RT_HD void reconstruct_hit(const SceneD& sc, V3 o, V3 d, const Hit& h, bool need
         if (!(flags & REC_SPHERE)) {
             const uint32_t geom = f2u(a.w);
             const Instance& inst = sc.instances[geom];
+            // the instance's inverse rows and its (shape, kind, material, light) quad as four 128-bit loads
+            float4 w0, w1, w2;
+            load_rows3(inst.w2o, w0, w1, w2);
+            const uint4 ids = load_u4(&inst.shape);
             out.t = h.t;
             out.geom_id = geom;
             out.prim_id = f2u(b.w);
-            out.material = inst.material;     // (the record's copies are the instance's values: one scattered load less for
-            out.light = inst.area_light;      //  meshes without uvs, whose fourth and fifth record words are never read)
+            out.material = ids.z;     // (the record's copies are the instance's values: one scattered load less for
+            out.light = ids.w;        //  meshes without uvs, whose fourth and fifth record words are never read)
             const float u = h.u, v = h.v, w = 1.0f - u - v;
             const V3 n_obj = (flags & REC_FLAT) ? xyz(a) : unit(w * xyz(a) + u * xyz(b) + v * xyz(c));
             V2 uv0 = mk2(0, 0), uv1 = mk2(1, 0), uv2 = mk2(0, 1);
@@ -146,9 +150,11 @@ RT_HD void reconstruct_hit(const SceneD& sc, V3 o, V3 d, const Hit& h, bool need
             }
             out.uv = w * uv0 + u * uv1 + v * uv2;
             out.point = o + d * h.t;
-            out.normal = unit(unit(apply_vector_transposed(inst.w2o, n_obj)));
-            out.dpdu = apply_vector(inst.o2w, mk3(0.0f));
-            out.dpdv = out.dpdu;
+            out.normal = unit(unit(mk3(w0.x * n_obj.x + w1.x * n_obj.y + w2.x * n_obj.z, w0.y * n_obj.x + w1.y * n_obj.y + w2.y * n_obj.z,
+                                       w0.z * n_obj.x + w1.z * n_obj.y + w2.z * n_obj.z)));   // apply_vector_transposed(inst.w2o, n_obj)
+            // dpdu / dpdv = o2w * 0: only the anti-aliased primary hit reads them, and that hit takes the long way below
+            out.dpdu = mk3(0.0f);
+            out.dpdv = mk3(0.0f);
             return;
         }
     }
@@ -248,7 +254,9 @@ RT_HD MatCtx matctx_from_differentials(const HitInfo& hit, const Ray& ray, const
 struct LightSample { V3 radiance; V3 origin; V3 dir; float distance, pdf; };
 
 // lights.rs:14-122 (quirks kept: object-space triangle area and normal, un-normalised dir_world in the cosine)
-RT_HD LightSample sample_light(const SceneD& sc, const LightD& l, V3 point, Sampler& s) {
+// `em_tri_count` / `em_has_normals`: the two fields of the emitter's shape record an area light needs (callers read them from
+// SceneD::shapes, or from the kernel-parameter copy for light 0).
+RT_HD LightSample sample_light(const SceneD& sc, const LightD& l, uint32_t em_tri_count, bool em_has_normals, V3 point, Sampler& s) {
     LightSample ls;
     V3 a = mk3(l.a[0], l.a[1], l.a[2]), b = mk3(l.b[0], l.b[1], l.b[2]);
     if (l.kind == 0) {
@@ -262,10 +270,9 @@ RT_HD LightSample sample_light(const SceneD& sc, const LightD& l, V3 point, Samp
         ls.radiance = b; ls.origin = point - a * diam; ls.dir = unit(a); ls.distance = diam; ls.pdf = 1.0f;
         return ls;
     }
-    const ShapeD& em = sc.shapes[l.shape];
     float pdf = 1.0f;
-    pdf /= (float)em.tri_count;
-    uint32_t tri = s.u32_range(0, em.tri_count);
+    pdf /= (float)em_tri_count;
+    uint32_t tri = s.u32_range(0, em_tri_count);
     V2 smp = s.uniform2();
     V3 bary;
     if (smp.x < smp.y) { float b0 = smp.x / 2.0f, b1 = smp.y - smp.x / 2.0f; bary = mk3(b0, b1, 1.0f - b0 - b1); }
@@ -279,13 +286,8 @@ RT_HD LightSample sample_light(const SceneD& sc, const LightD& l, V3 point, Samp
     V3 dir_world = point - p_world;
     float d = length(dir_world);
     V3 n;
-    if (em.normal_offset == NONE) n = mk3(r1.w, r2.w, ldg(&lt->nz).x);
-    else {
-        const uint32_t* t = sc.tris + 3 * (size_t)(em.tri_offset + tri);
-        const uint32_t i0 = ldg(t), i1 = ldg(t + 1), i2 = ldg(t + 2);
-        n = unit(bary.x * load3(sc.normals, em.normal_offset + i0) + bary.y * load3(sc.normals, em.normal_offset + i1) +
-                 bary.z * load3(sc.normals, em.normal_offset + i2));
-    }
+    if (!em_has_normals) n = mk3(r1.w, r2.w, ldg(&lt->nz).x);
+    else n = unit(bary.x * xyz(ldg(&lt->n0)) + bary.y * xyz(ldg(&lt->n1)) + bary.z * xyz(ldg(&lt->n2)));   // the table's copies of the vertex normals
     ls.radiance = dot(dir_world, n) < 0.0f ? mk3(0.0f) : b;
     pdf *= (d * d) / fabsf(dot(dir_world, n));
     ls.origin = p_world; ls.dir = dir_world / d; ls.distance = d; ls.pdf = pdf;
@@ -433,7 +435,7 @@ RT_HD bool shade_begin(uint32_t q, const SceneD& sc, const RenderParams& rp, con
         mc = matctx_from_differentials(S.hit, S.ray, rdiff);
     } else mc = matctx_no_aa(S.hit.uv);
 
-    get_surface(sc, sc.materials[S.hit.material], mc, S.surf);
+    get_surface_of(sc, S.hit.material, mc, S.surf);
     S.fr.n = S.hit.normal;
     make_orthonormal_basis(S.hit.normal, S.fr.x, S.fr.y);
     S.wo = S.fr.to_local(-S.ray.d);
@@ -468,12 +470,13 @@ template <int MODE, typename Surf>
 RT_HD uint32_t nee_pass(const SceneD& sc, const RenderParams& rp, const Wave& w, const ShadeState<Surf>& S, Sampler& s, uint32_t first, uint32_t limit,
                         StagePtr stage) {
     uint32_t k = 0;
-    for (uint32_t li = 0; li < sc.light_count; li++) {
-        const LightD& light = sc.lights[li];
+    // one light at a time; `first_only` runs the body for light 0 from the kernel-parameter copy (SceneD::light0), whose
+    // fields are then constant-bank operands; the remaining lights come from memory
+    auto one_light = [&](const LightD& light, uint32_t em_tri_count, bool em_has_normals) {
         const uint32_t n = light.kind == 2 ? rp.light_sample_count : 1u;
         const float inv_n = 1.0f / (float)n;
         for (uint32_t j = 0; j < n; j++) {
-            LightSample ls = sample_light(sc, light, S.hit.point, s);
+            LightSample ls = sample_light(sc, light, em_tri_count, em_has_normals, S.hit.point, s);
             V3 wi = S.fr.to_local(-ls.dir);
             // contribution if unoccluded (lib.rs:337-343); zero contributions never need a shadow ray
             V3 c = mk3(0.0f);
@@ -495,6 +498,14 @@ RT_HD uint32_t nee_pass(const SceneD& sc, const RenderParams& rp, const Wave& w,
                 k++;
             }
         }
+    };
+    uint32_t li = 0;
+    if (sc.use_light0 && sc.light_count) { one_light(sc.light0, sc.light0_tri_count, sc.light0_has_normals != 0u); li = 1; }
+    for (; li < sc.light_count; li++) {
+        const LightD& light = sc.lights[li];
+        uint32_t tc = 0; bool hn = false;
+        if (light.kind == 2) { const ShapeD& em = sc.shapes[light.shape]; tc = em.tri_count; hn = em.normal_offset != NONE; }
+        one_light(light, tc, hn);
     }
     if (MODE == 2)   // the passes are the same arithmetic; should a compiler ever make them disagree, stay in bounds
         for (; k < limit; k++) {

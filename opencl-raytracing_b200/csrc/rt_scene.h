@@ -55,7 +55,9 @@ struct LightD {
 // object-space vertices, Mesh::tri_area (mesh.rs:271-278) and, for meshes without vertex normals, the geometric normal
 // unit(cross(p2 - p0, p1 - p0)) of lights.rs:93-95. Computed once per scene by light_tri_body with the reference's
 // formulas, so sample_light returns what it would have computed from the mesh arrays.
-struct LightTri { float4 p0_area, p1_nx, p2_ny, nz; };
+// For emitters WITH vertex normals the three object-space normals of the triangle ride along (copies of the mesh array:
+// lights.rs:96-105 interpolates them per sample), which spares three index loads and nine scalar normal loads per light sample.
+struct LightTri { float4 p0_area, p1_nx, p2_ny, nz, n0, n1, n2; };
 
 struct MaterialD { uint32_t kind, remap_roughness, albedo, eta, kappa, roughness, thickness, coat_albedo; };
 
@@ -133,6 +135,17 @@ struct SceneD {
     uint32_t tex_uses_derivs; // some texture is an image or a checker: the only consumers of the uv derivatives (MatCtx); without
                               // one, the primary hit skips the camera-ray differentials (same values: nothing would read them)
     uint32_t watertight;      // RTCUDA_BACKEND_WATERTIGHT: Woop's watertight triangle test instead of the reference's Moller-Trumbore
+    // Scene-wide constants of the shade kernel that live in the KERNEL PARAMETER block (constant bank: operands of the
+    // arithmetic, no load instruction, no scoreboard wait) instead of behind pointers. ncu, round 2: a C3 vertex issued 207
+    // global loads, 180 of them in the four light samples — the light record, its emitter's shape record and the emitter's
+    // vertex normals, all at warp-uniform addresses (profiles/r4c_ncu_summary.md).
+    //   light0           copy of lights[0] (valid when light_count >= 1); the other lights are read from memory
+    //   light0_tri_count / light0_has_normals   what sample_light needs of the emitter's shape record
+    //   mat_const        per material: xyz = the albedo when it is a CONSTANT texture, w = 1 then (else 0): Diffuse
+    //                    surfaces skip the material -> texture -> value chain of dependent loads
+    LightD light0;
+    uint32_t light0_tri_count, light0_has_normals, use_light0, _pad_l0;
+    const float4* mat_const;
     float scene_center[3];
     float scene_radius;       // +inf when the BVH root is a leaf (bvh2.rs:448-452 quirk, see rt_shade.h)
     // World bounds of all primitives, grown by 1e-3 of their largest extent: camera rays that miss them are not queued
@@ -148,7 +161,7 @@ RT_HD void set_scene_bounds(SceneD& sc, V3 mn, V3 mx, bool any) {
 }
 
 RT_HD V3 load3(const float* p, uint32_t i) { return mk3(ldg(p + 3 * (size_t)i), ldg(p + 3 * (size_t)i + 1), ldg(p + 3 * (size_t)i + 2)); }
-RT_HD void light_tri_body(uint32_t tri, const ShapeD& em, const float* vertices, const uint32_t* tris, LightTri* out) {
+RT_HD void light_tri_body(uint32_t tri, const ShapeD& em, const float* vertices, const uint32_t* tris, const float* normals, LightTri* out) {
     const uint32_t* t = tris + 3 * (size_t)(em.tri_offset + tri);
     const V3 p0 = load3(vertices, em.vertex_offset + t[0]), p1 = load3(vertices, em.vertex_offset + t[1]), p2 = load3(vertices, em.vertex_offset + t[2]);
     const float area = length(cross(p1 - p0, p2 - p0)) / 2.0f;
@@ -158,6 +171,11 @@ RT_HD void light_tri_body(uint32_t tri, const ShapeD& em, const float* vertices,
     r.p1_nx = make_float4(p1.x, p1.y, p1.z, n.x);
     r.p2_ny = make_float4(p2.x, p2.y, p2.z, n.y);
     r.nz = make_float4(n.z, 0.0f, 0.0f, 0.0f);
+    r.n0 = r.n1 = r.n2 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (em.normal_offset != NONE) {
+        const V3 a = load3(normals, em.normal_offset + t[0]), b = load3(normals, em.normal_offset + t[1]), c = load3(normals, em.normal_offset + t[2]);
+        r.n0 = make_float4(a.x, a.y, a.z, 0.0f); r.n1 = make_float4(b.x, b.y, b.z, 0.0f); r.n2 = make_float4(c.x, c.y, c.z, 0.0f);
+    }
     out[tri] = r;
 }
 

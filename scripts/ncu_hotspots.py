@@ -11,7 +11,8 @@ top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kre.split("<")[0]], capture_output=True, text=True).stdout
 lines = raw.splitlines()
 # first kernel block whose full name contains the requested text (k_shadow< vs k_shadow_gather)
-start = next(i for i, l in enumerate(lines) if l.startswith('"Kernel Name"') and kre in l)
+nth = int(os.environ.get("NTH", "0"))   # which launch of the kernel in the report
+start = [i for i, l in enumerate(lines) if l.startswith('"Kernel Name"') and kre in l][nth]
 end = next((i for i in range(start + 1, len(lines)) if lines[i].startswith('"Kernel Name"')), len(lines))
 kname = next(csv.reader([lines[start]]))[1]
 rows = list(csv.reader(lines[start + 1:end]))

@@ -36,6 +36,7 @@ struct HostScene {
     std::vector<ShapeD> shapes;
     std::vector<LightD> lights;
     std::vector<LightTri> light_tris;
+    std::vector<float4> mat_const;
     std::vector<MaterialD> materials;
     std::vector<TextureD> textures;
     std::vector<ImageD> images;
@@ -88,7 +89,7 @@ void build(HostScene& hs, const rtcuda_scene_desc* d) {
             b.tri_table = (uint32_t)hs.light_tris.size();
             hs.light_tris.resize(hs.light_tris.size() + hs.shapes[a.shape].tri_count);
             for (uint32_t t = 0; t < hs.shapes[a.shape].tri_count; t++)
-                light_tri_body(t, hs.shapes[a.shape], d->vertices, d->tris, hs.light_tris.data() + b.tri_table);
+                light_tri_body(t, hs.shapes[a.shape], d->vertices, d->tris, d->normals, hs.light_tris.data() + b.tri_table);
         }
     }
     hs.materials.resize(d->material_count);
@@ -148,6 +149,21 @@ void build(HostScene& hs, const rtcuda_scene_desc* d) {
     sc.vertices = d->vertices; sc.tris = d->tris; sc.normals = d->normals; sc.uvs = d->uvs;
     sc.instance_count = d->instance_count; sc.light_count = d->light_count; sc.material_count = d->material_count;
     sc.texture_count = d->texture_count; sc.env_texture = d->environment_light_texture;
+    // the kernel-parameter copies (SceneD::light0, mat_const) exactly as api.cu fills them
+    hs.mat_const.assign(d->material_count, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+    for (uint32_t i = 0; i < d->material_count; i++) {
+        const uint32_t t = d->materials[i].albedo;
+        if (t != RTCUDA_NONE && t < d->texture_count && d->textures[t].kind == RTCUDA_TEXTURE_CONSTANT)
+            hs.mat_const[i] = make_float4(d->textures[t].value[0], d->textures[t].value[1], d->textures[t].value[2], 1.0f);
+    }
+    sc.mat_const = d->material_count ? hs.mat_const.data() : nullptr;
+    sc.use_light0 = 0;
+    if (d->light_count) {
+        sc.light0 = hs.lights[0];
+        sc.light0_tri_count = hs.lights[0].kind == 2 ? hs.shapes[hs.lights[0].shape].tri_count : 0u;
+        sc.light0_has_normals = hs.lights[0].kind == 2 && hs.shapes[hs.lights[0].shape].normal_offset != NONE ? 1u : 0u;
+        sc.use_light0 = std::getenv("HOSTSIM_NO_LIGHT0") ? 0u : 1u;
+    }
     sc.watertight = std::getenv("HOSTSIM_WATERTIGHT") ? 1u : 0u;   // test switch for RTCUDA_BACKEND_WATERTIGHT
     sc.all_diffuse = 1;
     for (uint32_t m = 0; m < d->material_count; m++) if (d->materials[m].kind != 0) sc.all_diffuse = 0;

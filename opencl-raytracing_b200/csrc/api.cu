@@ -36,12 +36,23 @@ struct RtError {
     std::string msg;
 };
 
+// what the device had left when an allocation failed (appended to the error text)
+inline std::string oom_note(cudaError_t e) {
+    if (e != cudaErrorMemoryAllocation) return "";
+    cudaGetLastError();
+    int dev = -1;
+    size_t free_b = 0, total_b = 0;
+    cudaGetDevice(&dev);
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return ""; }
+    return " (device " + std::to_string(dev) + ": " + std::to_string(free_b >> 20) + " MiB free of " + std::to_string(total_b >> 20) + ")";
+}
+
 #define CK(call)                                                                                            \
     do {                                                                                                    \
         cudaError_t e_ = (call);                                                                            \
         if (e_ != cudaSuccess) {                                                                            \
             rtcuda_status st_ = e_ == cudaErrorMemoryAllocation ? RTCUDA_ERR_OUT_OF_MEMORY : RTCUDA_ERR_CUDA; \
-            throw RtError{st_, std::string(#call) + ": " + cudaGetErrorString(e_)};                           \
+            throw RtError{st_, std::string(#call) + ": " + cudaGetErrorString(e_) + oom_note(e_)};            \
         }                                                                                                   \
     } while (0)
 

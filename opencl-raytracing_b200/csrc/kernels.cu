@@ -14,15 +14,19 @@
 namespace rt {
 
 constexpr int BLOCK = 256;
-// resident blocks per SM asked of the Diffuse-only shade kernel (80 registers, ~160 B of spills): measured best of 2 / 3 / 4 on C3
+// Block shape of k_shade: 128 threads, 7 resident blocks per SM asked of the Diffuse-only instantiation = 72 registers per thread and
+// 28 warps per SM. The kernel waits on dependent loads (queue entry -> path state / primitive record -> instance), so warps in
+// flight count for more than registers: on C3 (256 threads x 3 blocks = 80 registers, 24 warps) 76.1 ms -> 72.5 ms; 64 registers /
+// 32 warps spills too much (79.1 ms), 96 registers / 20 warps 81.2 ms (profiles/r4f_ab.log, r4g_ab.log). The general
+// instantiation (every non-Diffuse material) keeps 128 registers.
 #ifndef SHADE_BLOCKS
-#define SHADE_BLOCKS 3
+#define SHADE_BLOCKS 7
 #endif
-// queue positions handed out per warp (two atomics per warp with output) instead of per block (one scan + two barriers per
-// chunk): shade 114 -> 110 ms on C3, 10.9 -> 10.0 ms on C5s (A/B: profiles/r1o_ab.log)
-#ifndef SHADE_WARP_ALLOC
-#define SHADE_WARP_ALLOC 1
+#ifndef SHADE_THREADS
+#define SHADE_THREADS 128
 #endif
+// (queue positions are handed out per warp — two atomics per warp with output — instead of per block with one scan and two
+// barriers per chunk: shade 114 -> 110 ms on C3, 10.9 -> 10.0 ms on C5s, profiles/r1o_ab.log)
 
 static inline uint32_t grid_for(uint32_t n, int block = BLOCK) { return n ? (n + block - 1) / block : 1; }
 
@@ -33,10 +37,8 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 #ifndef RT_REFILL_PREFETCH
 #define RT_REFILL_PREFETCH 1
 #endif
-// k_shade: prefetch of the next chunk's slot-indexed state and primitive record (0 = off)
-#ifndef RT_SHADE_PREFETCH
-#define RT_SHADE_PREFETCH 0
-#endif
+// (k_shade: an L2 prefetch of the next chunk's slot-indexed state and primitive record, one iteration ahead, cost 3 ms of 87 on C3
+// instead of hiding the two dependent round trips at the head of a vertex — profiles/r4b_ab.log, variant spf)
 
 // ---------------------------------------------------------------------------------------------------
 // queue compaction: one global atomic per block per queue
@@ -192,99 +194,57 @@ __global__ void __launch_bounds__(BLOCK, 4) k_extend(const __grid_constant__ Sce
 // rays, NEE vertices, shadow rays (a variable number per thread, consecutive per vertex) — and the last lane issues
 // the warp's two global atomics (one per queue counter; the 64-bit one carries vertices | shadow rays << 32).
 template <typename Surf>
-__global__ void __launch_bounds__(BLOCK, std::is_same<Surf, DiffuseSurface>::value ? SHADE_BLOCKS : 2) k_shade(const __grid_constant__ SceneD sc, const __grid_constant__ RenderParams rp,
+__global__ void __launch_bounds__(SHADE_THREADS, std::is_same<Surf, DiffuseSurface>::value ? SHADE_BLOCKS : 512 / SHADE_THREADS) k_shade(const __grid_constant__ SceneD sc, const __grid_constant__ RenderParams rp,
                                                   const __grid_constant__ Wave w) {
-#if !SHADE_WARP_ALLOC
-    __shared__ unsigned long long s_warp[BLOCK / 32][2];   // per warp: [0] continuation rays, [1] vertices | shadow rays << 32
-    __shared__ unsigned long long s_base[2];
-    const unsigned warp = threadIdx.x >> 5;
-#endif
     const uint32_t n = *w.n_in;
-    const unsigned lane = threadIdx.x & 31u;
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
 #if RT_NEE_SMEM > 0
     // staging columns of the next-event entries (rt_integrator.h StagePtr): NEE_SMEM entries x 3 fields per thread, 48 KB per block
-    __shared__ float4 s_stage[3 * NEE_SMEM * BLOCK];
-    const StagePtr stage_col{s_stage + threadIdx.x, (uint32_t)BLOCK, NEE_SMEM};
+    __shared__ float4 s_stage[3 * NEE_SMEM * SHADE_THREADS];
+    const StagePtr stage_col{s_stage + threadIdx.x, (uint32_t)SHADE_THREADS, NEE_SMEM};
 #else
     const StagePtr stage_col{nullptr, 0u, 0u};
 #endif
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&w.stats[STAT_SHADED], (unsigned long long)n);
-#if RT_SHADE_PREFETCH
-    // Software pipeline over the chunks of this block: a vertex costs two dependent DRAM round trips before any arithmetic
-    // (queue entry -> slot / primitive -> path state / primitive record). The slot and primitive of the NEXT chunk's entry are
-    // loaded one iteration early (two registers), their state and record lines are prefetched into L2 at the top of this
-    // iteration, and the entry after that is prefetched as lines.
-    const uint32_t stride = gridDim.x * BLOCK;
-    uint32_t slot_next = NONE, prim_next = NONE;
-    {
-        const uint32_t q1 = blockIdx.x * BLOCK + threadIdx.x + stride;
-        if (q1 < n) { slot_next = f2u(w.ray_d_in[q1].w); prim_next = f2u(w.hits[q1].y); }
-    }
-#endif
-    for (uint32_t base = blockIdx.x * BLOCK; base < n; base += gridDim.x * BLOCK) {
+    for (uint32_t base = blockIdx.x * SHADE_THREADS; base < n; base += gridDim.x * SHADE_THREADS) {
         const uint32_t q = base + threadIdx.x;
-#if RT_SHADE_PREFETCH
-        if (slot_next != NONE) prefetch_l2(w.state + slot_next);
-        if (prim_next != NONE && sc.shade_recs) prefetch_l2(sc.shade_recs + prim_next);
-        if (q + stride < n) prefetch_l2(w.ray_o_in + q + stride);
-        {
-            const uint32_t q2 = q + 2u * stride;
-            slot_next = NONE; prim_next = NONE;
-            if (q2 < n) { slot_next = f2u(w.ray_d_in[q2].w); prim_next = f2u(w.hits[q2].y); }
-        }
-#endif
-        shade_vertex<Surf>(q < n, q, sc, rp, w, [&](bool cont, bool has_vertex, uint32_t k, bool final_skipped, uint32_t& rpos, uint32_t& vpos, uint32_t& first) {
-            const unsigned FULL = 0xffffffffu;
-            const unsigned mc = __ballot_sync(FULL, cont), mv = __ballot_sync(FULL, has_vertex);
-            if (w.depth + 1 == rp.max_ray_depth) {   // launch-uniform: only the shade launch before the last depth can skip rays
-                const unsigned mf = __ballot_sync(FULL, final_skipped);
-                if (mf && lane == 0) atomicAdd(&w.stats[STAT_FINAL_SKIPPED], (unsigned long long)__popc(mf));
-            }
-            uint32_t incl = k;   // inclusive warp scan of the shadow-ray counts
+        // Per-warp allocation (two atomics per warp that has output, no block barrier: the warps of a block drift apart on
+        // their dependent loads, and a barrier per chunk made all of them wait for the slowest), issued as early as their
+        // counts are known and consumed as late as possible: the shadow-queue atomic right after next-event estimation (it
+        // returns during BSDF sampling), the ray-queue atomic before the shadow entries are copied out. Waiting for the two
+        // returns back to back was 6 % of the kernel's stall samples (ncu, profiles/r4e).
+        unsigned long long base1 = 0;   // lane 31: vertices | shadow rays << 32 before this warp's
+        uint32_t base0 = 0, incl = 0;    // lane 31: rays before this warp's; inclusive scan of the shadow-ray counts
+        unsigned mc = 0, mv = 0;
+        shade_vertex<Surf>(q < n, q, sc, rp, w,
+            [&](bool cont, bool has_vertex, uint32_t k, bool final_skipped, uint32_t& rpos, uint32_t& vpos, uint32_t& first) {
+                (void)has_vertex; (void)rpos;
+                mc = __ballot_sync(FULL, cont);
+                if (w.depth + 1 == rp.max_ray_depth) {   // launch-uniform: only the shade launch before the last depth can skip rays
+                    const unsigned mf = __ballot_sync(FULL, final_skipped);
+                    if (mf && lane == 0) atomicAdd(&w.stats[STAT_FINAL_SKIPPED], (unsigned long long)__popc(mf));
+                }
+                if (lane == 31 && mc) base0 = atomicAdd(w.n_out, (uint32_t)__popc(mc));
+                const unsigned long long b1 = __shfl_sync(FULL, base1, 31);
+                vpos = (uint32_t)b1 + (uint32_t)__popc(mv & lt);
+                first = (uint32_t)(b1 >> 32) + (incl - k);
+            },
+            stage_col,
+            [&](bool has_vertex, uint32_t k) {
+                mv = __ballot_sync(FULL, has_vertex);
+                incl = k;   // inclusive warp scan of the shadow-ray counts
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t up = __shfl_up_sync(FULL, incl, o);
-                if ((int)lane >= o) incl += up;
-            }
-#if SHADE_WARP_ALLOC
-            // per-warp allocation: two atomics per warp that has output, no block barrier (the warps of a block drift apart
-            // on their dependent loads; a barrier per chunk made all of them wait for the slowest)
-            unsigned long long base0 = 0, base1 = 0;
-            if (lane == 31) {
-                const uint32_t n0 = (uint32_t)__popc(mc);
-                const unsigned long long n1 = (unsigned long long)__popc(mv) | ((unsigned long long)incl << 32);
-                if (n0) base0 = (unsigned long long)atomicAdd(w.n_out, n0);
-                if (n1) base1 = atomicAdd(w.n_shadow, n1);
-            }
-            base0 = __shfl_sync(FULL, base0, 31);
-            base1 = __shfl_sync(FULL, base1, 31);
-            const unsigned lt = (1u << lane) - 1u;
-            const unsigned long long b1 = base1;
-            rpos = (uint32_t)base0 + (uint32_t)__popc(mc & lt);
-            vpos = (uint32_t)b1 + (uint32_t)__popc(mv & lt);
-#else
-            if (lane == 31) {
-                s_warp[warp][0] = (unsigned long long)__popc(mc);
-                s_warp[warp][1] = (unsigned long long)__popc(mv) | ((unsigned long long)incl << 32);
-            }
-            __syncthreads();
-            unsigned long long before0 = 0, before1 = 0, total0 = 0, total1 = 0;
-#pragma unroll
-            for (int i = 0; i < BLOCK / 32; i++) {
-                const unsigned long long a = s_warp[i][0], b = s_warp[i][1];
-                if (i < (int)warp) { before0 += a; before1 += b; }
-                total0 += a; total1 += b;
-            }
-            if (threadIdx.x == 0) s_base[0] = total0 ? (unsigned long long)atomicAdd(w.n_out, (uint32_t)total0) : 0ull;
-            if (threadIdx.x == 32) s_base[1] = total1 ? atomicAdd(w.n_shadow, total1) : 0ull;
-            __syncthreads();
-            const unsigned lt = (1u << lane) - 1u;
-            const unsigned long long b1 = s_base[1] + before1;
-            rpos = (uint32_t)(s_base[0] + before0) + (uint32_t)__popc(mc & lt);
-            vpos = (uint32_t)b1 + (uint32_t)__popc(mv & lt);
-#endif
-            first = (uint32_t)(b1 >> 32) + (incl - k);
-        }, stage_col);
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t up = __shfl_up_sync(FULL, incl, o);
+                    if ((int)lane >= o) incl += up;
+                }
+                if (lane == 31) {
+                    const unsigned long long n1 = (unsigned long long)__popc(mv) | ((unsigned long long)incl << 32);
+                    if (n1) base1 = atomicAdd(w.n_shadow, n1);
+                }
+            },
+            [&](uint32_t& rpos) { rpos = __shfl_sync(FULL, base0, 31) + (uint32_t)__popc(mc & lt); });
     }
 }
 
@@ -378,16 +338,16 @@ void launch_raygen(cudaStream_t st, const SceneD& sc, const RenderParams& rp, co
     k_raygen<<<grid_for(n), BLOCK, 0, st>>>(sc, rp, w, n);
     lc.launches++;
 }
-static uint32_t persistent_grid(const void* kernel, uint32_t n_max) {
+static uint32_t persistent_grid(const void* kernel, uint32_t n_max, int block = BLOCK) {
     static int sm_counts[64] = {0};   // per device: a process may drive several GPUs (multi-device contexts)
     int dev = 0;
     cudaGetDevice(&dev);
     int& sm_count = sm_counts[dev & 63];
     if (!sm_count) cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
     int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, BLOCK, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0);
     const uint32_t resident = (uint32_t)sm_count * (uint32_t)(per_sm > 0 ? per_sm : 1);
-    return std::max(1u, std::min(resident, grid_for(n_max)));
+    return std::max(1u, std::min(resident, grid_for(n_max, block)));
 }
 void launch_extend(cudaStream_t st, const SceneD& sc, const Wave& w, uint32_t n_max, float t_min, uint32_t* fetch_counter, bool stats,
                    LaunchCounter& lc) {
@@ -396,8 +356,8 @@ void launch_extend(cudaStream_t st, const SceneD& sc, const Wave& w, uint32_t n_
     lc.launches++;
 }
 void launch_shade(cudaStream_t st, const SceneD& sc, const RenderParams& rp, const Wave& w, uint32_t n_max, LaunchCounter& lc) {
-    if (sc.all_diffuse) k_shade<DiffuseSurface><<<persistent_grid((const void*)k_shade<DiffuseSurface>, n_max), BLOCK, 0, st>>>(sc, rp, w);
-    else k_shade<Surface><<<persistent_grid((const void*)k_shade<Surface>, n_max), BLOCK, 0, st>>>(sc, rp, w);
+    if (sc.all_diffuse) k_shade<DiffuseSurface><<<persistent_grid((const void*)k_shade<DiffuseSurface>, n_max, SHADE_THREADS), SHADE_THREADS, 0, st>>>(sc, rp, w);
+    else k_shade<Surface><<<persistent_grid((const void*)k_shade<Surface>, n_max, SHADE_THREADS), SHADE_THREADS, 0, st>>>(sc, rp, w);
     lc.launches++;
 }
 void launch_shadow(cudaStream_t st, const SceneD& sc, const Wave& w, uint32_t n_max, uint32_t* fetch_counter, bool stats, LaunchCounter& lc) {

@@ -518,14 +518,23 @@ RT_HD uint32_t nee_pass(const SceneD& sc, const RenderParams& rp, const Wave& w,
 }
 
 // alloc(continue_path, has_nee_vertex, n_shadow_rays, final_ray_skipped, &ray_pos, &vertex_pos, &first_shadow_ray)
-template <typename Surf, typename Alloc>
-RT_HD void shade_vertex(bool active, uint32_t q, const SceneD& sc, const RenderParams& rp, const Wave& w, Alloc&& alloc, StagePtr shared_stage = StagePtr{nullptr, 0u, 0u}) {
+// The kernel splits the allocation in three so that the two global atomics of a warp are in flight while it still has work:
+//   early(has_nee_vertex, n_shadow_rays)   right after next-event estimation: the shadow-queue atomic is issued here and
+//                                          returns during BSDF sampling;
+//   alloc(...)                             as above, but it may leave ray_pos unset ...
+//   late(&ray_pos)                         ... until after the shadow entries have been copied out.
+// All three are warp-collective: every thread of the launch calls each of them exactly once per chunk. The CPU harness passes
+// `alloc` only.
+template <typename Surf, typename Alloc, typename Early, typename Late>
+RT_HD void shade_vertex(bool active, uint32_t q, const SceneD& sc, const RenderParams& rp, const Wave& w, Alloc&& alloc, StagePtr shared_stage, Early&& early,
+                        Late&& late) {
     ShadeState<Surf> S;
     Sampler s2;
     BsdfSample bs;
     NeeStage local_stage;
     uint32_t k = 0;
     bool alive = false, final_skipped = false;
+    V3 nd = mk3(0.0f);
     // few light samples per vertex (the usual case): one evaluation, entries staged (shared memory when the kernel offers a
     // column that holds them, else thread-local memory) until their queue position is known; otherwise count first and
     // evaluate again when writing
@@ -537,6 +546,9 @@ RT_HD void shade_vertex(bool active, uint32_t q, const SceneD& sc, const RenderP
         const bool add_direct = rp.accumulate_bounces || rp.max_ray_depth == w.depth + 1;
         const bool nee = !surface_is_delta(S.surf) && add_direct;
         if (nee) k = staged ? nee_pass<1>(sc, rp, w, S, s2, 0u, NEE_STAGE, stage) : nee_pass<0>(sc, rp, w, S, s2, 0u, 0u, stage);
+    }
+    early(k != 0u, k);
+    if (active) {
         alive = surface_sample(S.surf, S.wo, s2, bs) == S_VALID;
         if (alive && (is_zero(bs.f) || bs.pdf == 0.0f)) alive = false;
         // The ray of the last depth can only add emitted light after a specular bounce, or the environment on a miss
@@ -546,11 +558,25 @@ RT_HD void shade_vertex(bool active, uint32_t q, const SceneD& sc, const RenderP
             alive = false;
             final_skipped = true;
         }
+        // Everything that does not need a queue position happens BEFORE the allocation (a warp-wide scan plus two global
+        // atomics whose return the warp waits for): the emitted light, the path state of the continuation, and the new
+        // direction. What stays live across the wait is the hit point, the direction and three counters — the frame, the
+        // BSDF sample, the weights and the sampler state used to be carried across it through thread-local memory, and the
+        // reloads behind the wait were 17 % of the kernel's stall samples (ncu, profiles/r4e).
+        if (S.dirty) add_emitted(w, S);
+        if (alive) {
+            const V3 pw = S.path_weight * (bs.f * fabsf(bs.wi.z) / bs.pdf);
+            const uint32_t spec = (bs.component & SPECULAR) ? 1u : 0u;
+            w.state[S.slot].weight = make_float4(pw.x, pw.y, pw.z, u2f(spec | (s2.dimension << 8)));
+            RngState rs;
+            rs.state = s2.rng.state; rs.inc = s2.rng.inc;
+            w.state[S.slot].rng = rs;
+            nd = S.fr.to_world(bs.wi);
+        }
     }
     uint32_t rpos = 0, vpos = 0, first = 0;
     alloc(alive, k != 0u, k, final_skipped, rpos, vpos, first);
-    if (!active) return;
-    if (k) {
+    if (active && k) {
         if (staged)
             for (uint32_t j = 0; j < k; j++) {
                 const size_t e = (size_t)first + j;
@@ -562,18 +588,16 @@ RT_HD void shade_vertex(bool active, uint32_t q, const SceneD& sc, const RenderP
         RT_CHECK(vpos < w.capacity && S.slot < w.capacity);
         w.svertex[vpos] = make_uint4(S.slot, first, k, 0u);
     }
-    if (S.dirty) add_emitted(w, S);
+    late(rpos);
     if (!alive) return;
-    const V3 pw = S.path_weight * (bs.f * fabsf(bs.wi.z) / bs.pdf);
-    const uint32_t spec = (bs.component & SPECULAR) ? 1u : 0u;
-    w.state[S.slot].weight = make_float4(pw.x, pw.y, pw.z, u2f(spec | (s2.dimension << 8)));
-    RngState rs;
-    rs.state = s2.rng.state; rs.inc = s2.rng.inc;
-    w.state[S.slot].rng = rs;
-    const V3 nd = S.fr.to_world(bs.wi);
     RT_CHECK(rpos < w.capacity);
     w.ray_o_out[rpos] = make_float4(S.hit.point.x, S.hit.point.y, S.hit.point.z, RT_INF);
     w.ray_d_out[rpos] = make_float4(nd.x, nd.y, nd.z, u2f(S.slot));
+}
+
+template <typename Surf, typename Alloc>
+RT_HD void shade_vertex(bool active, uint32_t q, const SceneD& sc, const RenderParams& rp, const Wave& w, Alloc&& alloc, StagePtr shared_stage = StagePtr{nullptr, 0u, 0u}) {
+    shade_vertex<Surf>(active, q, sc, rp, w, alloc, shared_stage, [](bool, uint32_t) {}, [](uint32_t&) {});
 }
 
 // ---- shadow gather: add the unoccluded contributions of one NEE vertex to its path, in light-sample order ----

@@ -330,13 +330,13 @@ struct rtcuda_scene {
     // frame then reach the GPU in one submission, so a host thread that loses its core for tens of ms (shared box) no longer
     // leaves the GPU idle between kernels (5-40 ms gaps per 360 ms frame, profiles/r1s_gap.log).
     cudaGraphExec_t frame_exec = nullptr;
-    std::vector<uint64_t> frame_key;
+    std::vector<uint64_t> frame_key, seen_key;   // key of the instantiated graph; key of the last frame launched directly
     unsigned long long frame_launches = 0;
     bool capturing = false;
     ~rtcuda_scene() {
         if (frame_exec) cudaGraphExecDestroy(frame_exec);
         for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
-        if (packed) cudaFree(packed);
+        if (packed) cudaFreeAsync(packed, tls_stream);   // (the releasing thread has entered this scene's context)
         if (h_packed) g_pinned_cache.park(h_packed, h_packed_words * 4);
         for (uint32_t* q : peer_list) if (q) cudaFree(q);
         for (uint32_t* q : peer_recv) if (q) cudaFree(q);
@@ -1201,6 +1201,16 @@ void render_device(rtcuda_scene* s, const rtcuda_settings* settings, const rtcud
                                              (uint64_t)(uintptr_t)out->beauty, (uint64_t)(uintptr_t)s->arena.base, (uint64_t)(uintptr_t)s->accum.p,
                                              (uint64_t)(uintptr_t)s->stats_dev.p, (uint64_t)(uintptr_t)s->beauty_list, nb, np_batch, ns_batch, sample_lo,
                                              sample_hi, shadow_k, (uint64_t)s->ctx->bs.collect_stats, (uint64_t)sum_mode, (uint64_t)accumulate};
+                // The first frame of a key is launched directly: capture + instantiation cost 2-3 ms, which a one-shot
+                // `render(scene, settings)` would pay for a graph it never replays. The second frame with the same key is
+                // captured, later ones replay it.
+                if ((!s->frame_exec || key != s->frame_key) && key != s->seen_key) {
+                    if (s->frame_exec) { cudaGraphExecDestroy(s->frame_exec); s->frame_exec = nullptr; }
+                    s->frame_key.clear();
+                    s->seen_key = key;
+                    reset_spans(s);
+                    enqueue_frame();
+                } else {
                 if (!s->frame_exec || key != s->frame_key) {
                     reset_spans(s);
                     const unsigned long long l0 = s->lc.launches;
@@ -1226,6 +1236,7 @@ void render_device(rtcuda_scene* s, const rtcuda_settings* settings, const rtcud
                 }
                 CK(cudaGraphLaunch(s->frame_exec, st));
                 s->lc.launches += s->frame_launches;
+                }
             }
         }
     }
@@ -1453,10 +1464,11 @@ size_t pack_owned(rtcuda_scene* sub, const PlaneSlot planes[N_PLANES]) {
     size_t words = 0;
     for (int i = 0; i < N_PLANES; i++) if (planes[i].ptr) words += (size_t)np * planes[i].ch;
     if (words > sub->packed_words) {
-        CK(cudaStreamSynchronize(st));
-        if (sub->packed) cudaFree(sub->packed);
+        // from the stream-ordered pool (peer-accessible like the geometry arrays; a plain cudaMalloc / cudaFree pair costs
+        // milliseconds per one-shot render once peer mappings exist)
+        if (sub->packed) CK(cudaFreeAsync(sub->packed, st));
         sub->packed = nullptr; sub->packed_words = 0;
-        CK(cudaMalloc((void**)&sub->packed, words * 4));
+        CK(cudaMallocAsync((void**)&sub->packed, words * 4, st));
         sub->packed_words = words;
     }
     size_t off = 0;
@@ -1500,19 +1512,29 @@ void multi_render_host(rtcuda_scene* parent, const rtcuda_settings* settings, rt
         tr.mark("pack + d2h");
         const uint32_t np = sub->n_my_pixels, W = sub->width;
         const uint32_t* list = sub->host_pixel_list.data();
-        size_t off = 0;
-        for (int i = 0; i < N_PLANES; i++) {
-            if (!dp[i].ptr) continue;
-            const uint32_t ch = dp[i].ch;
-            uint32_t* dst = (uint32_t*)hp[i].ptr;
-            const uint32_t* src = sub->h_packed + off;
-            for (uint32_t k = 0; k < np; k++) {
-                const uint32_t p = list[k];
-                uint32_t* d = dst + ((size_t)(p >> 16) * W + (p & 0xffffu)) * ch;
-                for (uint32_t c = 0; c < ch; c++) d[c] = src[(size_t)k * ch + c];
+        // scatter into the caller's planes on a few host threads per GPU (a 1080p beauty plane on one thread: 13 ms)
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        const unsigned n_thr = (unsigned)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(8, hw / parent->subs.size()), np / 65536));
+        auto scatter = [&](uint32_t k0, uint32_t k1) {
+            size_t off = 0;
+            for (int i = 0; i < N_PLANES; i++) {
+                if (!dp[i].ptr) continue;
+                const uint32_t ch = dp[i].ch;
+                uint32_t* dst = (uint32_t*)hp[i].ptr;
+                const uint32_t* src = sub->h_packed + off;
+                for (uint32_t k = k0; k < k1; k++) {
+                    const uint32_t p = list[k];
+                    uint32_t* d = dst + ((size_t)(p >> 16) * W + (p & 0xffffu)) * ch;
+                    for (uint32_t c = 0; c < ch; c++) d[c] = src[(size_t)k * ch + c];
+                }
+                off += (size_t)np * ch;
             }
-            off += (size_t)np * ch;
-        }
+        };
+        std::vector<std::thread> helpers;
+        const uint32_t per = (np + n_thr - 1) / n_thr;
+        for (unsigned t = 1; t < n_thr; t++) helpers.emplace_back(scatter, std::min(np, per * t), std::min(np, per * (t + 1)));
+        scatter(0, std::min(np, per));
+        for (std::thread& h : helpers) h.join();
         tr.mark("host scatter");
     });
 }

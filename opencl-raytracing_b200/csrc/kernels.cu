@@ -112,6 +112,10 @@ constexpr int TRI_MIN = RT_TRI_MIN;
 #ifndef TRI_PER_PHASE
 #define TRI_PER_PHASE 2
 #endif
+// (refills served from per-warp reservations of 32 / 64 / 128 queue positions — one atomic per reservation instead of one per
+// refill — with both halves of a ray loaded before either is looked at and a bare MUFU.RCP for 1 / direction: k_extend 61.3 ->
+// 60.6 ms, k_shadow 112.8 -> 113.2-115.9 ms on C3; the extra loop-carried state spills in the 48-register kernel — not kept,
+// profiles/r4j_ab.log)
 // (a second node step per node phase for lanes that found inner children only: extend 92 -> 98 ms, shadow 149 -> 165 ms — not kept)
 // Resident blocks per SM asked of the any-hit kernel: 5 (48 registers, ~76 B of spills) hides more of its load latency than the 4
 // that 64 registers allow — k_shadow 174 -> 168 ms on C3; the closest-hit kernel carries more state and lost 1 % (A/B in

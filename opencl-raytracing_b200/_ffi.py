@@ -143,7 +143,7 @@ ABI_STRUCTS = [Camera, Shape, Instance, Light, Material, Texture, Image, SceneDe
 # every symbol include/rtcuda.h declares
 EXPORTED_SYMBOLS = ["rtcuda_init", "rtcuda_shutdown", "rtcuda_scene_upload", "rtcuda_scene_release", "rtcuda_release_cached_memory", "rtcuda_render",
                     "rtcuda_render_device", "rtcuda_render_samples_device", "rtcuda_render_samples_accumulate_device", "rtcuda_render_pixel", "rtcuda_get_stats", "rtcuda_last_error",
-                    "rtcuda_abi_version", "rtcuda_abi_struct_sizes"]
+                    "rtcuda_abi_version", "rtcuda_abi_struct_sizes", "rtcuda_host_alloc", "rtcuda_host_free"]
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, "libraytracing_cuda.so")
@@ -174,6 +174,10 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.rtcuda_scene_upload.restype = C.c_int
     lib.rtcuda_scene_release.argtypes = [C.c_void_p]
     lib.rtcuda_scene_release.restype = None
+    lib.rtcuda_host_alloc.argtypes = [C.c_size_t]
+    lib.rtcuda_host_alloc.restype = C.c_void_p
+    lib.rtcuda_host_free.argtypes = [C.c_void_p]
+    lib.rtcuda_host_free.restype = None
     lib.rtcuda_release_cached_memory.argtypes = []
     lib.rtcuda_release_cached_memory.restype = None
     lib.rtcuda_render.argtypes = [C.c_void_p, C.POINTER(Settings), C.POINTER(Outputs)]
@@ -211,3 +215,19 @@ def check(lib: C.CDLL, status: int, what: str) -> None:
     if status != 0:
         msg = lib.rtcuda_last_error()
         raise RtCudaError(f"{what} failed: {STATUS_NAMES.get(status, status)}: {msg.decode() if msg else ''}")
+
+
+def host_array(lib: C.CDLL, shape, dtype):
+    """A numpy array over page-locked memory from rtcuda_host_alloc (None when the library has none to give). The buffer returns
+    to the library's cache when the last array that views it is collected."""
+    import weakref
+    import numpy as np
+    dt = np.dtype(dtype)
+    n = int(np.prod(shape))
+    nbytes = n * dt.itemsize
+    ptr = lib.rtcuda_host_alloc(nbytes)
+    if not ptr:
+        return None
+    buf = (C.c_uint8 * nbytes).from_address(ptr)
+    weakref.finalize(buf, lib.rtcuda_host_free, ptr)   # numpy keeps `buf` alive as the base of every view
+    return np.frombuffer(buf, dtype=dt, count=n).reshape(shape)

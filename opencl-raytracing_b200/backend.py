@@ -113,7 +113,7 @@ class CudaRenderer:
 
     def render(self, settings: RaytracerSettings) -> RenderOutput:
         """raytracing_cpu::render: host planes, row-major [H,W,C]."""
-        out = RenderOutput.allocate(self.width, self.height, AovFlags(settings.outputs))
+        out = RenderOutput.allocate(self.width, self.height, AovFlags(settings.outputs), lib=self.lib)
         self.render_into(settings, out)
         return out
 

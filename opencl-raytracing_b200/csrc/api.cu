@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <condition_variable>
 #include <functional>
@@ -85,19 +86,26 @@ template <typename T>
 struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
+    // `peer_visible`: a plain cudaMalloc, which other GPUs of a multi-device context can read and write once peer access is
+    // enabled (cudaDeviceEnablePeerAccess maps every plain allocation). The stream-ordered pools stay private to their device:
+    // with peer access granted on the pools (cudaMemPoolSetAccess) cudaMallocAsync failed with "out of memory" on boxes with
+    // 150 GB free when several host threads grew peer-mapped pools at once (2-GPU test box, 8-GPU bench box, round 2).
+    bool peer_visible = false, is_plain = false;
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
     ~DevBuf() { release(); }
     void release() {
-        if (p) cudaFreeAsync(p, tls_stream);
+        if (p) { if (is_plain) cudaFree(p); else cudaFreeAsync(p, tls_stream); }
         p = nullptr;
         n = 0;
     }
     void alloc(size_t count) {
         release();
         n = count;
-        CK(cudaMallocAsync((void**)&p, std::max<size_t>(count, 1) * sizeof(T), tls_stream));
+        is_plain = peer_visible;
+        if (is_plain) CK(cudaMalloc((void**)&p, std::max<size_t>(count, 1) * sizeof(T)));
+        else CK(cudaMallocAsync((void**)&p, std::max<size_t>(count, 1) * sizeof(T), tls_stream));
     }
     void ensure(size_t count) {
         if (count > n || !p) alloc(count);
@@ -212,6 +220,31 @@ struct PinnedCache {
 };
 static PinnedCache g_pinned_cache;
 
+// Host planes handed out by rtcuda_host_alloc (page-locked, from the cache above): a frame rendered into one of them is written
+// by the GPU's copy engine directly — no staging buffer, no host memcpy, and no first-touch page faults in a freshly
+// allocated frame (a new 25 MB pageable plane costs ~2.5 ms of faults and zeroing per 1080p call).
+struct HostAllocs {
+    std::mutex mu;
+    std::map<uintptr_t, size_t> live;   // base -> bytes
+    void add(void* p, size_t bytes) { std::lock_guard<std::mutex> g(mu); live[(uintptr_t)p] = bytes; }
+    size_t take(void* p) {
+        std::lock_guard<std::mutex> g(mu);
+        auto it = live.find((uintptr_t)p);
+        if (it == live.end()) return 0;
+        const size_t b = it->second;
+        live.erase(it);
+        return b;
+    }
+    bool covers(const void* p, size_t bytes) {
+        std::lock_guard<std::mutex> g(mu);
+        auto it = live.upper_bound((uintptr_t)p);
+        if (it == live.begin()) return false;
+        --it;
+        return (uintptr_t)p + bytes <= it->first + it->second;
+    }
+};
+static HostAllocs g_host_allocs;
+
 // dst <- src on up to `max_threads` host threads (a 25 MB frame: ~2.5 ms on one core)
 static void parallel_memcpy(void* dst, const void* src, size_t bytes, unsigned max_threads = 4) {
     const size_t chunk = 4u << 20;
@@ -291,7 +324,7 @@ struct rtcuda_scene {
     // ... and, in each sub-scene, what the exchange of owned pixels needs (multi_* functions below): the packed planes of this
     // rank's pixels on its GPU, their pinned host mirror, the host copy of the pixel list; on rank 0 also the other ranks'
     // pixel lists and a receive buffer per rank (plain cudaMalloc: peer-accessible once peer access is enabled).
-    uint32_t* packed = nullptr; size_t packed_words = 0;
+    uint32_t* packed = nullptr; size_t packed_words = 0; bool packed_plain = false;
     uint32_t* h_packed = nullptr; size_t h_packed_words = 0;
     std::vector<TileRec> host_tiles;   // the tiles this context owns (build_pixel_list), also on the device:
     DevBuf<TileRec> tiles;
@@ -337,7 +370,7 @@ struct rtcuda_scene {
     ~rtcuda_scene() {
         if (frame_exec) cudaGraphExecDestroy(frame_exec);
         for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
-        if (packed) cudaFreeAsync(packed, tls_stream);   // (the releasing thread has entered this scene's context)
+        if (packed) { if (packed_plain) cudaFree(packed); else cudaFreeAsync(packed, tls_stream); }   // (the releasing thread has entered this scene's context)
         if (h_packed) g_pinned_cache.park(h_packed, h_packed_words * 4);
         for (TileRec* q : peer_list) if (q) cudaFree(q);
         for (uint32_t* q : peer_recv) if (q) cudaFree(q);
@@ -551,7 +584,7 @@ void build_bvh(rtcuda_scene* s, const std::vector<Instance>& instances, uint32_t
     const uint32_t n = n_prims;
     DevBuf<Prim> prims_unsorted;
     DevBuf<float4> aabb_lo, aabb_hi, node_lo, node_hi;
-    DevBuf<uint32_t> bounds_keys, vals, vals_sorted, left, right, parent, count, visit, counters, cl_a, cl_b, nn, ploc_out, ploc_state;
+    DevBuf<uint32_t> bounds_keys, vals, vals_sorted, left, right, parent, count, visit, counters, cl_a, cl_b, nn, ploc_out, ploc_state, level_count;
     DevBuf<uint64_t> keys, keys_sorted, scan;
     DevBuf<WorkItem> queue_a, queue_b;
     DevBuf<uint8_t> sort_temp, scan_temp;
@@ -637,20 +670,36 @@ void build_bvh(rtcuda_scene* s, const std::vector<Instance>& instances, uint32_t
     bool too_deep = false;
     WorkItem* qin = queue_a.p;
     WorkItem* qout = queue_b.p;
+    // item counts per level live on the device (level_count[L]); the host queues up to 4 levels per read-back, each launch sized
+    // for an upper bound of its level (8^L items, never more than n)
+    constexpr uint32_t MAX_LEVELS = (uint32_t)(TRAVERSE_STACK / 2 - 1);
+    level_count.alloc(MAX_LEVELS + 8);
+    CK(cudaMemsetAsync(level_count.p, 0, (MAX_LEVELS + 8) * 4, st));
+    const uint32_t one = 1;
+    CK(cudaMemcpyAsync(level_count.p, &one, 4, cudaMemcpyHostToDevice, st));
+    uint64_t bound = 1;
     while (n_items) {
-        // a ray holds at most two stack entries per level of the wide tree (the rest of a node group and a postponed
-        // primitive group, rt_traverse.h): deeper trees than the traversal stack covers are refused, not overrun
-        if (++n_levels > (uint32_t)(TRAVERSE_STACK / 2 - 1)) { too_deep = true; break; }
-        b.queue_in = qin;
-        b.queue_out = qout;
-        launch_collapse(st, b, n_items, s->lc);
-        CK(cudaMemcpyAsync(h_counters, counters.p, sizeof h_counters, cudaMemcpyDeviceToHost, st));
+        uint32_t queued = 0;
+        for (; queued < 4; queued++) {
+            // a ray holds at most two stack entries per level of the wide tree (the rest of a node group and a postponed
+            // primitive group, rt_traverse.h): deeper trees than the traversal stack covers are refused, not overrun
+            if (n_levels + queued + 1 > MAX_LEVELS) break;
+            b.queue_in = qin;
+            b.queue_out = qout;
+            launch_collapse(st, b, (uint32_t)std::min<uint64_t>(bound, n), level_count.p + n_levels + queued, s->lc);
+            bound = std::min<uint64_t>(bound * 8, n);
+            std::swap(qin, qout);
+        }
+        if (!queued) { too_deep = true; break; }
+        uint32_t h_levels[5] = {0, 0, 0, 0, 0};   // counts of the levels just run ([0]) .. of the level after them ([queued])
+        CK(cudaMemcpyAsync(h_levels, level_count.p + n_levels, (queued + 1) * 4, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
-        n_items = h_counters[0];
-        const uint32_t zero = 0;
-        CK(cudaMemcpyAsync(counters.p, &zero, 4, cudaMemcpyHostToDevice, st));
-        std::swap(qin, qout);
+        n_items = h_levels[queued];
+        for (uint32_t k = 1; k <= queued; k++) if (h_levels[k] == 0) { n_items = 0; queued = k; break; }   // levels past the last one ran empty
+        n_levels += queued;
     }
+    CK(cudaMemcpyAsync(h_counters, counters.p, sizeof h_counters, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     if (!use_lbvh && std::getenv("RTCUDA_TEST_PLOC_TOO_DEEP")) too_deep = true;   // test hook for the fallback below
     if (!too_deep) break;
     if (use_lbvh) throw RtError{RTCUDA_ERR_UNSUPPORTED, "wide BVH deeper than the traversal stack allows (degenerate primitive distribution)"};
@@ -708,8 +757,17 @@ void upload_scene(rtcuda_scene* s, const rtcuda_scene_desc* d, const GeoShare* s
     for (const rtcuda_shape& a : rs) own_arrays |= a.kind == RTCUDA_SHAPE_TRIANGLE_MESH && a.vertices != nullptr;
     struct Piece { int which; size_t dst_off; const void* src; size_t bytes; };   // which: 0 vertices, 1 tris, 2 normals, 3 uvs (byte offsets)
     std::vector<Piece> pieces;
+    constexpr size_t SHARE_MIN = 4u << 20;   // smaller arrays: every GPU reads the host copy itself
+    const bool sharing = share && share->world > 1;
+    // arrays that hold a piece the GPUs pass between them live in plain (peer-mapped) allocations
+    auto geo_alloc = [&](auto& buf, size_t count, size_t elem_bytes, size_t largest_piece_bytes) {
+        (void)elem_bytes;
+        buf.peer_visible = sharing && largest_piece_bytes >= SHARE_MIN;
+        buf.alloc(count);
+    };
     if (!own_arrays) {
-        s->vertices.alloc(d->vertex_count * 3); s->tris.alloc(d->tri_count * 3); s->normals.alloc(d->normal_count * 3); s->uvs.alloc(d->uv_count * 2);
+        geo_alloc(s->vertices, d->vertex_count * 3, 4, d->vertex_count * 12); geo_alloc(s->tris, d->tri_count * 3, 4, d->tri_count * 12);
+        geo_alloc(s->normals, d->normal_count * 3, 4, d->normal_count * 12); geo_alloc(s->uvs, d->uv_count * 2, 4, d->uv_count * 8);
         pieces.push_back({0, 0, d->vertices, d->vertex_count * 12});
         pieces.push_back({1, 0, d->tris, d->tri_count * 12});
         pieces.push_back({2, 0, d->normals, d->normal_count * 12});
@@ -726,7 +784,14 @@ void upload_scene(rtcuda_scene* s, const rtcuda_scene_desc* d, const GeoShare* s
             if (a.uvs) nuv += a.vertex_count;
             REQUIRE(nv < 0xffffffffull && nt < 0xffffffffull, "too many vertices / triangles");
         }
-        s->vertices.alloc(nv * 3); s->tris.alloc(nt * 3); s->normals.alloc(nn * 3); s->uvs.alloc(nuv * 2);
+        size_t big_v = 0, big_t = 0, big_n = 0, big_uv = 0;   // the largest piece of each array
+        for (const rtcuda_shape& a : rs) {
+            if (a.kind != RTCUDA_SHAPE_TRIANGLE_MESH) continue;
+            big_v = std::max<size_t>(big_v, (size_t)a.vertex_count * 12); big_t = std::max<size_t>(big_t, (size_t)a.tri_count * 12);
+            if (a.normals) big_n = std::max<size_t>(big_n, (size_t)a.vertex_count * 12);
+            if (a.uvs) big_uv = std::max<size_t>(big_uv, (size_t)a.vertex_count * 8);
+        }
+        geo_alloc(s->vertices, nv * 3, 4, big_v); geo_alloc(s->tris, nt * 3, 4, big_t); geo_alloc(s->normals, nn * 3, 4, big_n); geo_alloc(s->uvs, nuv * 2, 4, big_uv);
         for (const rtcuda_shape& a : rs) {
             if (a.kind != RTCUDA_SHAPE_TRIANGLE_MESH) continue;
             pieces.push_back({0, (size_t)a.vertex_offset * 12, a.vertices, (size_t)a.vertex_count * 12});
@@ -739,12 +804,11 @@ void upload_scene(rtcuda_scene* s, const rtcuda_scene_desc* d, const GeoShare* s
         auto base_of = [](rtcuda_scene* q, int which) -> uint8_t* {
             return which == 0 ? (uint8_t*)q->vertices.p : which == 1 ? (uint8_t*)q->tris.p : which == 2 ? (uint8_t*)q->normals.p : (uint8_t*)q->uvs.p;
         };
-        const bool shared = share && share->world > 1;
+        const bool shared = sharing;
         if (shared) {   // every GPU's arrays must exist before anybody writes into them
             CK(cudaStreamSynchronize(st));
             if (!share->meet->wait()) throw RtError{RTCUDA_ERR_CUDA, "another device failed during the upload"};
         }
-        constexpr size_t SHARE_MIN = 4u << 20;   // smaller arrays: every GPU reads the host copy itself
         for (const Piece& pc : pieces) {
             if (!pc.bytes) continue;
             if (!shared || pc.bytes < SHARE_MIN) {
@@ -1325,14 +1389,19 @@ void render_host(rtcuda_scene* s, const rtcuda_settings* settings, rtcuda_output
         CK(cudaStreamSynchronize(st));
         return;
     }
+    std::vector<char> direct(copies.size(), 0);   // planes from rtcuda_host_alloc: the copy engine writes them itself
+    for (size_t i = 0; i < copies.size(); i++) direct[i] = g_host_allocs.covers(copies[i].host, copies[i].bytes) ? 1 : 0;
     try {
-        for (const Copy& c : copies) CK(cudaMemcpyAsync(stage + c.off, c.devp, c.bytes, cudaMemcpyDeviceToHost, st));
+        for (size_t i = 0; i < copies.size(); i++) {
+            const Copy& c = copies[i];
+            CK(cudaMemcpyAsync(direct[i] ? c.host : (void*)(stage + c.off), c.devp, c.bytes, cudaMemcpyDeviceToHost, st));
+        }
         CK(cudaStreamSynchronize(st));
     } catch (...) {
         g_pinned_cache.park(stage, got);
         throw;
     }
-    for (const Copy& c : copies) parallel_memcpy(c.host, stage + c.off, c.bytes);
+    for (size_t i = 0; i < copies.size(); i++) if (!direct[i]) parallel_memcpy(copies[i].host, stage + copies[i].off, copies[i].bytes);
     g_pinned_cache.park(stage, got);
 }
 
@@ -1425,14 +1494,18 @@ void multi_upload(rtcuda_ctx* ctx, const rtcuda_scene_desc* desc, rtcuda_scene* 
 }
 
 void multi_release(rtcuda_scene* parent) {
+    // one host thread per GPU, like every other multi-device call (the ~40 stream-ordered frees of a sub-scene are host work)
+    std::vector<std::thread> threads;
     for (rtcuda_scene* sub : parent->subs) {
         if (!sub) continue;
-        cudaSetDevice(sub->ctx->device);
-        tls_stream = sub->ctx->stream;
-        cudaStreamSynchronize(tls_stream);
-        delete sub;
-        cudaStreamSynchronize(tls_stream);
+        threads.emplace_back([sub] {
+            cudaSetDevice(sub->ctx->device);
+            tls_stream = sub->ctx->stream;
+            cudaStreamSynchronize(tls_stream);   // the parked path-state arena may be picked up by another stream next
+            delete sub;
+        });
     }
+    for (std::thread& t : threads) t.join();
     parent->subs.clear();
 }
 
@@ -1464,17 +1537,19 @@ rtcuda_outputs staging_planes(rtcuda_scene* s, uint32_t o, const rtcuda_outputs&
 }
 
 // Gather this GPU's owned pixels of every requested plane into its packed buffer (plane after plane); returns the words used.
-size_t pack_owned(rtcuda_scene* sub, const PlaneSlot planes[N_PLANES]) {
+size_t pack_owned(rtcuda_scene* sub, const PlaneSlot planes[N_PLANES], bool peer_visible) {
     cudaStream_t st = sub->ctx->stream;
     const uint32_t np = sub->n_my_pixels;
     size_t words = 0;
     for (int i = 0; i < N_PLANES; i++) if (planes[i].ptr) words += (size_t)np * planes[i].ch;
-    if (words > sub->packed_words) {
-        // from the stream-ordered pool (peer-accessible like the geometry arrays; a plain cudaMalloc / cudaFree pair costs
-        // milliseconds per one-shot render once peer mappings exist)
-        if (sub->packed) CK(cudaFreeAsync(sub->packed, st));
+    if (words > sub->packed_words || (peer_visible && !sub->packed_plain)) {
+        // host frames: from the stream-ordered pool (a plain cudaMalloc / cudaFree pair costs milliseconds per one-shot render
+        // once peer mappings exist); device planes: a plain allocation, which GPU 0 can be sent from (kept across frames)
+        if (sub->packed) { if (sub->packed_plain) { CK(cudaStreamSynchronize(st)); cudaFree(sub->packed); } else CK(cudaFreeAsync(sub->packed, st)); }
         sub->packed = nullptr; sub->packed_words = 0;
-        CK(cudaMallocAsync((void**)&sub->packed, words * 4, st));
+        if (peer_visible) CK(cudaMalloc((void**)&sub->packed, words * 4));
+        else CK(cudaMallocAsync((void**)&sub->packed, words * 4, st));
+        sub->packed_plain = peer_visible;
         sub->packed_words = words;
     }
     size_t off = 0;
@@ -1503,7 +1578,7 @@ void multi_render_host(rtcuda_scene* parent, const rtcuda_settings* settings, rt
         PlaneSlot dp[N_PLANES], hp[N_PLANES];
         planes_of(dev, o, dp);
         planes_of(*out, o, hp);
-        const size_t words = pack_owned(sub, dp);
+        const size_t words = pack_owned(sub, dp, false);
         if (!words) return;
         if (words > sub->h_packed_words) {
             if (sub->h_packed) g_pinned_cache.park(sub->h_packed, sub->h_packed_words * 4);
@@ -1568,7 +1643,7 @@ void multi_render_device(rtcuda_scene* parent, const rtcuda_settings* settings, 
         render_device(sub, settings, &dev, sample_lo, sample_hi, false);
         PlaneSlot dp[N_PLANES];
         planes_of(dev, o, dp);
-        const size_t words = pack_owned(sub, dp);
+        const size_t words = pack_owned(sub, dp, true);
         sent_words[r] = words;
         if (!words) return;
         if (words > first->peer_recv_words[r]) {   // receive buffer of rank r on GPU 0 (slot r is only ever touched by this thread)
@@ -1714,14 +1789,12 @@ RTCUDA_API rtcuda_status rtcuda_init(const rtcuda_backend_settings* settings, rt
             parent->subs.push_back(make_device_ctx(bs, count));
         }
         // NVLink peer access in both directions between every pair (geometry slices are forwarded all-to-all, owned pixels go to
-        // GPU 0), for plain allocations and for the stream-ordered pools the scene arrays come from
+        // GPU 0): what the GPUs pass between them lives in plain allocations
         static std::mutex peer_mu;
         static uint64_t peer_done[64] = {0};   // per process: pairs already set up (the calls below cost milliseconds each)
         std::lock_guard<std::mutex> peer_lock(peer_mu);
         for (uint32_t i = 0; i < n; i++) {
             CK(cudaSetDevice(settings->device_ids[i]));
-            cudaMemPool_t pool;
-            CK(cudaDeviceGetDefaultMemPool(&pool, settings->device_ids[i]));
             for (uint32_t j = 0; j < n; j++) {
                 if (settings->device_ids[i] == settings->device_ids[j]) continue;
                 const int di = settings->device_ids[i] & 63, dj = settings->device_ids[j] & 63;
@@ -1732,12 +1805,7 @@ RTCUDA_API rtcuda_status rtcuda_init(const rtcuda_backend_settings* settings, rt
                 if (!can) continue;   // copies between the two then go through the host (still correct)
                 const cudaError_t pe = cudaDeviceEnablePeerAccess(settings->device_ids[j], 0);
                 if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) CK(pe);
-                cudaGetLastError();
-                cudaMemAccessDesc desc{};
-                desc.location.type = cudaMemLocationTypeDevice;
-                desc.location.id = settings->device_ids[j];
-                desc.flags = cudaMemAccessFlagsProtReadWrite;
-                CK(cudaMemPoolSetAccess(pool, &desc, 1));   // device j may access device i's pool memory
+                cudaGetLastError();   // (plain allocations only: the pools stay private to their device, see DevBuf::peer_visible)
             }
         }
         *out_ctx = parent.release();
@@ -1784,6 +1852,20 @@ RTCUDA_API void rtcuda_release_cached_memory(void) {
     }
     cudaSetDevice(cur);
     cudaGetLastError();
+}
+
+RTCUDA_API void* rtcuda_host_alloc(size_t bytes) {
+    if (!bytes) return nullptr;
+    size_t got = 0;
+    void* p = g_pinned_cache.take(bytes, got);
+    if (p) g_host_allocs.add(p, got);
+    return p;
+}
+
+RTCUDA_API void rtcuda_host_free(void* p) {
+    if (!p) return;
+    const size_t bytes = g_host_allocs.take(p);
+    if (bytes) g_pinned_cache.park(p, bytes);
 }
 
 RTCUDA_API void rtcuda_scene_release(rtcuda_scene* scene) {

@@ -506,18 +506,25 @@ __global__ void __launch_bounds__(BLOCK) k_ploc_merge(BuildCtx b, const uint32_t
     ploc_merge_body(i, b);
     if (i == b.m - 1) { st_next[0] = b.ploc_out[0]; st_next[1] = b.next_node - b.ploc_out[1]; }   // (ploc_out: written by this thread just now)
 }
-__global__ void __launch_bounds__(128) k_collapse(BuildCtx b, uint32_t n_items) {
+// One wide level per launch. The level's item count is read from the device (`level[0]`), the launch is sized for an upper
+// bound; a one-thread kernel then moves the next level's count (counters[0], summed by the bodies) into `level[1]`: the host
+// queues several levels before it reads a count back (one round trip per level was a quarter of a small scene's build time).
+__global__ void __launch_bounds__(128) k_collapse(BuildCtx b, const uint32_t* level) {
     const uint32_t i = blockIdx.x * 128 + threadIdx.x;
-    if (i < n_items) collapse_body(i, b);
+    if (i < level[0]) collapse_body(i, b);
 }
-
+__global__ void k_collapse_next(uint32_t* counters, uint32_t* level) {
+    level[1] = counters[0];
+    counters[0] = 0u;
+}
 void launch_prim_setup(cudaStream_t st, const BuildCtx& b, LaunchCounter& lc) { k_prim_setup<<<grid_for(b.n), BLOCK, 0, st>>>(b); lc.launches++; }
 void launch_morton(cudaStream_t st, const BuildCtx& b, LaunchCounter& lc) { k_morton<<<grid_for(b.n), BLOCK, 0, st>>>(b); lc.launches++; }
 void launch_karras(cudaStream_t st, const BuildCtx& b, LaunchCounter& lc) { if (b.n > 1) { k_karras<<<grid_for(b.n - 1), BLOCK, 0, st>>>(b); lc.launches++; } }
 void launch_refit(cudaStream_t st, const BuildCtx& b, LaunchCounter& lc) { k_refit<<<grid_for(b.n), BLOCK, 0, st>>>(b); lc.launches++; }
-void launch_collapse(cudaStream_t st, const BuildCtx& b, uint32_t n_items, LaunchCounter& lc) {
-    k_collapse<<<grid_for(n_items, 128), 128, 0, st>>>(b, n_items);
-    lc.launches++;
+void launch_collapse(cudaStream_t st, const BuildCtx& b, uint32_t bound, uint32_t* level, LaunchCounter& lc) {
+    k_collapse<<<grid_for(bound, 128), 128, 0, st>>>(b, level);
+    k_collapse_next<<<1, 1, 0, st>>>(b.counters, level);
+    lc.launches += 2;
 }
 
 void launch_ploc_init(cudaStream_t st, const BuildCtx& b, LaunchCounter& lc) { k_ploc_init<<<grid_for(b.n), BLOCK, 0, st>>>(b); lc.launches++; }

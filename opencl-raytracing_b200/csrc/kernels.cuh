@@ -42,7 +42,7 @@ void launch_sort(cudaStream_t st, void* temp, size_t temp_bytes, const uint64_t*
                  uint32_t* vals_out, uint32_t n, LaunchCounter& lc);
 void launch_karras(cudaStream_t st, const BuildCtx& b, LaunchCounter& lc);
 void launch_refit(cudaStream_t st, const BuildCtx& b, LaunchCounter& lc);
-void launch_collapse(cudaStream_t st, const BuildCtx& b, uint32_t n_items, LaunchCounter& lc);
+void launch_collapse(cudaStream_t st, const BuildCtx& b, uint32_t bound, uint32_t* level, LaunchCounter& lc);
 void launch_ploc_init(cudaStream_t st, const BuildCtx& b, LaunchCounter& lc);
 size_t ploc_scan_temp_bytes(uint32_t n);
 // one PLOC round: nearest neighbours, merge flags, exclusive scan (CUB), merged nodes + compacted cluster list

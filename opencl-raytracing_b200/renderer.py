@@ -95,12 +95,16 @@ class RenderOutput:
                ("debug_depth", AovFlags.DEBUG_DEPTH, 1, np.float32))
 
     @classmethod
-    def allocate(cls, width: int, height: int, outputs: AovFlags) -> "RenderOutput":
+    def allocate(cls, width: int, height: int, outputs: AovFlags, lib=None) -> "RenderOutput":
+        """The planes the backend fills. With `lib` (the loaded library) they are page-locked buffers from rtcuda_host_alloc, which
+        the GPU writes without a staging copy and which go back to the library's cache when the arrays are garbage-collected;
+        without it, plain numpy arrays (zero-filled)."""
         out = cls(width, height)
         for name, flag, ch, dt in cls._PLANES:
             if outputs & flag:
                 shape = (height, width, ch) if ch > 1 else (height, width)
-                setattr(out, name, np.zeros(shape, dtype=dt))
+                arr = _ffi.host_array(lib, shape, dt) if lib is not None else None
+                setattr(out, name, arr if arr is not None else np.zeros(shape, dtype=dt))
         return out
 
     def to_c(self) -> _ffi.Outputs:

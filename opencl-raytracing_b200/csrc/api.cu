@@ -82,6 +82,50 @@ struct Trace {
     }
 };
 
+// Plain (peer-mapped) device allocations released by a scene, parked per process like the path-state arenas: with peer
+// access enabled between 8 GPUs a cudaMalloc / cudaFree pair of a 200 MB array costs ~10 ms (every allocation is mapped into
+// seven other address spaces), which a one-shot render of a large mesh paid four times per GPU (C5 at 8 GPUs: upload + build
+// 40 -> 69 ms, release 1 -> 22 ms, profiles/r4o). At most PLAIN_KEEP buffers per device stay parked.
+struct PlainCache {
+    struct Slot { int device; void* p; size_t bytes; };
+    static constexpr size_t PLAIN_KEEP = 8;
+    std::mutex mu;
+    std::vector<Slot> parked;
+    void* take(int device, size_t need, size_t& got) {   // best fit that wastes at most half of the block
+        std::lock_guard<std::mutex> g(mu);
+        int best = -1;
+        for (int i = 0; i < (int)parked.size(); i++)
+            if (parked[i].device == device && parked[i].bytes >= need && parked[i].bytes <= 2 * need + (1u << 20) &&
+                (best < 0 || parked[i].bytes < parked[best].bytes)) best = i;
+        if (best < 0) return nullptr;
+        Slot sl = parked[best];
+        parked.erase(parked.begin() + best);
+        got = sl.bytes;
+        return sl.p;
+    }
+    void park(int device, void* p, size_t bytes) {
+        void* evict = nullptr;
+        {
+            std::lock_guard<std::mutex> g(mu);
+            parked.push_back({device, p, bytes});
+            size_t mine = 0;
+            int oldest = -1;
+            for (int i = 0; i < (int)parked.size(); i++) if (parked[i].device == device) { if (oldest < 0) oldest = i; mine++; }
+            if (mine > PLAIN_KEEP) { evict = parked[oldest].p; parked.erase(parked.begin() + oldest); }
+        }
+        if (evict) cudaFree(evict);   // (the calling thread has `device` current)
+    }
+    void release_all() {
+        std::lock_guard<std::mutex> g(mu);
+        int cur = 0;
+        cudaGetDevice(&cur);
+        for (const Slot& sl : parked) { cudaSetDevice(sl.device); cudaFree(sl.p); }
+        cudaSetDevice(cur);
+        parked.clear();
+    }
+};
+static PlainCache g_plain_cache;
+
 template <typename T>
 struct DevBuf {
     T* p = nullptr;
@@ -91,12 +135,17 @@ struct DevBuf {
     // with peer access granted on the pools (cudaMemPoolSetAccess) cudaMallocAsync failed with "out of memory" on boxes with
     // 150 GB free when several host threads grew peer-mapped pools at once (2-GPU test box, 8-GPU bench box, round 2).
     bool peer_visible = false, is_plain = false;
+    size_t plain_bytes = 0;
+    int plain_device = 0;
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
     ~DevBuf() { release(); }
     void release() {
-        if (p) { if (is_plain) cudaFree(p); else cudaFreeAsync(p, tls_stream); }
+        if (p) {
+            if (is_plain) { cudaStreamSynchronize(tls_stream); g_plain_cache.park(plain_device, p, plain_bytes); }   // (no work of this stream may still touch it)
+            else cudaFreeAsync(p, tls_stream);
+        }
         p = nullptr;
         n = 0;
     }
@@ -104,8 +153,13 @@ struct DevBuf {
         release();
         n = count;
         is_plain = peer_visible;
-        if (is_plain) CK(cudaMalloc((void**)&p, std::max<size_t>(count, 1) * sizeof(T)));
-        else CK(cudaMallocAsync((void**)&p, std::max<size_t>(count, 1) * sizeof(T), tls_stream));
+        const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+        if (is_plain) {
+            cudaGetDevice(&plain_device);
+            void* q = g_plain_cache.take(plain_device, bytes, plain_bytes);
+            if (!q) { CK(cudaMalloc(&q, bytes)); plain_bytes = bytes; }
+            p = (T*)q;
+        } else CK(cudaMallocAsync((void**)&p, bytes, tls_stream));
     }
     void ensure(size_t count) {
         if (count > n || !p) alloc(count);
@@ -1839,6 +1893,7 @@ RTCUDA_API rtcuda_status rtcuda_scene_upload(rtcuda_ctx* ctx, const rtcuda_scene
 
 RTCUDA_API void rtcuda_release_cached_memory(void) {
     g_arena_cache.release_all();
+    g_plain_cache.release_all();
     g_pinned_cache.release_all();
     int cur = 0, count = 0;
     if (cudaGetDevice(&cur) != cudaSuccess || cudaGetDeviceCount(&count) != cudaSuccess) return;

@@ -120,6 +120,9 @@ constexpr int TRI_MIN = RT_TRI_MIN;
 // Resident blocks per SM asked of the any-hit kernel: 5 (48 registers, ~76 B of spills) hides more of its load latency than the 4
 // that 64 registers allow — k_shadow 174 -> 168 ms on C3; the closest-hit kernel carries more state and lost 1 % (A/B in
 // profiles/r1_notes.md), so it keeps the register count it wants.
+#ifndef RT_SHADOW_PARALLEL_LOADS
+#define RT_SHADOW_PARALLEL_LOADS 0
+#endif
 #ifndef SHADOW_BLOCKS
 #define SHADOW_BLOCKS 5
 #endif
@@ -197,7 +200,7 @@ __global__ void __launch_bounds__(BLOCK, 4) k_extend(const __grid_constant__ Sce
 // profiles/r1_notes.md). Per chunk ONE warp scan hands out the positions of all three outputs — continuation
 // rays, NEE vertices, shadow rays (a variable number per thread, consecutive per vertex) — and the last lane issues
 // the warp's two global atomics (one per queue counter; the 64-bit one carries vertices | shadow rays << 32).
-template <typename Surf>
+template <typename Surf, bool SHARED_STAGE_ONLY>
 __global__ void __launch_bounds__(SHADE_THREADS, std::is_same<Surf, DiffuseSurface>::value ? SHADE_BLOCKS : 512 / SHADE_THREADS) k_shade(const __grid_constant__ SceneD sc, const __grid_constant__ RenderParams rp,
                                                   const __grid_constant__ Wave w) {
     const uint32_t n = *w.n_in;
@@ -221,7 +224,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, std::is_same<Surf, DiffuseSurfa
         unsigned long long base1 = 0;   // lane 31: vertices | shadow rays << 32 before this warp's
         uint32_t base0 = 0, incl = 0;    // lane 31: rays before this warp's; inclusive scan of the shadow-ray counts
         unsigned mc = 0, mv = 0;
-        shade_vertex<Surf>(q < n, q, sc, rp, w,
+        shade_vertex<Surf, SHARED_STAGE_ONLY>(q < n, q, sc, rp, w,
             [&](bool cont, bool has_vertex, uint32_t k, bool final_skipped, uint32_t& rpos, uint32_t& vpos, uint32_t& first) {
                 (void)has_vertex; (void)rpos;
                 mc = __ballot_sync(FULL, cont);
@@ -286,10 +289,18 @@ __global__ void __launch_bounds__(BLOCK, SHADOW_BLOCKS) k_shadow(const __grid_co
                 if (mine < n) {
                     q = mine;
                     const float4 o4 = w.sray_o[q], d4 = w.sray_d[q];
+#if RT_SHADOW_PARALLEL_LOADS
+                    // both halves of the entry are loaded before either is looked at (testing t_max first makes the direction a
+                    // second, dependent round trip)
+                    const uint32_t traced = o4.w >= 0.0f ? 1u : 0u;
+                    n_rays += traced;
+                    have = tr.init(sc, xyz(o4), xyz(d4), 0.001f, o4.w) ? traced : 0u;
+#else
                     if (o4.w >= 0.0f) {   // negative: never occluded (non-finite origin quirk), not traced
                         n_rays++;
                         have = tr.init(sc, xyz(o4), xyz(d4), 0.001f, o4.w) ? 1u : 0u;
                     }
+#endif
                 }
             }
             if (base + (uint32_t)cnt >= n) exhausted = 1u;
@@ -360,8 +371,13 @@ void launch_extend(cudaStream_t st, const SceneD& sc, const Wave& w, uint32_t n_
     lc.launches++;
 }
 void launch_shade(cudaStream_t st, const SceneD& sc, const RenderParams& rp, const Wave& w, uint32_t n_max, LaunchCounter& lc) {
-    if (sc.all_diffuse) k_shade<DiffuseSurface><<<persistent_grid((const void*)k_shade<DiffuseSurface>, n_max, SHADE_THREADS), SHADE_THREADS, 0, st>>>(sc, rp, w);
-    else k_shade<Surface><<<persistent_grid((const void*)k_shade<Surface>, n_max, SHADE_THREADS), SHADE_THREADS, 0, st>>>(sc, rp, w);
+    // launches whose light samples per vertex fit the shared-memory staging column take the instantiation without the thread-local one
+    const bool smem_only = RT_NEE_SMEM > 0 && w.shadow_k <= NEE_SMEM;
+    auto go = [&](auto kernel) { kernel<<<persistent_grid((const void*)kernel, n_max, SHADE_THREADS), SHADE_THREADS, 0, st>>>(sc, rp, w); };
+    // (Diffuse-only scenes: C4's shade 60.3 -> 55.6 ms; the general instantiation lost 2.5 ms of 38.5 on CM with it and keeps both
+    // stages — profiles/r4p_ab.log)
+    if (sc.all_diffuse) { if (smem_only) go(k_shade<DiffuseSurface, true>); else go(k_shade<DiffuseSurface, false>); }
+    else go(k_shade<Surface, false>);
     lc.launches++;
 }
 void launch_shadow(cudaStream_t st, const SceneD& sc, const Wave& w, uint32_t n_max, uint32_t* fetch_counter, bool stats, LaunchCounter& lc) {

@@ -525,21 +525,27 @@ RT_HD uint32_t nee_pass(const SceneD& sc, const RenderParams& rp, const Wave& w,
 //   late(&ray_pos)                         ... until after the shadow entries have been copied out.
 // All three are warp-collective: every thread of the launch calls each of them exactly once per chunk. The CPU harness passes
 // `alloc` only.
-template <typename Surf, typename Alloc, typename Early, typename Late>
+// SHARED_STAGE_ONLY: the caller guarantees that every vertex's entries fit the shared-memory column it passes (the kernel is
+// instantiated that way for launches with shadow_k <= NEE_SMEM): no thread-local staging array exists in that instantiation, and
+// the staging accesses are shared-memory instructions instead of generic ones.
+template <typename Surf, bool SHARED_STAGE_ONLY = false, typename Alloc, typename Early, typename Late>
 RT_HD void shade_vertex(bool active, uint32_t q, const SceneD& sc, const RenderParams& rp, const Wave& w, Alloc&& alloc, StagePtr shared_stage, Early&& early,
                         Late&& late) {
     ShadeState<Surf> S;
     Sampler s2;
     BsdfSample bs;
-    NeeStage local_stage;
+    typename std::conditional<SHARED_STAGE_ONLY, char, NeeStage>::type local_stage;
     uint32_t k = 0;
     bool alive = false, final_skipped = false;
     V3 nd = mk3(0.0f);
     // few light samples per vertex (the usual case): one evaluation, entries staged (shared memory when the kernel offers a
     // column that holds them, else thread-local memory) until their queue position is known; otherwise count first and
     // evaluate again when writing
-    const bool staged = w.shadow_k <= NEE_STAGE;
-    const StagePtr stage = (shared_stage.p && w.shadow_k <= shared_stage.capacity) ? shared_stage : StagePtr{local_stage.e, 1u, NEE_STAGE};
+    const bool staged = SHARED_STAGE_ONLY || w.shadow_k <= NEE_STAGE;
+    StagePtr stage = shared_stage;
+    if constexpr (!SHARED_STAGE_ONLY) {
+        if (!(shared_stage.p && w.shadow_k <= shared_stage.capacity)) stage = StagePtr{local_stage.e, 1u, NEE_STAGE};
+    } else (void)local_stage;
     if (active) active = shade_begin(q, sc, rp, w, S);
     if (active) {
         s2 = S.s;
@@ -597,7 +603,7 @@ RT_HD void shade_vertex(bool active, uint32_t q, const SceneD& sc, const RenderP
 
 template <typename Surf, typename Alloc>
 RT_HD void shade_vertex(bool active, uint32_t q, const SceneD& sc, const RenderParams& rp, const Wave& w, Alloc&& alloc, StagePtr shared_stage = StagePtr{nullptr, 0u, 0u}) {
-    shade_vertex<Surf>(active, q, sc, rp, w, alloc, shared_stage, [](bool, uint32_t) {}, [](uint32_t&) {});
+    shade_vertex<Surf, false>(active, q, sc, rp, w, alloc, shared_stage, [](bool, uint32_t) {}, [](uint32_t&) {});
 }
 
 // ---- shadow gather: add the unoccluded contributions of one NEE vertex to its path, in light-sample order ----

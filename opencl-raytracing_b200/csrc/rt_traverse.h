@@ -104,9 +104,18 @@ RT_HD bool triangle_watertight(V3 p0, V3 p1, V3 p2, V3 o, V3 d, float t_min, flo
     return true;
 }
 
+#ifndef RT_FAST_RCP
+#define RT_FAST_RCP 0   // 1: bare MUFU.RCP for 1 / direction (A/B switch; only the conservative box culling reads it)
+#endif
 RT_HD float safe_rcp_dir(float d) {
     float a = fabsf(d) > 1.0e-20f ? d : copysignf(1.0e-20f, d);
+#if defined(__CUDA_ARCH__) && RT_FAST_RCP
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+    return r;
+#else
     return 1.0f / a;
+#endif
 }
 
 // Quantised plane byte K of word w as the float 1 + q * 2^-15 (q in mantissa bits 8..15): one PRMT on the

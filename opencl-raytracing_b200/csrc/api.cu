@@ -699,6 +699,16 @@ void build_bvh(rtcuda_scene* s, const std::vector<Instance>& instances, uint32_t
         CK(cudaMemcpyAsync(ploc_state.p, h_state, sizeof h_state, cudaMemcpyHostToDevice, st));
         uint32_t flip = 0;
         while (b.m > 1) {
+            if (b.m <= PLOC_TAIL_MAX && !std::getenv("RTCUDA_NO_PLOC_TAIL")) {   // (the variable is an A/B aid)
+                // few clusters left: one block runs all remaining rounds in a single launch
+                launch_ploc_tail(st, b, ploc_state.p + 2 * flip, ploc_state.p + 2 * (flip ^ 1u), cl_a.p, cl_b.p, cin == cl_a.p, s->lc);
+                flip ^= 1u;
+                CK(cudaMemcpyAsync(h_state, ploc_state.p + 2 * flip, sizeof h_state, cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                if (h_state[0] != 1u) throw RtError{RTCUDA_ERR_CUDA, "PLOC tail did not finish"};
+                b.m = h_state[0]; b.next_node = h_state[1];
+                break;
+            }
             const uint32_t batch = b.m > (1u << 20) ? 1u : (b.m > (1u << 16) ? 4u : 8u), bound = b.m;
             for (uint32_t r = 0; r < batch; r++) {
                 b.cl_in = cin; b.cl_out = cout;

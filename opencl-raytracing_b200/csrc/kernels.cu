@@ -549,6 +549,69 @@ size_t ploc_scan_temp_bytes(uint32_t n) {
     cub::DeviceScan::ExclusiveSum(nullptr, bytes, (uint64_t*)nullptr, (uint64_t*)nullptr, (int)n);
     return bytes;
 }
+// The tail of PLOC in ONE launch: once few clusters are left (PLOC_TAIL_MAX), a single block of 1024 threads runs all remaining
+// rounds itself — nearest neighbours, flags, a block-wide exclusive scan and the merge, separated by block barriers — instead
+// of seven tiny dependent kernels per round. A 20 k-triangle scene needs ~30 rounds, and that chain of ~200 launches (each a few
+// microseconds of latency, not of work) was half of its build time. Same per-item bodies, same order, same tree.
+constexpr uint32_t PLOC_TAIL_THREADS = 1024;
+__global__ void __launch_bounds__(PLOC_TAIL_THREADS) k_ploc_tail(BuildCtx b, const uint32_t* st, uint32_t* st_out, uint32_t* cl_a, uint32_t* cl_b, uint32_t in_is_a) {
+    __shared__ unsigned long long s_warp[PLOC_TAIL_THREADS / 32];
+    __shared__ uint32_t s_m, s_next;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    if (tid == 0) { s_m = st[0]; s_next = st[1]; }
+    __syncthreads();
+    uint32_t flip = in_is_a ? 0u : 1u;
+    for (;;) {
+        const uint32_t m = s_m;
+        if (m <= 1u) break;
+        b.m = m; b.next_node = s_next;
+        b.cl_in = flip ? cl_b : cl_a;
+        b.cl_out = flip ? cl_a : cl_b;
+        for (uint32_t i = tid; i < m; i += PLOC_TAIL_THREADS) ploc_nn_body(i, b);
+        __syncthreads();
+        for (uint32_t i = tid; i < m; i += PLOC_TAIL_THREADS) ploc_flag_body(i, b);
+        __syncthreads();
+        // exclusive scan of b.scan[0 .. m) in place: a contiguous chunk per thread, the chunk totals scanned across the block
+        const uint32_t chunk = (m + PLOC_TAIL_THREADS - 1) / PLOC_TAIL_THREADS;
+        const uint32_t lo = min(m, tid * chunk), hi = min(m, lo + chunk);
+        unsigned long long sum = 0;
+        for (uint32_t i = lo; i < hi; i++) sum += b.scan[i];
+        unsigned long long incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long up = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)lane >= o) incl += up;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long w = s_warp[lane];   // 32 warps
+            unsigned long long wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long up = __shfl_up_sync(0xffffffffu, wi, o);
+                if ((int)lane >= o) wi += up;
+            }
+            s_warp[lane] = wi - w;   // exclusive
+        }
+        __syncthreads();
+        unsigned long long run = s_warp[warp] + (incl - sum);
+        for (uint32_t i = lo; i < hi; i++) { const unsigned long long f = b.scan[i]; b.scan[i] = run; run += f; }
+        __syncthreads();
+        for (uint32_t i = tid; i < m; i += PLOC_TAIL_THREADS) ploc_merge_body(i, b);
+        __syncthreads();
+        if (tid == 0) { s_m = b.ploc_out[0]; s_next = b.next_node - b.ploc_out[1]; }   // (written by the thread of item m - 1, before the barrier)
+        flip ^= 1u;
+        __syncthreads();
+        if (s_m >= m) break;   // no progress (cannot happen: the best pair is always mutual): the host sees m != 1 and reports it
+    }
+    if (tid == 0) { st_out[0] = s_m; st_out[1] = s_next; }
+}
+void launch_ploc_tail(cudaStream_t st, const BuildCtx& b, const uint32_t* state, uint32_t* state_out, uint32_t* cl_a, uint32_t* cl_b, bool in_is_a, LaunchCounter& lc) {
+    k_ploc_tail<<<1, PLOC_TAIL_THREADS, 0, st>>>(b, state, state_out, cl_a, cl_b, in_is_a ? 1u : 0u);
+    lc.launches++;
+}
+
 // one round; `bound` >= the round's cluster count (the count at the start of the batch), state = {m, next_node} ping-pong pair
 void launch_ploc_round(cudaStream_t st, const BuildCtx& b, uint32_t bound, const uint32_t* state, uint32_t* state_next, void* scan_temp,
                        size_t scan_temp_bytes, LaunchCounter& lc) {

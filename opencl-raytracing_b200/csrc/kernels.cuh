@@ -45,6 +45,8 @@ void launch_refit(cudaStream_t st, const BuildCtx& b, LaunchCounter& lc);
 void launch_collapse(cudaStream_t st, const BuildCtx& b, uint32_t bound, uint32_t* level, LaunchCounter& lc);
 void launch_ploc_init(cudaStream_t st, const BuildCtx& b, LaunchCounter& lc);
 size_t ploc_scan_temp_bytes(uint32_t n);
+constexpr uint32_t PLOC_TAIL_MAX = 8192;   // clusters at or below which one block finishes PLOC in a single launch (kernels.cu k_ploc_tail)
+void launch_ploc_tail(cudaStream_t st, const BuildCtx& b, const uint32_t* state, uint32_t* state_out, uint32_t* cl_a, uint32_t* cl_b, bool in_is_a, LaunchCounter& lc);
 // one PLOC round: nearest neighbours, merge flags, exclusive scan (CUB), merged nodes + compacted cluster list
 void launch_ploc_round(cudaStream_t st, const BuildCtx& b, uint32_t bound, const uint32_t* state, uint32_t* state_next, void* scan_temp,
                        size_t scan_temp_bytes, LaunchCounter& lc);

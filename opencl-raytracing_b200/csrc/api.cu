@@ -126,6 +126,29 @@ struct PlainCache {
 };
 static PlainCache g_plain_cache;
 
+// Streams of released contexts, parked per process and device: creating and destroying a stream costs ~50-100 us each, which a
+// one-shot render on 8 GPUs paid 16 times per call (init 0.4 ms, shutdown 0.8 ms of a 40 ms call).
+struct StreamCache {
+    std::mutex mu;
+    std::vector<std::pair<int, cudaStream_t>> parked;
+    cudaStream_t take(int device) {
+        std::lock_guard<std::mutex> g(mu);
+        for (size_t i = 0; i < parked.size(); i++)
+            if (parked[i].first == device) { cudaStream_t st = parked[i].second; parked.erase(parked.begin() + i); return st; }
+        return nullptr;
+    }
+    void park(int device, cudaStream_t st) { std::lock_guard<std::mutex> g(mu); parked.push_back({device, st}); }
+    void release_all() {
+        std::lock_guard<std::mutex> g(mu);
+        int cur = 0;
+        cudaGetDevice(&cur);
+        for (auto& e : parked) { cudaSetDevice(e.first); cudaStreamDestroy(e.second); }
+        cudaSetDevice(cur);
+        parked.clear();
+    }
+};
+static StreamCache g_stream_cache;
+
 template <typename T>
 struct DevBuf {
     T* p = nullptr;
@@ -1801,7 +1824,8 @@ rtcuda_ctx* make_device_ctx(const rtcuda_backend_settings& bs, int device_count)
     ctx->device = bs.device_id;
     ctx->bs = bs;
     CK(cudaSetDevice(ctx->device));
-    CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->stream = g_stream_cache.take(ctx->device);
+    if (!ctx->stream) CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     cudaMemPool_t pool;
     CK(cudaDeviceGetDefaultMemPool(&pool, ctx->device));
     uint64_t keep = UINT64_MAX;   // freed blocks stay in the pool until rtcuda_release_cached_memory
@@ -1811,10 +1835,7 @@ rtcuda_ctx* make_device_ctx(const rtcuda_backend_settings& bs, int device_count)
 void destroy_ctx(rtcuda_ctx* ctx) {
     if (!ctx) return;
     for (rtcuda_ctx* sub : ctx->subs) destroy_ctx(sub);
-    if (ctx->stream) {
-        cudaSetDevice(ctx->device);
-        cudaStreamDestroy(ctx->stream);
-    }
+    if (ctx->stream) g_stream_cache.park(ctx->device, ctx->stream);   // (pending stream-ordered frees stay ordered before whatever the next owner submits)
     delete ctx;
 }
 }  // namespace
@@ -1904,6 +1925,7 @@ RTCUDA_API rtcuda_status rtcuda_scene_upload(rtcuda_ctx* ctx, const rtcuda_scene
 RTCUDA_API void rtcuda_release_cached_memory(void) {
     g_arena_cache.release_all();
     g_plain_cache.release_all();
+    g_stream_cache.release_all();
     g_pinned_cache.release_all();
     int cur = 0, count = 0;
     if (cudaGetDevice(&cur) != cudaSuccess || cudaGetDeviceCount(&count) != cudaSuccess) return;

@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 T=${1:-r4m}
 N=${2:-8}
 nvidia-smi --query-gpu=index,name --format=csv,noheader > gpurun_out/${T}_gpu.txt
-timeout 600 python -m pytest tests -m gpu -q -k "multi_device" > gpurun_out/${T}_pytest_n${N}.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_pytest_n${N}.log; tail -3 gpurun_out/${T}_pytest_n${N}.log
+[ -n "$SKIP_TESTS" ] || timeout 600 python -m pytest tests -m gpu -q -k "multi_device" > gpurun_out/${T}_pytest_n${N}.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_pytest_n${N}.log; tail -3 gpurun_out/${T}_pytest_n${N}.log
 for wl in C3 C5; do
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 5 --warmup 3 --workload $wl --no-cpu-baseline > gpurun_out/${T}_bench_${wl}_n${N}.json 2> gpurun_out/${T}_bench_${wl}_n${N}.err
 python - $T $wl $N <<'PY'

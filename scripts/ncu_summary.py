@@ -28,11 +28,13 @@ KEYS = [("gpu__time_duration.sum", "duration"), ("launch__grid_size", "grid"), (
         ("smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio", "stall no_instruction"),
         ("smsp__inst_executed_op_local_ld.sum", "local loads"), ("smsp__inst_executed_op_local_st.sum", "local stores")]
 rep = sys.argv[1]
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+# either an .ncu-rep, or the text of `ncu -i <rep> --page raw --csv` made on the GPU box; optional: the launch IDs to tabulate
+raw = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr, units = rows[0], rows[1]
 idx = {h: i for i, h in enumerate(hdr)}
-kern = [r for r in rows[2:]]
+want = set(sys.argv[2].split(",")) if len(sys.argv) > 2 else None
+kern = [r for r in rows[2:] if want is None or r[idx["ID"]] in want]
 print("| metric | " + " | ".join(r[idx["Kernel Name"]].split("(")[0].replace("void ", "") for r in kern) + " |")
 print("|---|" + "---|" * len(kern))
 for k, label in KEYS:

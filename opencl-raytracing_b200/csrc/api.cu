@@ -399,8 +399,8 @@ struct rtcuda_scene {
     // Multi-device scene: the per-GPU scenes (subs[r] belongs to ctx->subs[r]); the parent holds nothing else of the above.
     std::vector<rtcuda_scene*> subs;
     // ... and, in each sub-scene, what the exchange of owned pixels needs (multi_* functions below): the packed planes of this
-    // rank's pixels on its GPU, their pinned host mirror, the host copy of the pixel list; on rank 0 also the other ranks'
-    // pixel lists and a receive buffer per rank (plain cudaMalloc: peer-accessible once peer access is enabled).
+    // rank's tiles on its GPU, their pinned host mirror, the tile table (host_tiles / tiles below); on rank 0 also the other ranks'
+    // tile tables and a receive buffer per rank (plain cudaMalloc: peer-accessible once peer access is enabled).
     uint32_t* packed = nullptr; size_t packed_words = 0; bool packed_plain = false;
     uint32_t* h_packed = nullptr; size_t h_packed_words = 0;
     std::vector<TileRec> host_tiles;   // the tiles this context owns (build_pixel_list), also on the device:

@@ -262,6 +262,28 @@ def test_primary_rays_that_miss_the_scene_bounds_are_not_queued(rc, oracle):
     assert estats["primary_rays_culled"] == 0                                # misses light the pixel through the environment map
 
 
+def test_page_locked_frame_planes_equal_pageable_ones(rc):
+    """rtcuda_host_alloc planes (the copy engine writes the frame itself) vs planes from anywhere else (pinned staging + host copy):
+    same bits, one and several devices; the buffers go back to the library's cache when the arrays are collected"""
+    import gc
+    sc = load_scene("cb_texture", 200, 120)
+    st = rc.RaytracerSettings(outputs=A.BEAUTY | A.NORMALS | A.UV_COORDS | A.DEBUG_IDS, samples_per_pixel=2)
+    lib = rc._ffi.load_library()
+    ids = _device_ids(2)
+    for backend in ({}, {"num_devices": len(ids), "device_ids": ids, "tile_size": 16}):
+        with rc.CudaRenderer(sc, rc.CudaBackendSettings(**backend)) as r:
+            pinned = r.render(st)                                           # planes from rtcuda_host_alloc
+            plain = rc.RenderOutput.allocate(200, 120, rc.AovFlags(st.outputs))   # numpy's own memory
+            r.render_into(st, plain)
+            for plane in ("beauty", "normals", "uv", "debug_ids"):
+                assert np.array_equal(getattr(pinned, plane), getattr(plain, plane)), plane
+    ptrs = {getattr(pinned, plane).ctypes.data for plane in ("beauty", "normals", "uv", "debug_ids")}
+    del pinned
+    gc.collect()
+    again = rc._ffi.host_array(lib, (120, 200, 3), np.float32)   # a parked buffer is handed out again
+    assert again is not None and again.ctypes.data in ptrs
+
+
 def test_own_arrays_and_scene_wide_arrays_upload_the_same_scene(rc):
     """rtcuda_shape.vertices / tris / normals / uvs (zero-copy from the caller's meshes) vs the concatenated scene-wide arrays"""
     import ctypes as C

@@ -60,6 +60,8 @@ def load_workload(name, synthetic_tris=0):
         sc = rc.test_scenes.synthetic_mesh_scene(sc, *SYNTHETIC[name])
     sc.camera = sc.camera.with_raster_size(w, h)
     st = rc.RaytracerSettings(samples_per_pixel=spp, max_ray_depth=depth, light_sample_count=ls)
+    if name == "C4":   # BASELINE config C4: "with normal,uv AOVs (texture fetch + AOV path)"
+        st.outputs = rc.AovFlags.BEAUTY | rc.AovFlags.NORMALS | rc.AovFlags.UV_COORDS
     return sc, st
 
 
@@ -173,7 +175,7 @@ def main():
     tile = args.tile_size or TILE_SIZE.get(args.workload, 16)
     part = (f"{tile}x{tile} tiles round-robin" if args.partition == "tiles" else "sample ranges of every pixel")
     config = {"workload": f"{args.workload}: {what} {W}x{H}, {spp} spp, depth {depth}, light samples {ls}, "
-                          f"independent sampler, seed 42",
+                          f"independent sampler, seed 42" + (", beauty + normal + uv planes" if args.workload == "C4" else ""),
               "triangles": None, "partition": f"{part} over {world} GPU(s), scene replicated, 1 NCCL collective per frame (tiles: gather of the owned pixels to rank 0; samples: sum-reduce)",
               "l2": "every step re-streams ~17 GB of wavefront state per batch through L2 (>> 126 MB) and a 512 MiB buffer is "
                     "written between timed steps; the 3 MB BVH is L2-resident by design"}
@@ -327,7 +329,7 @@ def main():
             rc._ffi.load_library().rtcuda_release_cached_memory()   # rank 0's arenas on the other ranks' GPUs
             dist.distributed_c10d._get_default_store().set("bench_e2e_done", "1")
     sync_all()
-    d2h = int(W * H * 3 * 4)
+    d2h = int(W * H * 4 * sum(ch for _n, flag, ch, _dt in rc.RenderOutput._PLANES if rc.AovFlags(st.outputs) & flag))
 
     if rank != 0:
         dr.close()

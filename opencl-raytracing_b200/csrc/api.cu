@@ -421,6 +421,7 @@ struct rtcuda_scene {
     View<PathState> state;
     View<float4> radiance, ray_o[2], ray_d[2], hits, sray_o, sray_d, scontrib;
     View<uint4> svertex;
+    View<uint32_t> deferred;
     View<uint32_t> counters;
     View<unsigned long long> counters64;
     DevBuf<unsigned long long> stats_dev;
@@ -1014,7 +1015,9 @@ void upload_scene(rtcuda_scene* s, const rtcuda_scene_desc* d, const GeoShare* s
     // constant albedo per material (SceneD::mat_const)
     std::vector<float4> mat_const(d->material_count, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
     for (uint32_t i = 0; i < d->material_count; i++) {
+        if (d->materials[i].kind != RTCUDA_MATERIAL_DIFFUSE) continue;   // w = 0
         const uint32_t t = d->materials[i].albedo;
+        mat_const[i].w = 2.0f;
         if (t != RTCUDA_NONE && t < d->texture_count && d->textures[t].kind == RTCUDA_TEXTURE_CONSTANT)
             mat_const[i] = make_float4(d->textures[t].value[0], d->textures[t].value[1], d->textures[t].value[2], 1.0f);
     }
@@ -1039,7 +1042,12 @@ void upload_scene(rtcuda_scene* s, const rtcuda_scene_desc* d, const GeoShare* s
     }
     sc.watertight = (s->ctx->bs.flags & RTCUDA_BACKEND_WATERTIGHT) ? 1u : 0u;
     sc.all_diffuse = 1;
-    for (uint32_t m = 0; m < d->material_count; m++) if (d->materials[m].kind != RTCUDA_MATERIAL_DIFFUSE) sc.all_diffuse = 0;
+    sc.any_diffuse = 0;
+    for (uint32_t m = 0; m < d->material_count; m++) {
+        if (d->materials[m].kind != RTCUDA_MATERIAL_DIFFUSE) sc.all_diffuse = 0;
+        else sc.any_diffuse = 1;
+    }
+    if (std::getenv("RTCUDA_NO_MATERIAL_SPLIT")) sc.any_diffuse = sc.all_diffuse;   // (A/B aid: mixed scenes through the general kernel only)
     sc.tex_uses_derivs = 0;
     for (uint32_t t = 0; t < d->texture_count; t++)
         if (d->textures[t].kind == RTCUDA_TEXTURE_IMAGE || d->textures[t].kind == RTCUDA_TEXTURE_CHECKER) sc.tex_uses_derivs = 1;
@@ -1137,7 +1145,7 @@ uint32_t shadow_entries_per_vertex(const rtcuda_scene* s, const RenderParams& rp
 // Bytes of path state for `cap` slots (every buffer ensure_wave carves, plus alignment slack).
 size_t arena_bytes(size_t cap, uint32_t shadow_k, uint32_t max_depth) {
     const size_t k = std::max(1u, shadow_k), n_counters = 4 * ((size_t)max_depth + 3);
-    return cap * (16 + 16 * 7 + 16) + cap * k * 48 + n_counters * 4 + ((size_t)max_depth + 3) * 8 + 16 * 256;
+    return cap * (16 + 16 * 7 + 16 + 4) + cap * k * 48 + n_counters * 4 + ((size_t)max_depth + 3) * 8 + 16 * 256;
 }
 
 // Allocate the wavefront state for `capacity` path slots.
@@ -1155,6 +1163,7 @@ void ensure_wave(rtcuda_scene* s, uint32_t capacity, uint32_t shadow_k, uint32_t
     for (int i = 0; i < 2; i++) { view(s->ray_o[i], cap); view(s->ray_d[i], cap); }
     view(s->hits, cap);
     view(s->svertex, cap);
+    view(s->deferred, cap);
     view(s->sray_o, cap * k);
     view(s->sray_d, cap * k);
     view(s->scontrib, cap * k);
@@ -1203,6 +1212,7 @@ void run_batch(rtcuda_scene* s, const RenderParams& rp, Wave w, uint32_t n_paths
     uint32_t* rays = s->counters.p;                       // rays[d]: queue length at depth d
     uint32_t* fetch_ext = s->counters.p + (max_depth + 3);      // work-fetch cursors of the persistent kernels
     uint32_t* fetch_sh = s->counters.p + 2 * (max_depth + 3);
+    uint32_t* deferred_n = s->counters.p + 3 * (max_depth + 3);   // vertices the Diffuse shade kernel left for the general one, per depth
     unsigned long long* shadows = s->counters64.p;              // shadows[d]: NEE vertices | shadow rays << 32
     CK(cudaMemsetAsync(s->counters.p, 0, 4 * ((size_t)max_depth + 3) * 4, st));
     CK(cudaMemsetAsync(s->counters64.p, 0, ((size_t)max_depth + 3) * 8, st));
@@ -1217,6 +1227,7 @@ void run_batch(rtcuda_scene* s, const RenderParams& rp, Wave w, uint32_t n_paths
         w.ray_o_in = s->ray_o[in].p; w.ray_d_in = s->ray_d[in].p;
         w.ray_o_out = s->ray_o[out].p; w.ray_d_out = s->ray_d[out].p;
         w.n_in = rays + depth; w.n_out = rays + depth + 1; w.n_shadow = shadows + depth;
+        w.deferred = s->deferred.p; w.n_deferred = deferred_n + depth;
         { SpanGuard g(s, CLS_EXTEND, timing); launch_extend(st, s->sc, w, n_paths, depth == 0 ? s->sc.camera.near_clip : 0.0001f, fetch_ext + depth, collect, s->lc); }
         { SpanGuard g(s, CLS_SHADE, timing); launch_shade(st, s->sc, rp, w, n_paths, s->lc); }
         if (depth < max_depth && w.shadow_k) {
@@ -1307,7 +1318,7 @@ void render_device(rtcuda_scene* s, const rtcuda_settings* settings, const rtcud
                 }
             }
             if (!capacity) {
-                const size_t bytes_per_slot = 16 + 16 * 7 + 16 + 48 * (size_t)std::max(1u, shadow_k);
+                const size_t bytes_per_slot = 16 + 16 * 7 + 16 + 4 + 48 * (size_t)std::max(1u, shadow_k);
                 size_t free_b = 0, total_b = 0;
                 CK(cudaMemGetInfo(&free_b, &total_b));
                 const size_t have_b = free_b + s->wave_bytes();

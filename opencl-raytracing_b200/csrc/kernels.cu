@@ -200,10 +200,15 @@ __global__ void __launch_bounds__(BLOCK, 4) k_extend(const __grid_constant__ Sce
 // profiles/r1_notes.md). Per chunk ONE warp scan hands out the positions of all three outputs — continuation
 // rays, NEE vertices, shadow rays (a variable number per thread, consecutive per vertex) — and the last lane issues
 // the warp's two global atomics (one per queue counter; the 64-bit one carries vertices | shadow rays << 32).
-template <typename Surf, bool SHARED_STAGE_ONLY>
+// Scenes that mix Diffuse with other materials are shaded in two launches per depth (SPLIT): the Diffuse instantiation walks the
+// whole queue and leaves the vertices with another material on a list (SPLIT = 1: one atomic per such vertex); the general
+// instantiation then walks that list only (SPLIT = 2). Run over everything, the general kernel executed at 11.5 of 32 lanes (a
+// warp's Diffuse and conductor lanes take turns), a quarter of its stall samples were instruction-cache misses of its 26 k
+// instructions, and the Diffuse majority paid for its 128 registers (rough-metal box CM: ncu, profiles/r5b).
+template <typename Surf, bool SHARED_STAGE_ONLY, int SPLIT>
 __global__ void __launch_bounds__(SHADE_THREADS, std::is_same<Surf, DiffuseSurface>::value ? SHADE_BLOCKS : 512 / SHADE_THREADS) k_shade(const __grid_constant__ SceneD sc, const __grid_constant__ RenderParams rp,
                                                   const __grid_constant__ Wave w) {
-    const uint32_t n = *w.n_in;
+    const uint32_t n = SPLIT == 2 ? *w.n_deferred : *w.n_in;
     const unsigned FULL = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
 #if RT_NEE_SMEM > 0
@@ -213,9 +218,10 @@ __global__ void __launch_bounds__(SHADE_THREADS, std::is_same<Surf, DiffuseSurfa
 #else
     const StagePtr stage_col{nullptr, 0u, 0u};
 #endif
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&w.stats[STAT_SHADED], (unsigned long long)n);
+    if (SPLIT != 2 && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&w.stats[STAT_SHADED], (unsigned long long)n);
     for (uint32_t base = blockIdx.x * SHADE_THREADS; base < n; base += gridDim.x * SHADE_THREADS) {
-        const uint32_t q = base + threadIdx.x;
+        const uint32_t qi = base + threadIdx.x;
+        const uint32_t q = SPLIT == 2 ? (qi < n ? w.deferred[qi] : 0u) : qi;
         // Per-warp allocation (two atomics per warp that has output, no block barrier: the warps of a block drift apart on
         // their dependent loads, and a barrier per chunk made all of them wait for the slowest), issued as early as their
         // counts are known and consumed as late as possible: the shadow-queue atomic right after next-event estimation (it
@@ -224,7 +230,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, std::is_same<Surf, DiffuseSurfa
         unsigned long long base1 = 0;   // lane 31: vertices | shadow rays << 32 before this warp's
         uint32_t base0 = 0, incl = 0;    // lane 31: rays before this warp's; inclusive scan of the shadow-ray counts
         unsigned mc = 0, mv = 0;
-        shade_vertex<Surf, SHARED_STAGE_ONLY>(q < n, q, sc, rp, w,
+        shade_vertex<Surf, SHARED_STAGE_ONLY, SPLIT == 1>(qi < n, q, sc, rp, w,
             [&](bool cont, bool has_vertex, uint32_t k, bool final_skipped, uint32_t& rpos, uint32_t& vpos, uint32_t& first) {
                 (void)has_vertex; (void)rpos;
                 mc = __ballot_sync(FULL, cont);
@@ -251,7 +257,8 @@ __global__ void __launch_bounds__(SHADE_THREADS, std::is_same<Surf, DiffuseSurfa
                     if (n1) base1 = atomicAdd(w.n_shadow, n1);
                 }
             },
-            [&](uint32_t& rpos) { rpos = __shfl_sync(FULL, base0, 31) + (uint32_t)__popc(mc & lt); });
+            [&](uint32_t& rpos) { rpos = __shfl_sync(FULL, base0, 31) + (uint32_t)__popc(mc & lt); },
+            [&](uint32_t deferred_q) { w.deferred[atomicAdd(w.n_deferred, 1u)] = deferred_q; });
     }
 }
 
@@ -376,8 +383,12 @@ void launch_shade(cudaStream_t st, const SceneD& sc, const RenderParams& rp, con
     auto go = [&](auto kernel) { kernel<<<persistent_grid((const void*)kernel, n_max, SHADE_THREADS), SHADE_THREADS, 0, st>>>(sc, rp, w); };
     // (Diffuse-only scenes: C4's shade 60.3 -> 55.6 ms; the general instantiation lost 2.5 ms of 38.5 on CM with it and keeps both
     // stages — profiles/r4p_ab.log)
-    if (sc.all_diffuse) { if (smem_only) go(k_shade<DiffuseSurface, true>); else go(k_shade<DiffuseSurface, false>); }
-    else go(k_shade<Surface, false>);
+    if (sc.all_diffuse) { if (smem_only) go(k_shade<DiffuseSurface, true, 0>); else go(k_shade<DiffuseSurface, false, 0>); }
+    else if (sc.any_diffuse) {   // mixed materials: the Diffuse kernel first, then the general kernel over what it left
+        if (smem_only) go(k_shade<DiffuseSurface, true, 1>); else go(k_shade<DiffuseSurface, false, 1>);
+        go(k_shade<Surface, false, 2>);
+        lc.launches++;
+    } else go(k_shade<Surface, false, 0>);
     lc.launches++;
 }
 void launch_shadow(cudaStream_t st, const SceneD& sc, const Wave& w, uint32_t n_max, uint32_t* fetch_counter, bool stats, LaunchCounter& lc) {

@@ -540,7 +540,7 @@ RT_HD void get_surface(const SceneD& sc, const MaterialD& m, const MatCtx& c, Di
 RT_HD void get_surface_of(const SceneD& sc, uint32_t material, const MatCtx& c, DiffuseSurface& out) {
     if (sc.mat_const) {
         const float4 mc = ldg(sc.mat_const + material);
-        if (mc.w != 0.0f) { out.albedo = xyz(mc); return; }
+        if (mc.w == 1.0f) { out.albedo = xyz(mc); return; }
     }
     get_surface(sc, sc.materials[material], c, out);
 }

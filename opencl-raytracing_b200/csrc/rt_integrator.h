@@ -56,6 +56,10 @@ struct Wave {
     float4* sray_d;              // unit direction light -> shading point
     float4* scontrib;            // weighted contribution.xyz if unoccluded; zeroed by k_shadow when the ray is blocked
     uint4* svertex;              // slot | first ray | ray count | -
+    // material split (scenes that mix Diffuse with other materials): queue positions of the vertices the Diffuse shade kernel
+    // met with another material and left for the general kernel, and their count at this depth
+    uint32_t* deferred;
+    uint32_t* n_deferred;
 };
 
 enum { STAT_PRIMARY = 0, STAT_BOUNCE = 1, STAT_SHADOW = 2, STAT_AOV = 3, STAT_EXT_NODES = 4, STAT_EXT_PRIMS = 5, STAT_SH_NODES = 6,
@@ -377,8 +381,10 @@ RT_HD void add_emitted(const Wave& w, const ShadeState<Surf>& S) {
 }
 
 // lib.rs:284-322: miss / emission / material setup. False when the path ends here (state already written back).
-template <typename Surf>
-RT_HD bool shade_begin(uint32_t q, const SceneD& sc, const RenderParams& rp, const Wave& w, ShadeState<Surf>& S) {
+// DEFER_OTHERS (the Diffuse kernel of a scene with mixed materials): a vertex whose material is not Diffuse is left untouched for
+// the general kernel (`deferred` set, nothing read-modified-written yet).
+template <typename Surf, bool DEFER_OTHERS = false>
+RT_HD bool shade_begin(uint32_t q, const SceneD& sc, const RenderParams& rp, const Wave& w, ShadeState<Surf>& S, bool& deferred) {
     const float4 ro4 = w.ray_o_in[q], rd4 = w.ray_d_in[q], h4 = w.hits[q];
     const uint32_t slot = f2u(rd4.w);
     S.slot = slot;
@@ -413,6 +419,7 @@ RT_HD bool shade_begin(uint32_t q, const SceneD& sc, const RenderParams& rp, con
 
     const bool aa = depth == 0 && rp.antialias_primary_rays && sc.tex_uses_derivs;
     reconstruct_hit(sc, S.ray.o, S.ray.d, h, aa, S.hit);
+    if (DEFER_OTHERS && ldg(sc.mat_const + S.hit.material).w == 0.0f) { deferred = true; return false; }
 
     const bool add_zero_bounce = rp.accumulate_bounces || rp.max_ray_depth == depth;
     if (specular_bounce && add_zero_bounce && S.hit.light != NONE) {
@@ -528,9 +535,10 @@ RT_HD uint32_t nee_pass(const SceneD& sc, const RenderParams& rp, const Wave& w,
 // SHARED_STAGE_ONLY: the caller guarantees that every vertex's entries fit the shared-memory column it passes (the kernel is
 // instantiated that way for launches with shadow_k <= NEE_SMEM): no thread-local staging array exists in that instantiation, and
 // the staging accesses are shared-memory instructions instead of generic ones.
-template <typename Surf, bool SHARED_STAGE_ONLY = false, typename Alloc, typename Early, typename Late>
+// DEFER_OTHERS: see shade_begin; `defer(q)` receives the queue positions left for the general kernel.
+template <typename Surf, bool SHARED_STAGE_ONLY = false, bool DEFER_OTHERS = false, typename Alloc, typename Early, typename Late, typename Defer>
 RT_HD void shade_vertex(bool active, uint32_t q, const SceneD& sc, const RenderParams& rp, const Wave& w, Alloc&& alloc, StagePtr shared_stage, Early&& early,
-                        Late&& late) {
+                        Late&& late, Defer&& defer) {
     ShadeState<Surf> S;
     Sampler s2;
     BsdfSample bs;
@@ -546,7 +554,11 @@ RT_HD void shade_vertex(bool active, uint32_t q, const SceneD& sc, const RenderP
     if constexpr (!SHARED_STAGE_ONLY) {
         if (!(shared_stage.p && w.shadow_k <= shared_stage.capacity)) stage = StagePtr{local_stage.e, 1u, NEE_STAGE};
     } else (void)local_stage;
-    if (active) active = shade_begin(q, sc, rp, w, S);
+    if (active) {
+        bool deferred = false;
+        active = shade_begin<Surf, DEFER_OTHERS>(q, sc, rp, w, S, deferred);
+        if (DEFER_OTHERS && deferred) defer(q);
+    }
     if (active) {
         s2 = S.s;
         const bool add_direct = rp.accumulate_bounces || rp.max_ray_depth == w.depth + 1;
@@ -603,7 +615,7 @@ RT_HD void shade_vertex(bool active, uint32_t q, const SceneD& sc, const RenderP
 
 template <typename Surf, typename Alloc>
 RT_HD void shade_vertex(bool active, uint32_t q, const SceneD& sc, const RenderParams& rp, const Wave& w, Alloc&& alloc, StagePtr shared_stage = StagePtr{nullptr, 0u, 0u}) {
-    shade_vertex<Surf, false>(active, q, sc, rp, w, alloc, shared_stage, [](bool, uint32_t) {}, [](uint32_t&) {});
+    shade_vertex<Surf, false, false>(active, q, sc, rp, w, alloc, shared_stage, [](bool, uint32_t) {}, [](uint32_t&) {}, [](uint32_t) {});
 }
 
 // ---- shadow gather: add the unoccluded contributions of one NEE vertex to its path, in light-sample order ----

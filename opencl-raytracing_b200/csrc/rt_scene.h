@@ -141,10 +141,13 @@ struct SceneD {
     // vertex normals, all at warp-uniform addresses (profiles/r4c_ncu_summary.md).
     //   light0           copy of lights[0] (valid when light_count >= 1); the other lights are read from memory
     //   light0_tri_count / light0_has_normals   what sample_light needs of the emitter's shape record
-    //   mat_const        per material: xyz = the albedo when it is a CONSTANT texture, w = 1 then (else 0): Diffuse
-    //                    surfaces skip the material -> texture -> value chain of dependent loads
+    //   mat_const        per material: w = 1: Diffuse with a CONSTANT albedo texture, xyz = that albedo (Diffuse surfaces skip
+    //                    the material -> texture -> value chain of dependent loads); w = 2: Diffuse, albedo from its texture;
+    //                    w = 0: any other material (the Diffuse shade kernel of a mixed scene leaves those vertices to the
+    //                    general kernel)
+    //   any_diffuse      some material is Diffuse (with all_diffuse == 0: the scene mixes materials)
     LightD light0;
-    uint32_t light0_tri_count, light0_has_normals, use_light0, _pad_l0;
+    uint32_t light0_tri_count, light0_has_normals, use_light0, any_diffuse;
     const float4* mat_const;
     float scene_center[3];
     float scene_radius;       // +inf when the BVH root is a leaf (bvh2.rs:448-452 quirk, see rt_shade.h)

@@ -152,7 +152,9 @@ void build(HostScene& hs, const rtcuda_scene_desc* d) {
     // the kernel-parameter copies (SceneD::light0, mat_const) exactly as api.cu fills them
     hs.mat_const.assign(d->material_count, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
     for (uint32_t i = 0; i < d->material_count; i++) {
+        if (d->materials[i].kind != 0) continue;
         const uint32_t t = d->materials[i].albedo;
+        hs.mat_const[i].w = 2.0f;
         if (t != RTCUDA_NONE && t < d->texture_count && d->textures[t].kind == RTCUDA_TEXTURE_CONSTANT)
             hs.mat_const[i] = make_float4(d->textures[t].value[0], d->textures[t].value[1], d->textures[t].value[2], 1.0f);
     }

@@ -176,16 +176,16 @@ __global__ void __launch_bounds__(BLOCK, 4) k_extend(const __grid_constant__ Sce
 #endif
                 if (mine < n) {
                     q = mine;
-                    const float4 o4 = w.ray_o_in[q], d4 = w.ray_d_in[q];
+                    const float4 o4 = ld_stream(&w.ray_o_in[q]), d4 = ld_stream(&w.ray_d_in[q]);
                     have = tr.init(sc, xyz(o4), xyz(d4), t_min, o4.w) ? 1u : 0u;
-                    if (!have) w.hits[q] = make_float4(o4.w, u2f(NONE), 0.0f, 0.0f);
+                    if (!have) st_stream(&w.hits[q], make_float4(o4.w, u2f(NONE), 0.0f, 0.0f));
                 }
             }
             if (base + (uint32_t)cnt >= n) exhausted = 1u;
         }
         warp_phase(tr, have, sc, &ts);
         if (have && !tr.next()) {
-            w.hits[q] = make_float4(tr.hit.t, u2f(tr.hit.prim), tr.hit.u, tr.hit.v);
+            st_stream(&w.hits[q], make_float4(tr.hit.t, u2f(tr.hit.prim), tr.hit.u, tr.hit.v));
             have = 0u;
         }
     }
@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(BLOCK, SHADOW_BLOCKS) k_shadow(const __grid_co
 #endif
                 if (mine < n) {
                     q = mine;
-                    const float4 o4 = w.sray_o[q], d4 = w.sray_d[q];
+                    const float4 o4 = ld_stream(&w.sray_o[q]), d4 = ld_stream(&w.sray_d[q]);
 #if RT_SHADOW_PARALLEL_LOADS
                     // both halves of the entry are loaded before either is looked at (testing t_max first makes the direction a
                     // second, dependent round trip)

@@ -385,7 +385,7 @@ RT_HD void add_emitted(const Wave& w, const ShadeState<Surf>& S) {
 // the general kernel (`deferred` set, nothing read-modified-written yet).
 template <typename Surf, bool DEFER_OTHERS = false>
 RT_HD bool shade_begin(uint32_t q, const SceneD& sc, const RenderParams& rp, const Wave& w, ShadeState<Surf>& S, bool& deferred) {
-    const float4 ro4 = w.ray_o_in[q], rd4 = w.ray_d_in[q], h4 = w.hits[q];
+    const float4 ro4 = ld_stream(&w.ray_o_in[q]), rd4 = ld_stream(&w.ray_d_in[q]), h4 = ld_stream(&w.hits[q]);
     const uint32_t slot = f2u(rd4.w);
     S.slot = slot;
     S.ray.o = xyz(ro4);
@@ -600,7 +600,7 @@ RT_HD void shade_vertex(bool active, uint32_t q, const SceneD& sc, const RenderP
                 const size_t e = (size_t)first + j;
                 RT_CHECK(e < (size_t)w.capacity * (w.shadow_k ? w.shadow_k : 1u));
                 const float4* se = stage.p + (size_t)(3u * j) * stage.stride;
-                w.sray_o[e] = se[0]; w.sray_d[e] = se[stage.stride]; w.scontrib[e] = se[2u * stage.stride];
+                st_stream(&w.sray_o[e], se[0]); st_stream(&w.sray_d[e], se[stage.stride]); st_stream(&w.scontrib[e], se[2u * stage.stride]);
             }
         else nee_pass<2>(sc, rp, w, S, S.s, first, k, stage);
         RT_CHECK(vpos < w.capacity && S.slot < w.capacity);
@@ -609,8 +609,8 @@ RT_HD void shade_vertex(bool active, uint32_t q, const SceneD& sc, const RenderP
     late(rpos);
     if (!alive) return;
     RT_CHECK(rpos < w.capacity);
-    w.ray_o_out[rpos] = make_float4(S.hit.point.x, S.hit.point.y, S.hit.point.z, RT_INF);
-    w.ray_d_out[rpos] = make_float4(nd.x, nd.y, nd.z, u2f(S.slot));
+    st_stream(&w.ray_o_out[rpos], make_float4(S.hit.point.x, S.hit.point.y, S.hit.point.z, RT_INF));
+    st_stream(&w.ray_d_out[rpos], make_float4(nd.x, nd.y, nd.z, u2f(S.slot)));
 }
 
 template <typename Surf, typename Alloc>

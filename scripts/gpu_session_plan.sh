@@ -1,7 +1,10 @@
 # A/B plan of the current session (sourced by gpu_session.sh)
-one split CM RTCUDA_NO_MATERIAL_SPLIT=1
-one split CM X=1
-one split CD RTCUDA_NO_MATERIAL_SPLIT=1
-one split CD X=1
-one split C3 X=1
-cp ab/split.so $LIB
+one cur C3 X=1
+one stream C3 X=1
+one cur C4 X=1
+one stream C4 X=1
+one cur CM X=1
+one stream CM X=1
+one cur C5s X=1
+one stream C5s X=1
+cp ab/cur.so $LIB

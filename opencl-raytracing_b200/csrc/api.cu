@@ -1372,38 +1372,39 @@ void render_device(rtcuda_scene* s, const rtcuda_settings* settings, const rtcud
                 // The first frame of a key is launched directly: capture + instantiation cost 2-3 ms, which a one-shot
                 // `render(scene, settings)` would pay for a graph it never replays. The second frame with the same key is
                 // captured, later ones replay it.
-                if ((!s->frame_exec || key != s->frame_key) && key != s->seen_key) {
+                const bool have_graph = s->frame_exec && key == s->frame_key;
+                if (!have_graph && key != s->seen_key) {   // first frame of this key: direct launches
                     if (s->frame_exec) { cudaGraphExecDestroy(s->frame_exec); s->frame_exec = nullptr; }
                     s->frame_key.clear();
                     s->seen_key = key;
                     reset_spans(s);
                     enqueue_frame();
                 } else {
-                if (!s->frame_exec || key != s->frame_key) {
-                    reset_spans(s);
-                    const unsigned long long l0 = s->lc.launches;
-                    cudaGraph_t graph = nullptr;
-                    CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-                    s->capturing = true;
-                    try {
-                        enqueue_frame();
-                    } catch (...) {
+                    if (!have_graph) {                     // second frame of this key: capture and instantiate
+                        reset_spans(s);
+                        const unsigned long long l0 = s->lc.launches;
+                        cudaGraph_t graph = nullptr;
+                        CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+                        s->capturing = true;
+                        try {
+                            enqueue_frame();
+                        } catch (...) {
+                            s->capturing = false;
+                            cudaStreamEndCapture(st, &graph);
+                            if (graph) cudaGraphDestroy(graph);
+                            throw;
+                        }
                         s->capturing = false;
-                        cudaStreamEndCapture(st, &graph);
-                        if (graph) cudaGraphDestroy(graph);
-                        throw;
+                        CK(cudaStreamEndCapture(st, &graph));
+                        const cudaError_t ie = cudaGraphInstantiate(&s->frame_exec, graph, 0);
+                        cudaGraphDestroy(graph);
+                        CK(ie);
+                        s->frame_launches = s->lc.launches - l0;
+                        s->lc.launches = l0;
+                        s->frame_key = key;
                     }
-                    s->capturing = false;
-                    CK(cudaStreamEndCapture(st, &graph));
-                    const cudaError_t ie = cudaGraphInstantiate(&s->frame_exec, graph, 0);
-                    cudaGraphDestroy(graph);
-                    CK(ie);
-                    s->frame_launches = s->lc.launches - l0;
-                    s->lc.launches = l0;
-                    s->frame_key = std::move(key);
-                }
-                CK(cudaGraphLaunch(s->frame_exec, st));
-                s->lc.launches += s->frame_launches;
+                    CK(cudaGraphLaunch(s->frame_exec, st));
+                    s->lc.launches += s->frame_launches;
                 }
             }
         }

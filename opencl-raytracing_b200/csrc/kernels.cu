@@ -19,6 +19,12 @@ constexpr int BLOCK = 256;
 // flight count for more than registers: on C3 (256 threads x 3 blocks = 80 registers, 24 warps) 76.1 ms -> 72.5 ms; 64 registers /
 // 32 warps spills too much (79.1 ms), 96 registers / 20 warps 81.2 ms (profiles/r4f_ab.log, r4g_ab.log). The general
 // instantiation (every non-Diffuse material) keeps 128 registers.
+// k_shade prefetches the queue entry (ray origin, direction, hit: three coalesced streams) of a thread's next iteration into L2 at
+// the top of the current one: the first of the three dependent round trips at the head of a vertex becomes an L2 hit. C3 shade
+// 71.9 -> 69.3 ms, rough-metal box 23.6 -> 22.4, C4 unchanged (profiles/r6a_ab.log). The value is the distance in iterations.
+#ifndef RT_SHADE_QUEUE_PREFETCH
+#define RT_SHADE_QUEUE_PREFETCH 1
+#endif
 #ifndef SHADE_BLOCKS
 #define SHADE_BLOCKS 7
 #endif
@@ -222,6 +228,12 @@ __global__ void __launch_bounds__(SHADE_THREADS, std::is_same<Surf, DiffuseSurfa
     for (uint32_t base = blockIdx.x * SHADE_THREADS; base < n; base += gridDim.x * SHADE_THREADS) {
         const uint32_t qi = base + threadIdx.x;
         const uint32_t q = SPLIT == 2 ? (qi < n ? w.deferred[qi] : 0u) : qi;
+#if RT_SHADE_QUEUE_PREFETCH
+        if (SPLIT != 2) {   // the queue entry of this thread's next iteration, into L2 (three streams, one line each per 8 threads)
+            const uint32_t qn = qi + (uint32_t)RT_SHADE_QUEUE_PREFETCH * gridDim.x * SHADE_THREADS;
+            if (qn < n) { prefetch_l2(w.ray_o_in + qn); prefetch_l2(w.ray_d_in + qn); prefetch_l2(w.hits + qn); }
+        }
+#endif
         // Per-warp allocation (two atomics per warp that has output, no block barrier: the warps of a block drift apart on
         // their dependent loads, and a barrier per chunk made all of them wait for the slowest), issued as early as their
         // counts are known and consumed as late as possible: the shadow-queue atomic right after next-event estimation (it

@@ -97,3 +97,36 @@ def texture_zoo_scene(width=160, height=160):
     out.camera = rc.Camera.lookat_camera_perspective((0.0, 4.4, 0.4), (0, 0, 0.75), (0, 0, 1), False,
                                                      float(np.float32(37.8) * np.float32(math.pi / 180)), width, height)
     return out
+
+
+def _trs(translate, axis, angle, scale):
+    """object-to-world = T * R(axis, angle) * S as a Transform whose inverse is the matrix inverse (float64, rounded once)"""
+    import numpy as np
+    import raytracing_cuda as rc
+    a = np.asarray(axis, dtype=np.float64)
+    a = a / np.linalg.norm(a)
+    K = np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
+    R = np.eye(3) + np.sin(angle) * K + (1 - np.cos(angle)) * (K @ K)
+    M = np.eye(4)
+    M[:3, :3] = R @ np.diag(np.asarray(scale, dtype=np.float64))
+    M[:3, 3] = translate
+    f = M.astype(np.float32)
+    return rc.test_scenes.Transform(f, np.linalg.inv(f.astype(np.float64)).astype(np.float32))
+
+
+def instanced_bunnies_scene(width=128, height=96):
+    """Test-only scene for mesh reuse (glTF: several nodes referencing one mesh -> several Transform primitives over ONE Basic
+    primitive, scene/scene.rs:430-443, geometry.rs:92-136): the Cornell box of cb.glb (x, y in [-1, 1], z in [0, 1.5]) with the
+    bunny mesh used by three instances — scaled + translated, rotated + scaled, and non-uniformly scaled + rotated about a
+    tilted axis."""
+    import raytracing_cuda as rc
+    base = load_scene("cb", width, height)
+    b = rc.SceneBuilder()
+    b.scene = base
+    tex = b.add_constant_texture((0.7, 0.55, 0.3, 1.0))
+    mat = b.add_material(rc.Material(rc._ffi.MATERIAL_DIFFUSE, albedo=tex))
+    shape_index = len(base.shapes)
+    b.add_shape_with_transform(bunny_mesh(), mat, _trs((-0.5, -0.2, 0.0), (0, 0, 1), 0.0, (0.6, 0.6, 0.6)), None)
+    b.add_instance(shape_index, _trs((0.45, 0.1, 0.0), (0, 0, 1), 1.1, (0.5, 0.5, 0.5)))
+    b.add_instance(shape_index, _trs((0.0, 0.45, 0.1), (0.3, 0.2, 1.0), -0.7, (0.4, 0.7, 0.5)))
+    return b.build()

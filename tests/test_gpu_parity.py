@@ -262,6 +262,19 @@ def test_primary_rays_that_miss_the_scene_bounds_are_not_queued(rc, oracle):
     assert estats["primary_rays_culled"] == 0                                # misses light the pixel through the environment map
 
 
+def test_reused_mesh_instances(rc, oracle):
+    """one mesh under three Transform primitives (glTF mesh reuse, scene/scene.rs:430-443): the flattened world-space tree gives
+    the reference's ids / normals / uv / depth and beauty"""
+    from conftest import instanced_bunnies_scene
+    sc = instanced_bunnies_scene(320, 240)
+    st = rc.RaytracerSettings(outputs=dbg() | A.BEAUTY, samples_per_pixel=8, max_ray_depth=6, light_sample_count=2)
+    out, stats = gpu_render(rc, sc, st)
+    ref, _ = oracle.render(sc, st)
+    assert_first_hit_parity(out, ref)
+    rep = assert_beauty_parity(out.beauty, ref.beauty, what="instanced bunnies")
+    print(f"\n[parity] reused mesh x3: {rep}")
+
+
 def test_page_locked_frame_planes_equal_pageable_ones(rc):
     """rtcuda_host_alloc planes (the copy engine writes the frame itself) vs planes from anywhere else (pinned staging + host copy):
     same bits, one and several devices; the buffers go back to the library's cache when the arrays are collected"""

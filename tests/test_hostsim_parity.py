@@ -4,7 +4,7 @@ the `-m gpu` tests repeat the same comparisons through libraytracing_cuda.so on 
 import numpy as np
 import pytest
 
-from conftest import load_scene, bunny_mesh
+from conftest import load_scene, bunny_mesh, instanced_bunnies_scene
 from parity import assert_first_hit_parity, assert_beauty_parity, luminance, beauty_close
 
 A = None
@@ -284,3 +284,18 @@ def test_pixels_outside_the_scene_rectangle_are_dropped_exactly(rc, oracle, host
         assert (oref.debug_ids[~ins] == 0xffffffff).all()
         ys, xs = np.nonzero(oref.debug_ids[..., 0] != 0xffffffff)
         assert r[0] <= xs.min() and xs.max() <= r[2] and xs.min() - r[0] <= 6
+
+
+def test_reused_mesh_instances(rc, oracle, hostsim):
+    """one mesh under three Transform primitives (translation, rotation + scale, non-uniform scale): ids, normals (inverse
+    transpose), uv, depth of the first hit and the beauty plane against the oracle"""
+    sc = instanced_bunnies_scene(96, 72)
+    assert len(sc.instances) == len(sc.shapes) + 2
+    st = rc.RaytracerSettings(outputs=dbg() | A.BEAUTY, samples_per_pixel=2, max_ray_depth=4, light_sample_count=2)
+    out, stats = hostsim.render(sc, st)
+    ref, ostats = oracle.render(sc, st, num_threads=8)
+    assert_first_hit_parity(out, ref)
+    geoms = set(np.unique(out.debug_ids[..., 0]).tolist())
+    assert {len(sc.instances) - 3, len(sc.instances) - 2, len(sc.instances) - 1} <= geoms   # all three instances are seen
+    assert stats["primary_rays"] == ostats["primary_rays"]
+    assert_beauty_parity(out.beauty, ref.beauty)

@@ -168,7 +168,8 @@ void build(HostScene& hs, const rtcuda_scene_desc* d) {
     }
     sc.watertight = std::getenv("HOSTSIM_WATERTIGHT") ? 1u : 0u;   // test switch for RTCUDA_BACKEND_WATERTIGHT
     sc.all_diffuse = 1;
-    for (uint32_t m = 0; m < d->material_count; m++) if (d->materials[m].kind != 0) sc.all_diffuse = 0;
+    sc.any_diffuse = 0;
+    for (uint32_t m = 0; m < d->material_count; m++) { if (d->materials[m].kind != 0) sc.all_diffuse = 0; else sc.any_diffuse = 1; }
     sc.tex_uses_derivs = 0;
     for (uint32_t t = 0; t < d->texture_count; t++)
         if (d->textures[t].kind == RTCUDA_TEXTURE_IMAGE || d->textures[t].kind == RTCUDA_TEXTURE_CHECKER) sc.tex_uses_derivs = 1;
@@ -525,10 +526,22 @@ int hostsim_render_samples(const rtcuda_scene_desc* d, const rtcuda_settings* st
                         n_out += cont; n_shadow += has_vertex; n_sray += k;
                         stats[1] += final_skipped;   // reported with the bounce rays: the oracle (like the reference) traces them
                     };
+                    // like launch_shade (kernels.cu): scenes that mix Diffuse with other materials take the Diffuse body first, which
+                    // leaves the other materials on a list for the general body (HOSTSIM_NO_MATERIAL_SPLIT: everything through the general one)
+                    const bool no_split = std::getenv("HOSTSIM_NO_MATERIAL_SPLIT") != nullptr;
+                    const bool split = !sc.all_diffuse && sc.any_diffuse && !no_split;
+                    std::vector<uint32_t> deferred;
+                    const StagePtr no_stage{nullptr, 0u, 0u};
                     for (uint32_t q = 0; q < n_rays; q++) {
                         cur_q = q;
                         if (sc.all_diffuse) shade_vertex<DiffuseSurface>(true, q, sc, rp, w, alloc);
+                        else if (split) shade_vertex<DiffuseSurface, false, true>(true, q, sc, rp, w, alloc, no_stage, [](bool, uint32_t) {}, [](uint32_t&) {},
+                                                                                  [&](uint32_t dq) { deferred.push_back(dq); });
                         else shade_vertex<Surface>(true, q, sc, rp, w, alloc);
+                    }
+                    for (uint32_t q : deferred) {
+                        cur_q = q;
+                        shade_vertex<Surface>(true, q, sc, rp, w, alloc);
                     }
                     uint32_t shadow_rays = 0;
                     std::vector<SimRay> sim;

@@ -299,3 +299,18 @@ def test_reused_mesh_instances(rc, oracle, hostsim):
     assert {len(sc.instances) - 3, len(sc.instances) - 2, len(sc.instances) - 1} <= geoms   # all three instances are seen
     assert stats["primary_rays"] == ostats["primary_rays"]
     assert_beauty_parity(out.beauty, ref.beauty)
+
+
+@pytest.mark.parametrize("name", ["rough_metal", "dielectric"])
+def test_material_split_gives_the_same_frame(rc, hostsim, monkeypatch, name):
+    """mixed materials: the Diffuse shade body first + the general body over the vertices it left (kernels.cu launch_shade) against
+    everything through the general body — the same frame (the Diffuse branches of the two bodies are the same arithmetic)"""
+    t = [t for t in rc.test_scenes.all_test_scenes() if t.name == name][0]
+    sc, st = t.scene_func(), t.settings_func()
+    sc.camera = _small_cornell_camera(rc)
+    st.samples_per_pixel, st.outputs = 4, A.BEAUTY
+    split, s1 = hostsim.render(sc, st)
+    monkeypatch.setenv("HOSTSIM_NO_MATERIAL_SPLIT", "1")
+    single, s2 = hostsim.render(sc, st)
+    assert s1["bounce_rays"] == s2["bounce_rays"] and s1["shadow_rays"] == s2["shadow_rays"]
+    assert np.array_equal(split.beauty, single.beauty, equal_nan=True)

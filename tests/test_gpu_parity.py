@@ -262,6 +262,21 @@ def test_primary_rays_that_miss_the_scene_bounds_are_not_queued(rc, oracle):
     assert estats["primary_rays_culled"] == 0                                # misses light the pixel through the environment map
 
 
+def test_material_split_matches_the_single_launch(rc, monkeypatch):
+    """mixed materials: Diffuse kernel + general kernel over the deferred vertices (launch_shade) against everything through the
+    general kernel (RTCUDA_NO_MATERIAL_SPLIT): same rays, the same frame up to the rounding of two instantiations"""
+    t = [t for t in rc.test_scenes.all_test_scenes() if t.name == "rough_metal"][0]
+    sc, st = t.scene_func(), t.settings_func()
+    st.samples_per_pixel, st.outputs = 16, A.BEAUTY
+    split, s1 = gpu_render(rc, sc, st)
+    monkeypatch.setenv("RTCUDA_NO_MATERIAL_SPLIT", "1")
+    single, s2 = gpu_render(rc, sc, st)
+    assert s1["kernel_launches"] > s2["kernel_launches"]
+    assert abs(s1["bounce_rays"] - s2["bounce_rays"]) <= max(4, s2["bounce_rays"] // 2000)
+    rep = assert_beauty_parity(split.beauty, single.beauty, what="material split", **SPECULAR_GATES)
+    print(f"\n[parity] material split vs single launch: {rep}")
+
+
 def test_reused_mesh_instances(rc, oracle):
     """one mesh under three Transform primitives (glTF mesh reuse, scene/scene.rs:430-443): the flattened world-space tree gives
     the reference's ids / normals / uv / depth and beauty"""

@@ -28,6 +28,16 @@ from .pbrt import scene_from_pbrt_file
 from . import exr, test_scenes
 
 
+def backend_settings_from_args(args) -> CudaBackendSettings:
+    """--gpu N: one device; --devices a,b,c: the multi-device context of ABI v3 (the CLI arm of INTEGRATION.md)"""
+    if getattr(args, "devices", None):
+        ids = [int(x) for x in args.devices.split(",") if x.strip() != ""]
+        if len(ids) > 1:
+            return CudaBackendSettings(num_devices=len(ids), device_ids=ids, tile_size=args.tile_size)
+        return CudaBackendSettings(device_id=ids[0])
+    return CudaBackendSettings(device_id=args.gpu)
+
+
 def build_parser() -> argparse.ArgumentParser:
     p = argparse.ArgumentParser(prog="cli", description="B200 render backend driver (mirror of crates/cli)")
     g = p.add_mutually_exclusive_group()
@@ -45,6 +55,9 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--width", type=int, help="Override the camera raster width")
     p.add_argument("--height", type=int, help="Override the camera raster height")
     p.add_argument("--gpu", type=int, default=0, help="CUDA device")
+    p.add_argument("--devices", help="Comma-separated CUDA devices: one call renders the frame on all of them (tiles dealt inside the "
+                                     "library, rtcuda_backend_settings.num_devices); the planes live on / return from the first one")
+    p.add_argument("--tile-size", type=int, default=0, help="Tile edge of the multi-device deal (0 = 64, the reference's RenderTile)")
     sub = p.add_subparsers(dest="command")
     full = sub.add_parser("full", help="Full frame render with AOV control")
     full.add_argument("--aov", help="Comma-separated AOV list (e.g. normal,uv or n,u)")
@@ -143,7 +156,7 @@ def main(argv=None) -> int:
         strata = int(np.ceil(np.sqrt(np.float32(settings.samples_per_pixel))))
         settings.sampler = Sampler.stratified(True, strata, strata)
 
-    backend = CudaBackendSettings(device_id=args.gpu)
+    backend = backend_settings_from_args(args)
     if args.command == "pixel":
         low = args.sample_offset or 0
         high = low + (args.sample_count if args.sample_count is not None else 1)

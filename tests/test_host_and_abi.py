@@ -164,6 +164,10 @@ def test_cli_argument_surface(rc, capsys):
     p = cli.build_parser().parse_args(["--scene-name", "cube", "pixel", "10", "20", "3", "1"])
     assert (p.x, p.y, p.sample_count, p.sample_offset) == (10, 20, 3, 1)
     assert cli.main([]) == 1 and cli.main(["--scene-name", "cube", "-t", "4", "full"]) == 1
+    m = cli.backend_settings_from_args(cli.build_parser().parse_args(["--scene-name", "cube", "--devices", "0,2,3", "--tile-size", "16", "full"]))
+    assert (m.num_devices, list(m.device_ids)[:3], m.tile_size) == (3, [0, 2, 3], 16)
+    one = cli.backend_settings_from_args(cli.build_parser().parse_args(["--scene-name", "cube", "--gpu", "1", "full"]))
+    assert (one.num_devices, one.device_id) == (0, 1)
 
 
 def test_partition_helpers():
